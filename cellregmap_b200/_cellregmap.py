@@ -1,0 +1,292 @@
+"""Host-side mirror of the reference API (cellregmap/_cellregmap.py) on top of libcrm_b200.
+
+Same names, argument meaning, return shapes and error behaviour as the reference:
+`CellRegMap(y, E, W=None, Ls=None, E1=None, hK=None)` (reference :63), `.scan_interaction` (:317),
+`.scan_association` (:246), `.scan_association_fast` (:284), `run_interaction` (:547),
+`run_association` (:471), `run_association_fast` (:502), `get_L_values` (:533), `lrt_pvalues` (:443),
+`compute_maf` (:589).  Inputs may be numpy arrays or torch tensors (CPU or CUDA); results are numpy
+arrays like the reference's.  All numerics run in the CUDA library; torch only owns device memory
+and streams.
+"""
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+EPS_SMALL = float(np.sqrt(np.finfo(float).eps))
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("cellregmap_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _to_dev(x, device, two_d=False):
+    """asarray(x, float) onto the device as a C-contiguous float64 tensor."""
+    if isinstance(x, torch.Tensor):
+        t = x.to(device=device, dtype=torch.float64)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(device)
+    if two_d and t.ndim == 1:
+        t = t.reshape(-1, 1)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _economic_svd(E):
+    """numpy_sugar.linalg.economic_svd on a torch tensor: thin SVD, singular values >= sqrt(eps)."""
+    U, S, Vh = torch.linalg.svd(E, full_matrices=False)
+    keep = S >= EPS_SMALL
+    return U[:, keep], S[keep], Vh[keep, :]
+
+
+def _L_concat(hK, E):
+    """[L_1 | ... | L_k] with L_i = diag(U_i S_i) hK  (reference get_L_values, :533-545), one device tensor."""
+    U, S, _ = _economic_svd(E)
+    us = U * S
+    n = hK.shape[0]
+    return (us[:, :, None] * hK[:, None, :]).reshape(n, us.shape[1] * hK.shape[1]).contiguous()
+
+
+def get_L_values(hK, E):
+    """List of L_i such that K o EE' = sum_i L_i L_i' (reference :533-545); numpy in, numpy out."""
+    E = np.asarray(E, float)
+    hK = np.asarray(hK, float)
+    U, S, _ = np.linalg.svd(E, full_matrices=False)
+    keep = S >= EPS_SMALL
+    us = U[:, keep] * S[keep]
+    return [us[:, i][:, None] * hK for i in range(us.shape[1])]
+
+
+class _Genotypes:
+    """Genotype matrix handed to the library: device tensor, or host memory streamed in column blocks."""
+
+    def __init__(self, G, device, n):
+        if isinstance(G, torch.Tensor) and G.is_cuda:
+            G = G.to(device=device, dtype=torch.float64)
+            if G.ndim != 2 or G.stride(1) != 1 or G.stride(0) < G.shape[1]:
+                G = G.contiguous()
+            self.keep, self.on_host = G, 0
+            self.ptr, self.ld = G.data_ptr(), G.stride(0) if G.shape[0] > 1 else G.shape[1]
+        else:
+            if isinstance(G, torch.Tensor):
+                G = G.to(dtype=torch.float64)
+                if G.ndim != 2 or not G.is_contiguous():
+                    G = G.contiguous()
+                self.ptr = G.data_ptr()
+            else:
+                G = np.ascontiguousarray(np.asarray(G, dtype=np.float64))
+                self.ptr = G.ctypes.data
+            self.keep, self.on_host = G, 1
+            self.ld = G.shape[1] if G.ndim == 2 else 1
+        assert G.ndim == 2, "G must be n x p"
+        assert G.shape[0] == n, "G must have one row per sample"
+        self.p = int(G.shape[1])
+
+
+class CellRegMap:
+    """Mixed model with genetic-effect heterogeneity across cellular contexts (reference :23-440).
+
+        y = W a + g b1 + g.b2 + e + u + eps,   b2 ~ N(0, v3 E0 E0'),  e ~ N(0, v1 rho1 E1 E1'),
+        u ~ N(0, v1 (1-rho1) K o E2 E2'),  eps ~ N(0, v2 I)
+    """
+
+    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None, device=None):
+        self._device = _device(device)
+        dev = self._device
+        self._y = _to_dev(y, dev).flatten()
+        self._E0 = _to_dev(E, dev)
+        n = self._y.shape[0]
+        Ls = [] if Ls is None else Ls
+        self._W = _to_dev(W, dev) if W is not None else torch.ones((n, 1), dtype=torch.float64, device=dev)
+        self._E1 = _to_dev(E1, dev) if E1 is not None else self._E0
+        if isinstance(Ls, torch.Tensor):      # pre-concatenated [L_1 | ... | L_k]
+            Lcat = _to_dev(Ls, dev)
+            n_blocks = 1
+        else:
+            blocks = [_to_dev(L, dev) for L in Ls]
+            for L in blocks:
+                assert L.ndim == 2
+                assert n == L.shape[0]
+            n_blocks = len(blocks)
+            Lcat = torch.cat(blocks, dim=1).contiguous() if n_blocks else None
+        assert self._W.ndim == 2
+        assert self._E0.ndim == 2
+        assert self._E1.ndim == 2
+        assert n == self._W.shape[0]
+        assert n == self._E0.shape[0]
+        assert n == self._E1.shape[0]
+        if n_blocks == 0:
+            if hK is None:
+                self._rho1 = [1.0]                       # reference :103-106
+            else:
+                Lcat = _to_dev(hK, dev, two_d=True)      # reference :107-116
+                assert Lcat.shape[0] == n
+                self._rho1 = np.linspace(0, 1, 11)
+        else:
+            self._rho1 = np.linspace(0, 1, 11)           # reference :117-131 (hK ignored)
+        self._L = Lcat
+        self._handle = ctypes.c_void_p(0)
+        torch.cuda.set_device(dev)
+        _lib.call("crm_create", ctypes.byref(self._handle), dev.index if dev.index is not None else torch.cuda.current_device())
+        rho = np.ascontiguousarray(np.asarray(self._rho1, dtype=np.float64))
+        mL = 0 if Lcat is None else int(Lcat.shape[1])
+        _lib.call("crm_setup", self._handle, _ptr(self._y), _ptr(self._W), self._W.stride(0), _ptr(self._E0),
+                  self._E0.stride(0), _ptr(self._E1), self._E1.stride(0), _ptr(Lcat), 0 if Lcat is None else Lcat.stride(0),
+                  n, int(self._W.shape[1]), int(self._E0.shape[1]), int(self._E1.shape[1]), mL,
+                  rho.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(rho.shape[0]), _stream())
+        dims = (ctypes.c_int64 * 7)()
+        _lib.call("crm_get_dims", self._handle, dims)
+        self._dims = {"n": dims[0], "c": dims[1], "k0": dims[2], "m": dims[3], "R": dims[4], "mp": dims[5], "max_rank": dims[6]}
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.load().crm_destroy(h)
+            except Exception:
+                pass
+            self._handle = ctypes.c_void_p(0)
+
+    @property
+    def n_samples(self):
+        return int(self._y.shape[0])
+
+    # ------------------------------------------------------------------------------------------
+    def _scan_interaction_device(self, G, idx_E=None, idx_G=None, diagnostics=False, overrides=None):
+        dev = self._device
+        torch.cuda.set_device(dev)
+        geno = _Genotypes(G, dev, self.n_samples)
+        p, R, k = geno.p, len(self._rho1), int(self._E0.shape[1])
+        out = {name: torch.empty(p, dtype=torch.float64, device=dev) for name in ("pv", "rho1", "e2", "g2", "eps2")}
+        diag = _lib.ScanDiag()
+        extra = {}
+        extra["flags"] = torch.zeros(p, dtype=torch.int32, device=dev)
+        diag.flags = extra["flags"].data_ptr()
+        if diagnostics:
+            extra.update(
+                lml=torch.empty((p, R), dtype=torch.float64, device=dev), delta=torch.empty((p, R), dtype=torch.float64, device=dev),
+                scale=torch.empty((p, R), dtype=torch.float64, device=dev), Q=torch.empty(p, dtype=torch.float64, device=dev),
+                lam=torch.empty((p, k), dtype=torch.float64, device=dev), nlam=torch.empty(p, dtype=torch.int32, device=dev),
+                M=torch.empty((p, k, k), dtype=torch.float64, device=dev), liu=torch.empty(p, dtype=torch.float64, device=dev),
+                ifault=torch.empty(p, dtype=torch.int32, device=dev), nfev=torch.empty((p, R), dtype=torch.int32, device=dev))
+            for name in ("lml", "delta", "scale", "Q", "lam", "nlam", "M", "liu", "ifault", "nfev"):
+                setattr(diag, name, extra[name].data_ptr())
+        keep = []
+        if overrides is not None:
+            ridx = torch.as_tensor(np.asarray(overrides["rho_idx"]), dtype=torch.int32, device=dev).contiguous()
+            ov0 = _to_dev(overrides["v0"], dev)
+            ov1 = _to_dev(overrides["v1"], dev)
+            keep += [ridx, ov0, ov1]
+            diag.ov_rho_idx, diag.ov_v0, diag.ov_v1 = ridx.data_ptr(), ov0.data_ptr(), ov1.data_ptr()
+        if idx_G is not None:
+            raise NotImplementedError("scan_interaction(idx_G=...) (permuted tested genotypes) is not available yet")
+        if idx_E is not None:      # row-permuted contexts in the tested design only (reference :398-401)
+            idx = torch.as_tensor(np.asarray(idx_E), device=dev)
+            Etest = self._E0[idx, :].contiguous()
+            _lib.call("crm_set_test_contexts", self._handle, _ptr(Etest), Etest.stride(0), _stream())
+        try:
+            _lib.call("crm_scan_interaction", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, p, geno.on_host,
+                      ctypes.c_void_p(0), 0, _ptr(out["pv"]), _ptr(out["rho1"]), _ptr(out["e2"]), _ptr(out["g2"]),
+                      _ptr(out["eps2"]), ctypes.byref(diag), _stream())
+        finally:
+            if idx_E is not None:
+                _lib.call("crm_set_test_contexts", self._handle, _ptr(self._E0), self._E0.stride(0), _stream())
+        out.update(extra)
+        return out
+
+    def scan_interaction(self, G, idx_E: Optional[any] = None, idx_G: Optional[any] = None):
+        """Score test of H0: v3 = 0 for every column of G (reference :317-440).
+        Returns (pvalues (p,), {"rho1", "e2", "g2", "eps2": (p,)})."""
+        out = self._scan_interaction_device(G, idx_E, idx_G)
+        flags = out["flags"].cpu().numpy()
+        if np.any(flags & 1):
+            raise RuntimeError("No eigenvalue is bigger than 0!!")
+        if np.any(flags & 4):
+            raise ValueError("The determinant of H should be positive.")
+        info = {key: out[key].cpu().numpy() for key in ("rho1", "e2", "g2", "eps2")}
+        return out["pv"].cpu().numpy(), info
+
+    def _scan_association(self, G, fast):
+        dev = self._device
+        torch.cuda.set_device(dev)
+        geno = _Genotypes(G, dev, self.n_samples)
+        pv = torch.empty(geno.p, dtype=torch.float64, device=dev)
+        alt = torch.empty(geno.p, dtype=torch.float64, device=dev)
+        info4 = torch.empty(4, dtype=torch.float64, device=dev)
+        null = torch.empty(1, dtype=torch.float64, device=dev)
+        _lib.call("crm_scan_association", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, geno.p, geno.on_host,
+                  1 if fast else 0, _ptr(pv), _ptr(alt), _ptr(info4), _ptr(null), _stream())
+        i4 = info4.cpu().numpy()
+        info = {"rho1": i4[0:1].copy(), "e2": i4[1:2].copy(), "g2": i4[2:3].copy(), "eps2": i4[3:4].copy()}
+        self._last_association = {"alt_lml": alt, "null_lml": null}
+        return pv.cpu().numpy(), info
+
+    def scan_association(self, G):
+        """LRT for a persistent effect of every column of G (reference :246-281)."""
+        return self._scan_association(G, fast=False)
+
+    def scan_association_fast(self, G):
+        """Same with delta frozen at the null fit (reference :284-314)."""
+        return self._scan_association(G, fast=True)
+
+
+def lrt_pvalues(null_lml, alt_lmls, dof=1):
+    """Likelihood-ratio p-values (reference :443-469)."""
+    if dof != 1:
+        raise NotImplementedError("only dof=1 is used by the reference path")
+    dev = _device()
+    alt = _to_dev(np.atleast_1d(np.asarray(alt_lmls, float)), dev)
+    pv = torch.empty_like(alt)
+    _lib.call("crm_lrt_pvalues", _ptr(alt), float(null_lml), alt.numel(), _ptr(pv), _stream())
+    return pv.cpu().numpy()
+
+
+def run_association(y, W, E, G, hK=None):
+    """Association test (reference :471-500).  NB the reference passes (y, W, E) positionally to
+    CellRegMap(y, E, W): W becomes the context/background matrix and E the covariates; kept."""
+    crm = CellRegMap(y, W, E, hK=hK)
+    return crm.scan_association(G)
+
+
+def run_association_fast(y, W, E, G, hK=None):
+    """Fast association test (reference :502-531); same positional quirk as run_association."""
+    crm = CellRegMap(y, W, E, hK=hK)
+    return crm.scan_association_fast(G)
+
+
+def _make_interaction_model(y, E, W, E1, E2, hK, device=None):
+    dev = _device(device)
+    E1 = E if E1 is None else E1
+    E2 = E if E2 is None else E2
+    Ls = None if hK is None else _L_concat(_to_dev(hK, dev, two_d=True), _to_dev(E2, dev))
+    return CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev)
+
+
+def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None):
+    """Interaction test (reference :547-587).  NB `idx_G` is forwarded as scan_interaction's second
+    positional argument, i.e. it permutes the rows of E (reference :586); kept."""
+    crm = _make_interaction_model(y, E, W, E1, E2, hK)
+    return crm.scan_interaction(G, idx_G)
+
+
+def compute_maf(X):
+    """Minor allele frequencies of dosage columns, NaN = missing (numpy branch of reference :589-638)."""
+    if isinstance(X, torch.Tensor):
+        X = X.detach().cpu().numpy()
+    X = np.asarray(X, float)
+    s0 = np.nansum(X, axis=0) / (2 * np.logical_not(np.isnan(X)).sum(axis=0))
+    return np.minimum(s0, 1 - s0)

@@ -1,0 +1,93 @@
+"""ctypes binding of libcrm_b200.so (C ABI declared in include/crm_b200.h).
+
+There is no CPU fallback: if the library is missing or cannot be loaded the import of the
+compute entry points raises, and every call checks the status code and raises CrmError."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcrm_b200.so")
+
+c_double_p = ctypes.c_void_p  # device / host addresses are passed as integers
+c_int32_p = ctypes.c_void_p
+
+
+class CrmError(RuntimeError):
+    """A call into libcrm_b200 returned a non-zero status."""
+
+    def __init__(self, status, message):
+        super().__init__(f"libcrm_b200 status {status}: {message}")
+        self.status = status
+
+
+class ScanDiag(ctypes.Structure):
+    """crm_scan_diag_t"""
+    _fields_ = [(name, ctypes.c_void_p) for name in (
+        "lml", "delta", "scale", "Q", "lam", "nlam", "M", "liu", "ifault", "flags", "nfev",
+        "ov_rho_idx", "ov_v0", "ov_v1")]
+
+
+# name -> (restype, argtypes); every symbol declared in include/crm_b200.h
+SIGNATURES = {
+    "crm_version": (ctypes.c_int, []),
+    "crm_last_error": (ctypes.c_char_p, []),
+    "crm_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "crm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "crm_setup": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int64,
+                                 c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_double), ctypes.c_int,
+                                 ctypes.c_void_p]),
+    "crm_set_test_contexts": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_void_p]),
+    "crm_get_dims": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    "crm_get_spectrum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_void_p]),
+    "crm_scan_interaction": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                            c_double_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
+                                            c_double_p, ctypes.POINTER(ScanDiag), ctypes.c_void_p]),
+    "crm_scan_association": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                            ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, ctypes.c_void_p]),
+    "crm_launch_count": (ctypes.c_longlong, []),
+    "crm_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                   ctypes.POINTER(ctypes.c_int64)]),
+    "crm_gemm": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64,
+                                ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                ctypes.c_int, ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int,
+                                ctypes.c_void_p]),
+    "crm_lmm_fit_rotated": (ctypes.c_int, [c_double_p] * 8 + [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                              ctypes.c_int64, ctypes.c_double, ctypes.c_int, c_double_p,
+                                                              c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p,
+                                                              ctypes.c_void_p]),
+    "crm_davies_pvalues": (ctypes.c_int, [c_double_p, c_double_p, c_int32_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
+                                          ctypes.c_double, c_double_p, c_double_p, c_int32_p, c_int32_p, c_double_p,
+                                          ctypes.c_void_p]),
+    "crm_lrt_pvalues": (ctypes.c_int, [c_double_p, ctypes.c_double, ctypes.c_int64, c_double_p, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (built in-tree by cellregmap_b200.build) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m cellregmap_b200.build` "
+            "(cellregmap_b200 has no CPU or PyTorch fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header drift apart
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().crm_last_error()
+        raise CrmError(status, msg.decode("utf-8", "replace") if msg else "")
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,751 @@
+// libcrm_b200.so -- C ABI (include/crm_b200.h) over the sm_100a kernels of this directory.
+// Host orchestration only: set-up of the per-gene state, batching of SNPs, kernel launches.
+#include <cusolverDn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "../../include/crm_b200.h"
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace crm {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define CRM_SOLVER(expr)                                                                     \
+    do {                                                                                     \
+        cusolverStatus_t _s = (expr);                                                        \
+        if (_s != CUSOLVER_STATUS_SUCCESS) {                                                 \
+            crm::set_error("%s failed with cusolverStatus %d (%s:%d)", #expr, (int)_s, __FILE__, __LINE__); \
+            return crm::CRM_ERR_SOLVER;                                                      \
+        }                                                                                    \
+    } while (0)
+
+static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+// grow-only device buffer
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return CRM_OK;
+        if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); ptr = nullptr; return CRM_ERR_CUDA; }
+        cap = bytes;
+        return CRM_OK;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+struct Handle {
+    int device = 0;
+    bool ready = false;
+    long long n = 0;
+    int c = 0, k0 = 0, k1 = 0, R = 0;
+    long long mL = 0;
+    int m = 0, mp = 0, Mx = 0, ldH = 0, kexp = 0, epitch = 0, M2 = 0, ld2 = 0, max_rank = 0;
+    std::vector<double> rho;
+    // per-gene state
+    DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
+    // null-model state for the association scans
+    // scan workspaces
+    DevBuf C, sq, Hg, gr, Vg, GEr, fit_lml, fit_delta, fit_scale, fit_beta, fit_x, fit_nfev, fit_flags;
+    DevBuf rho_idx, best_lml, v0, v1, perm, offsets, Q, lam, nlam, sflags, liu, ifault, conv, gchunk[2], gtchunk[2], scratch;
+    cusolverDnHandle_t solver = nullptr;
+    // optional timing of the rotation kernel (K1, EXPAND mode) with events on the launching stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_events;
+    double prof_flops = 0.0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    void free_all() {
+        DevBuf* all[] = {&Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
+                         &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
+                         &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
+                         &gtchunk[0], &gtchunk[1], &scratch};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// small set-up kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void build_eext_kernel(const double* E0, long long lde0, long long n, int k0, double* Eext, int epitch) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * epitch) return;
+    const long long i = idx / epitch; const int j = (int)(idx - i * epitch);
+    Eext[idx] = (j == 0) ? 1.0 : (j <= k0 ? E0[i * lde0 + (j - 1)] : 0.0);
+}
+// A2 = [1 | E0 | E0_j * E0_l (j >= l, packed)]
+__global__ void build_a2_kernel(const double* E0, long long lde0, long long n, int k0, double* A2, int ld2) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * ld2) return;
+    const long long i = idx / ld2; const int col = (int)(idx - i * ld2);
+    const int npair = k0 * (k0 + 1) / 2;
+    double v = 0.0;
+    if (col == 0) v = 1.0;
+    else if (col <= k0) v = E0[i * lde0 + (col - 1)];
+    else if (col < 1 + k0 + npair) {
+        const int e = col - 1 - k0;
+        int j = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (j * (j + 1) / 2 > e) j--;
+        while ((j + 1) * (j + 2) / 2 <= e) j++;
+        const int l = e - j * (j + 1) / 2;
+        v = E0[i * lde0 + j] * E0[i * lde0 + l];
+    }
+    A2[idx] = v;
+}
+// C_rho = D^(1/2) (H'H) D^(1/2), D = diag(rho I_k1, (1-rho) I)
+__global__ void scale_gram_kernel(const double* gram, int ldg, int m, int k1, double rho, double* out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * m) return;
+    const int a = idx / m, b = idx - a * m;
+    const double da = a < k1 ? sqrt(rho) : sqrt(1.0 - rho), db = b < k1 ? sqrt(rho) : sqrt(1.0 - rho);
+    out[idx] = da * db * gram[(long long)a * ldg + b];
+}
+// eigenpairs (ascending, eigenvector i in row i of V) -> S[i], Tt[a][rho*mp + i] = d_a V[i][a] / sqrt(S_i)
+__global__ void build_basis_kernel(const double* V, const double* ev, int m, int mp, int k1, double rho, int tall,
+                                   double* S, double* Tt, long long ldt, int rho_index, int* rank_out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const double evmax = ev[m - 1];
+    const double thr_rel = 1e-12 * evmax;
+    if (idx < mp) {
+        double s = 0.0;
+        if (idx < m) { const double e = ev[idx]; const bool keep = (e > thr_rel) && (tall || e >= CRM_EPS_SMALL) && e > 0.0; s = keep ? e : 0.0; }
+        S[idx] = s;
+    }
+    if (idx == 0) { int r = 0; for (int i = 0; i < m; i++) { const double e = ev[i]; if ((e > thr_rel) && (tall || e >= CRM_EPS_SMALL) && e > 0.0) r++; } rank_out[rho_index] = r; }
+    for (long long t = idx; t < (long long)m * mp; t += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(t / mp), i = (int)(t - (long long)a * mp);
+        double v = 0.0;
+        if (i < m) {
+            const double e = ev[i];
+            const bool keep = (e > thr_rel) && (tall || e >= CRM_EPS_SMALL) && e > 0.0;
+            if (keep) { const double da = a < k1 ? sqrt(rho) : sqrt(1.0 - rho); v = da * V[(long long)i * m + a] / sqrt(e); }
+        }
+        Tt[(long long)a * ldt + (long long)rho_index * mp + i] = v;
+    }
+}
+// yr[rho][i] = sum_a Tt[a][rho*mp+i] gram[a][m],  Wr[rho][cc][i] likewise with gram[a][m+1+cc]
+__global__ void rotate_null_kernel(const double* Tt, long long ldt, const double* gram, int ldg, int m, int mp, int R, int c,
+                                   double* yr, double* Wr) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)R * mp) return;
+    const int rho = (int)(idx / mp), i = (int)(idx - (long long)rho * mp);
+    for (int col = 0; col <= c; col++) {
+        double s = 0.0;
+        for (int a = 0; a < m; a++) s += Tt[(long long)a * ldt + idx] * gram[(long long)a * ldg + m + col];
+        if (col == 0) yr[idx] = s; else Wr[((long long)rho * c + (col - 1)) * mp + i] = s;
+    }
+}
+__global__ void extract_stats_kernel(const double* gram, int ldg, int m, int c, double* stats) {
+    const int t = threadIdx.x;
+    if (t == 0) stats[0] = gram[(long long)m * ldg + m];
+    if (t < c) stats[1 + t] = gram[(long long)m * ldg + m + 1 + t];
+    if (t < c * c) { const int a = t / c, b = t - a * c; stats[1 + c + t] = gram[(long long)(m + 1 + a) * ldg + m + 1 + b]; }
+}
+__global__ void finalize_interaction_kernel(const int* rho_idx, const double* v0, const double* v1, const double* grid, long long p,
+                                            double* rho1, double* e2, double* g2, double* eps2) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p) return;
+    const double r = grid[rho_idx[s]];
+    rho1[s] = r; e2[s] = v0[s] * r; g2[s] = v0[s] * (1.0 - r); eps2[s] = v1[s];
+}
+__global__ void override_select_kernel(const int* ov_idx, const double* ov_v0, const double* ov_v1, long long p, int* rho_idx, double* v0, double* v1) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p) return;
+    if (ov_idx) rho_idx[s] = ov_idx[s];
+    if (ov_v0) v0[s] = ov_v0[s];
+    if (ov_v1) v1[s] = ov_v1[s];
+}
+__global__ void or_flags_kernel(const int* fit_flags, const int* rho_idx, const int* sflags, int R, long long p, int* out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p) return;
+    const int f = fit_flags[s * R + rho_idx[s]];
+    out[s] = (sflags[s] & 1) | ((f & 1) << 1) | ((f & 2) << 1);
+}
+__global__ void copy_strided_kernel(const double* src, long long src_ld, long long rows, int cols, double* dst, long long dst_ld) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const long long r = idx / cols; const int cidx = (int)(idx - r * cols);
+    dst[r * dst_ld + cidx] = src[r * src_ld + cidx];
+}
+
+static inline unsigned blocks_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------
+// set-up
+// ------------------------------------------------------------------------------------------------
+static int build_test_contexts(Handle* h, const double* E0, long long lde0, cudaStream_t st) {
+    build_eext_kernel<<<blocks_for(h->n * h->epitch, 256), 256, 0, st>>>(E0, lde0, h->n, h->k0, h->Eext.as<double>(), h->epitch);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    build_a2_kernel<<<blocks_for(h->n * h->ld2, 256), 256, 0, st>>>(E0, lde0, h->n, h->k0, h->A2.as<double>(), h->ld2);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
+static int do_setup(Handle* h, const double* y, const double* W, long long ldw, const double* E0, long long lde0, const double* E1,
+                    long long lde1, const double* L, long long ldl, long long n, int c, int k0, int k1, long long mL,
+                    const double* rho_host, int R, cudaStream_t st) {
+    if (!y || !W || !E0 || !E1 || n <= 0 || c <= 0 || k0 <= 0 || k1 <= 0 || mL < 0 || R <= 0 || (mL > 0 && !L)) { set_error("crm_setup: bad arguments"); return CRM_ERR_INVALID; }
+    if (n > 2000000000LL) { set_error("n too large"); return CRM_ERR_UNSUPPORTED; }
+    if (c > 7) { set_error("at most 7 covariate columns are supported (got %d)", c); return CRM_ERR_UNSUPPORTED; }
+    if (R > 64) { set_error("rho grid too long"); return CRM_ERR_UNSUPPORTED; }
+    if (k1 + mL > 30000) { set_error("background half-covariance has %lld columns; limit is 30000", (long long)(k1 + mL)); return CRM_ERR_UNSUPPORTED; }
+    h->ready = false;
+    h->n = n; h->c = c; h->k0 = k0; h->k1 = k1; h->mL = mL; h->R = R;
+    h->m = (int)(k1 + mL);
+    h->mp = (int)round_up(h->m, 2);
+    h->Mx = h->m + 1 + c;
+    h->ldH = (int)round_up(h->Mx, 2);
+    h->kexp = 1 + k0;
+    {   // Eext pitch: >= kexp + 1 (zero column), {0,p,2p,3p} mod 16 spaced by >= 4
+        int pch = (h->kexp + 2) & ~1;
+        while (!(pch % 16 == 4 || pch % 16 == 12)) pch += 2;
+        h->epitch = pch;
+    }
+    h->M2 = 1 + k0 + k0 * (k0 + 1) / 2;
+    h->ld2 = (int)round_up(h->M2, 2);
+    h->rho.assign(rho_host, rho_host + R);
+    const int m = h->m, mp = h->mp, Mx = h->Mx, ldH = h->ldH;
+
+    CRM_CHECK(h->Hx.reserve((size_t)n * ldH * 8));
+    CRM_CHECK(h->Eext.reserve((size_t)n * h->epitch * 8));
+    CRM_CHECK(h->A2.reserve((size_t)n * h->ld2 * 8));
+    CRM_CHECK(h->gram.reserve((size_t)ldH * ldH * 8));
+    CRM_CHECK(h->S.reserve((size_t)R * mp * 8));
+    CRM_CHECK(h->yr.reserve((size_t)R * mp * 8));
+    CRM_CHECK(h->Wr.reserve((size_t)R * c * mp * 8));
+    CRM_CHECK(h->Tt.reserve((size_t)m * R * mp * 8));
+    CRM_CHECK(h->stats.reserve((size_t)(1 + c + c * c + R + 4) * 8));
+    CRM_CHECK(h->eigmat.reserve((size_t)m * m * 8));
+    CRM_CHECK(h->eigval.reserve((size_t)m * 8));
+    CRM_CHECK(h->devinfo.reserve((size_t)(R + 8) * sizeof(int)));
+
+    // Hx = [E1 | L | y | W]
+    double* Hx = h->Hx.as<double>();
+    CRM_CUDA(cudaMemsetAsync(Hx, 0, (size_t)n * ldH * 8, st));
+    CRM_CUDA(cudaMemcpy2DAsync(Hx, (size_t)ldH * 8, E1, (size_t)lde1 * 8, (size_t)k1 * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (mL > 0) CRM_CUDA(cudaMemcpy2DAsync(Hx + k1, (size_t)ldH * 8, L, (size_t)ldl * 8, (size_t)mL * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    CRM_CUDA(cudaMemcpy2DAsync(Hx + m, (size_t)ldH * 8, y, 8, 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    CRM_CUDA(cudaMemcpy2DAsync(Hx + m + 1, (size_t)ldH * 8, W, (size_t)ldw * 8, (size_t)c * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    CRM_CHECK(build_test_contexts(h, E0, lde0, st));
+
+    // Gram of [H | y | W] by the K1 kernel (plain mode): H'H, H'y, H'W, y'y, W'y, W'W
+    GemmOperands op{};
+    op.A = Hx; op.lda = ldH; op.a_cols = Mx;
+    op.B = Hx; op.ldb = ldH; op.b_cols = Mx;
+    op.B2 = Hx; op.ldb2 = ldH; op.b2_cols = Mx;
+    CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)n, 0, Mx, 0, Mx, h->gram.as<double>(), ldH, 1, st));
+    extract_stats_kernel<<<1, 64, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+
+    // per-rho eigendecomposition (cuSOLVER, one-off per gene)
+    if (!h->solver) CRM_SOLVER(cusolverDnCreate(&h->solver));
+    CRM_SOLVER(cusolverDnSetStream(h->solver, st));
+    int lwork = 0;
+    CRM_SOLVER(cusolverDnDsyevd_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, h->eigmat.as<double>(), m,
+                                          h->eigval.as<double>(), &lwork));
+    CRM_CHECK(h->eigwork.reserve((size_t)lwork * 8));
+    int* rank_dev = h->devinfo.as<int>() + 4;
+    const int tall = n > m ? 1 : 0;
+    for (int r = 0; r < R; r++) {
+        scale_gram_kernel<<<blocks_for((long long)m * m, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, m, k1, h->rho[r], h->eigmat.as<double>());
+        CRM_CUDA(cudaGetLastError()); count_launch();
+        CRM_SOLVER(cusolverDnDsyevd(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, h->eigmat.as<double>(), m,
+                                    h->eigval.as<double>(), h->eigwork.as<double>(), lwork, h->devinfo.as<int>()));
+        build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
+            h->eigmat.as<double>(), h->eigval.as<double>(), m, mp, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
+            h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
+        CRM_CUDA(cudaGetLastError()); count_launch();
+    }
+    rotate_null_kernel<<<blocks_for((long long)R * mp, 128), 128, 0, st>>>(h->Tt.as<double>(), (long long)R * mp, h->gram.as<double>(), ldH, m,
+                                                                         mp, R, c, h->yr.as<double>(), h->Wr.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    std::vector<int> info(R + 8, 0);
+    CRM_CUDA(cudaMemcpyAsync(info.data(), h->devinfo.as<int>(), (size_t)(R + 4) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaStreamSynchronize(st));
+    if (info[0] != 0) { set_error("cusolverDnDsyevd did not converge (devInfo=%d)", info[0]); return CRM_ERR_SOLVER; }
+    h->max_rank = 0;
+    for (int r = 0; r < R; r++) h->max_rank = std::max(h->max_rank, info[4 + r]);
+    h->ready = true;
+    return CRM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// interaction scan
+// ------------------------------------------------------------------------------------------------
+struct BatchPlan { long long batch; };
+
+static long long pick_batch(const Handle* h, long long p, bool interaction) {
+    // bytes of workspace per SNP
+    const double per_snp = interaction
+        ? 8.0 * ((double)h->kexp * h->ldH + h->ld2 + (double)h->R * h->mp + 2.0 * (double)h->k0 * h->mp + h->m)
+        : 8.0 * ((double)h->ldH + 2.0 * h->mp + h->m);
+    long long b = (long long)(6.0e9 / per_snp);
+    b = std::max(64LL, std::min(b, p));
+    b = std::min(b, (long long)(65535LL * GEMM_TILE_N / h->kexp));
+    return b;
+}
+
+static int reserve_scan(Handle* h, long long B, bool interaction) {
+    const int R = h->R, mp = h->mp, m = h->m, k = h->k0;
+    if (interaction) {
+        CRM_CHECK(h->C.reserve((size_t)B * h->kexp * h->ldH * 8));
+        CRM_CHECK(h->sq.reserve((size_t)B * h->ld2 * 8));
+        CRM_CHECK(h->gr.reserve((size_t)B * R * mp * 8));
+        CRM_CHECK(h->Vg.reserve((size_t)m * round_up(B * k, 2) * 8));
+        CRM_CHECK(h->GEr.reserve((size_t)B * k * mp * 8));
+        CRM_CHECK(h->lam.reserve((size_t)B * k * 8));
+    } else {
+        CRM_CHECK(h->C.reserve((size_t)B * h->ldH * 8));
+        CRM_CHECK(h->sq.reserve((size_t)B * 2 * 8));
+        CRM_CHECK(h->gr.reserve((size_t)B * mp * 8));
+    }
+    CRM_CHECK(h->Hg.reserve((size_t)m * round_up(B, 2) * 8));
+    const size_t pr = (size_t)B * R;
+    CRM_CHECK(h->fit_lml.reserve(pr * 8)); CRM_CHECK(h->fit_delta.reserve(pr * 8)); CRM_CHECK(h->fit_scale.reserve(pr * 8));
+    CRM_CHECK(h->fit_beta.reserve(pr * 8 * 8)); CRM_CHECK(h->fit_x.reserve(pr * 8));
+    CRM_CHECK(h->fit_nfev.reserve(pr * 4)); CRM_CHECK(h->fit_flags.reserve(pr * 4));
+    CRM_CHECK(h->rho_idx.reserve((size_t)B * 4)); CRM_CHECK(h->best_lml.reserve((size_t)B * 8));
+    CRM_CHECK(h->v0.reserve((size_t)B * 8)); CRM_CHECK(h->v1.reserve((size_t)B * 8));
+    CRM_CHECK(h->perm.reserve((size_t)B * 4)); CRM_CHECK(h->offsets.reserve((size_t)(R + 1) * 4));
+    CRM_CHECK(h->Q.reserve((size_t)B * 8)); CRM_CHECK(h->nlam.reserve((size_t)B * 4)); CRM_CHECK(h->sflags.reserve((size_t)B * 4));
+    CRM_CHECK(h->liu.reserve((size_t)B * 8)); CRM_CHECK(h->ifault.reserve((size_t)B * 4)); CRM_CHECK(h->conv.reserve((size_t)B * 4));
+    CRM_CHECK(h->scratch.reserve((size_t)(h->rho.size() + 16) * 8));
+    return CRM_OK;
+}
+
+static int ensure_streams(Handle* h) {
+    if (!h->copy_stream) {
+        CRM_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CRM_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+            CRM_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    return CRM_OK;
+}
+
+// Stage a column block [s0, s0+B) of a host matrix into a device chunk buffer (ld = Bp) on the copy stream.
+static int stage_host_block(Handle* h, const double* G, long long ldg, long long s0, long long B, long long Bp, DevBuf& buf, int slot,
+                            cudaStream_t compute) {
+    CRM_CHECK(buf.reserve((size_t)h->n * Bp * 8));
+    CRM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // previous consumer of this slot
+    CRM_CUDA(cudaMemcpy2DAsync(buf.ptr, (size_t)Bp * 8, G + s0, (size_t)ldg * 8, (size_t)B * 8, (size_t)h->n, cudaMemcpyHostToDevice, h->copy_stream));
+    CRM_CUDA(cudaEventRecord(h->ev_copy[slot], h->copy_stream));
+    (void)compute;
+    return CRM_OK;
+}
+
+static int interaction_batch(Handle* h, const double* Gd, long long ldg, long long gcols, const double* Gt, long long ldgt, long long B,
+                             double* out_pv, double* out_rho1, double* out_e2, double* out_g2, double* out_eps2,
+                             const crm_scan_diag_t* dg, long long s0, cudaStream_t st) {
+    const int R = h->R, mp = h->mp, m = h->m, k = h->k0, kexp = h->kexp, c = h->c, ldH = h->ldH, Mx = h->Mx;
+    double* C = h->C.as<double>();
+    double* sq = h->sq.as<double>();
+    // 1. rotation of [g, g.E0] onto [H | y | W]
+    {
+        GemmOperands op{};
+        op.A = h->Hx.as<double>(); op.lda = ldH; op.a_cols = Mx;
+        op.B = Gt ? Gt : Gd; op.ldb = Gt ? ldgt : ldg; op.b_cols = gcols;
+        op.B2 = h->Eext.as<double>(); op.ldb2 = h->epitch; op.b2_cols = h->epitch;
+        if (h->prof_on) {
+            cudaEvent_t e0, e1;
+            CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
+            CRM_CUDA(cudaEventRecord(e0, st));
+            h->prof_events.push_back(e0); h->prof_events.push_back(e1);
+            h->prof_flops += 2.0 * (double)h->n * (double)h->m * (double)kexp * (double)B;   // algorithmic: 2 n m (1+k) per SNP
+        }
+        CRM_CHECK(launch_gemm(GEMM_EXPAND, op, (int)h->n, 0, Mx, 0, (int)(B * kexp), C, ldH, kexp, st));
+        if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_events.back(), st));
+    }
+    // 2. squared-genotype Grams against [1 | E0 | pairs]:  g'g, (g.E0)'g, (g.E0)'(g.E0)
+    {
+        GemmOperands op{};
+        op.A = h->A2.as<double>(); op.lda = h->ld2; op.a_cols = h->M2;
+        op.B = Gt ? Gt : Gd; op.ldb = Gt ? ldgt : ldg; op.b_cols = gcols;
+        op.B2 = op.B; op.ldb2 = op.ldb; op.b2_cols = gcols;
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, op, (int)h->n, 0, h->M2, 0, (int)B, sq, h->ld2, 1, st));
+    }
+    if (Gt) {
+        // permuted tested genotypes: the null design still uses g itself -> overwrite row j=0 of C with the rotation of g,
+        // column 0 of sq with g'g and the (g.E0)'g block with (gt * g)' E0
+        set_error("idx_G (permuted tested genotypes) is not implemented in this build");
+        return CRM_ERR_UNSUPPORTED;
+    }
+    // 3. H'g as a K-outer operand, 4. rotated genotype for every rho
+    const long long ldhg = round_up(B, 2);
+    CRM_CHECK(launch_gather_transpose(C, ldH, nullptr, kexp, 0, 1, B, m, h->Hg.as<double>(), ldhg, st));
+    {
+        GemmOperands op{};
+        op.A = h->Tt.as<double>(); op.lda = (long long)R * mp; op.a_cols = (long long)R * mp;
+        op.B = h->Hg.as<double>(); op.ldb = ldhg; op.b_cols = B;
+        op.B2 = op.B; op.ldb2 = ldhg; op.b2_cols = B;
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, m, 0, R * mp, 0, (int)B, h->gr.as<double>(), (long long)R * mp, 1, st));
+    }
+    // 5. REML fits for every (SNP, rho)
+    FitArgs fa{};
+    fa.S = h->S.as<double>(); fa.yr = h->yr.as<double>(); fa.Wr = h->Wr.as<double>();
+    fa.gr = h->gr.as<double>(); fa.gr_ld = (long long)R * mp;
+    fa.gy = C + m; fa.gy_ld = (long long)kexp * ldH;
+    fa.gW = C + m + 1; fa.gW_ld = (long long)kexp * ldH;
+    fa.gg = sq; fa.gg_ld = h->ld2;
+    fa.stats = h->stats.as<double>();
+    fa.m = m; fa.mp = mp; fa.R = R; fa.c = c; fa.p = (int)B; fa.n = (double)h->n; fa.restricted = 1; fa.fixed_x = nullptr;
+    fa.lml = h->fit_lml.as<double>(); fa.delta = h->fit_delta.as<double>(); fa.scale = h->fit_scale.as<double>();
+    fa.beta = h->fit_beta.as<double>(); fa.xopt = h->fit_x.as<double>(); fa.nfev = h->fit_nfev.as<int>(); fa.flags = h->fit_flags.as<int>();
+    CRM_CHECK(launch_fit(fa, true, st));
+    // 6. best rho per SNP, grouping by rho
+    CRM_CHECK(launch_select(fa.lml, fa.delta, fa.scale, (int)B, R, h->rho_idx.as<int>(), h->best_lml.as<double>(), h->v0.as<double>(),
+                            h->v1.as<double>(), st));
+    if (dg && (dg->ov_rho_idx || dg->ov_v0 || dg->ov_v1)) {
+        override_select_kernel<<<blocks_for(B, 256), 256, 0, st>>>(dg->ov_rho_idx ? dg->ov_rho_idx + s0 : nullptr, dg->ov_v0 ? dg->ov_v0 + s0 : nullptr,
+                                                                  dg->ov_v1 ? dg->ov_v1 + s0 : nullptr, B, h->rho_idx.as<int>(), h->v0.as<double>(), h->v1.as<double>());
+        CRM_CUDA(cudaGetLastError()); count_launch();
+    }
+    CRM_CHECK(launch_group(h->rho_idx.as<int>(), (int)B, R, h->perm.as<int>(), h->offsets.as<int>(), st));
+    std::vector<int> off(R + 1);
+    CRM_CUDA(cudaMemcpyAsync(off.data(), h->offsets.as<int>(), (size_t)(R + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaStreamSynchronize(st));
+    // 7. H'(g.E0) in rho-sorted order as a K-outer operand, 8. rotation into the selected eigenbasis, group by group
+    const long long ldvg = round_up(B * k, 2);
+    CRM_CHECK(launch_gather_transpose(C, ldH, h->perm.as<int>(), kexp, 1, k, B * k, m, h->Vg.as<double>(), ldvg, st));
+    for (int r = 0; r < R; r++) {
+        const long long cnt = off[r + 1] - off[r];
+        if (cnt <= 0) continue;
+        GemmOperands op{};
+        op.A = h->Tt.as<double>(); op.lda = (long long)R * mp; op.a_cols = (long long)R * mp;
+        op.B = h->Vg.as<double>(); op.ldb = ldvg; op.b_cols = B * k;
+        op.B2 = op.B; op.ldb2 = ldvg; op.b2_cols = B * k;
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, m, r * mp, mp, (int)(off[r] * k), (int)(cnt * k), h->GEr.as<double>() + (long long)off[r] * k * mp, mp, 1, st));
+    }
+    // 9. score statistic + eigenvalues
+    ScoreArgs sa{};
+    sa.S = fa.S; sa.yr = fa.yr; sa.Wr = fa.Wr; sa.m = m; sa.mp = mp; sa.R = R; sa.c = c; sa.k = k; sa.kexp = kexp; sa.p = (int)B;
+    sa.perm = h->perm.as<int>(); sa.rho_idx = h->rho_idx.as<int>(); sa.v0 = h->v0.as<double>(); sa.v1 = h->v1.as<double>();
+    sa.gr = h->gr.as<double>(); sa.gr_ld = (long long)R * mp; sa.GEr = h->GEr.as<double>();
+    sa.rot = C; sa.rot_ld = ldH; sa.col_y = m; sa.col_W = m + 1;
+    sa.sq = sq; sa.sq_ld = h->ld2; sa.stats = h->stats.as<double>();
+    sa.Q = h->Q.as<double>(); sa.lam = h->lam.as<double>(); sa.lam_ld = k; sa.nlam = h->nlam.as<int>(); sa.flags = h->sflags.as<int>();
+    sa.Mout = (dg && dg->M) ? dg->M + s0 * k * k : nullptr;
+    CRM_CHECK(launch_score(sa, B, st));
+    // 10. p-values
+    PvalArgs pa{};
+    pa.Q = sa.Q; pa.lam = sa.lam; pa.nlam = sa.nlam; pa.lam_ld = k; pa.count = (int)B; pa.lim = 10000; pa.acc = 1e-6;
+    pa.pv = out_pv + s0; pa.liu = (dg && dg->liu) ? dg->liu + s0 : h->liu.as<double>();
+    pa.ifault = (dg && dg->ifault) ? dg->ifault + s0 : h->ifault.as<int>(); pa.converged = h->conv.as<int>(); pa.trace = nullptr;
+    CRM_CHECK(launch_pvalues(pa, st));
+    // 11. outputs
+    double* grid_dev = h->scratch.as<double>();
+    CRM_CUDA(cudaMemcpyAsync(grid_dev, h->rho.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
+    finalize_interaction_kernel<<<blocks_for(B, 256), 256, 0, st>>>(h->rho_idx.as<int>(), h->v0.as<double>(), h->v1.as<double>(), grid_dev, B,
+                                                                   out_rho1 + s0, out_e2 + s0, out_g2 + s0, out_eps2 + s0);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    if (dg) {
+        const size_t pr = (size_t)B * R;
+        if (dg->lml) CRM_CUDA(cudaMemcpyAsync(dg->lml + s0 * R, fa.lml, pr * 8, cudaMemcpyDeviceToDevice, st));
+        if (dg->delta) CRM_CUDA(cudaMemcpyAsync(dg->delta + s0 * R, fa.delta, pr * 8, cudaMemcpyDeviceToDevice, st));
+        if (dg->scale) CRM_CUDA(cudaMemcpyAsync(dg->scale + s0 * R, fa.scale, pr * 8, cudaMemcpyDeviceToDevice, st));
+        if (dg->nfev) CRM_CUDA(cudaMemcpyAsync(dg->nfev + s0 * R, fa.nfev, pr * 4, cudaMemcpyDeviceToDevice, st));
+        if (dg->Q) CRM_CUDA(cudaMemcpyAsync(dg->Q + s0, sa.Q, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+        if (dg->lam) CRM_CUDA(cudaMemcpyAsync(dg->lam + s0 * k, sa.lam, (size_t)B * k * 8, cudaMemcpyDeviceToDevice, st));
+        if (dg->nlam) CRM_CUDA(cudaMemcpyAsync(dg->nlam + s0, sa.nlam, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+        if (dg->flags) {
+            or_flags_kernel<<<blocks_for(B, 256), 256, 0, st>>>(fa.flags, h->rho_idx.as<int>(), sa.flags, R, B, dg->flags + s0);
+            CRM_CUDA(cudaGetLastError()); count_launch();
+        }
+    }
+    return CRM_OK;
+}
+
+static int do_scan_interaction(Handle* h, const double* G, long long ldg, long long p, int g_on_host, const double* Gtest, long long ldgt,
+                               double* out_pv, double* out_rho1, double* out_e2, double* out_g2, double* out_eps2,
+                               const crm_scan_diag_t* dg, cudaStream_t st) {
+    if (!h->ready) { set_error("crm_scan_interaction: handle is not set up"); return CRM_ERR_STATE; }
+    if (!G || p < 0 || ldg < p || !out_pv || !out_rho1 || !out_e2 || !out_g2 || !out_eps2) { set_error("crm_scan_interaction: bad arguments"); return CRM_ERR_INVALID; }
+    if (p == 0) return CRM_OK;
+    long long B = pick_batch(h, p, true);
+    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->n))));
+    CRM_CHECK(reserve_scan(h, B, true));
+    if (!g_on_host) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(G) & 15) == 0) && (ldg % 2 == 0);
+        for (long long s0 = 0; s0 < p; s0 += B) {
+            const long long b = std::min(B, p - s0);
+            const double* Gd = G + s0; long long ld = ldg, cols = p - s0;
+            const double* Gt = Gtest ? Gtest + s0 : nullptr;
+            if (!aligned || (s0 & 1)) {   // TMA needs a 16-byte aligned base and an even leading dimension: repack the block
+                const long long bp = round_up(b, 2);
+                CRM_CHECK(h->gchunk[0].reserve((size_t)h->n * bp * 8));
+                CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+                Gd = h->gchunk[0].as<double>(); ld = bp; cols = b;
+            }
+            CRM_CHECK(interaction_batch(h, Gd, ld, cols, Gt, ldgt, b, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, s0, st));
+        }
+        return CRM_OK;
+    }
+    // host-resident genotypes: double-buffered column blocks, copy of block i+1 overlaps compute of block i
+    CRM_CHECK(ensure_streams(h));
+    const long long nb = (p + B - 1) / B;
+    const long long Bp = round_up(B, 2);
+    CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
+    CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
+    CRM_CHECK(stage_host_block(h, G, ldg, 0, std::min(B, p), Bp, h->gchunk[0], 0, st));
+    for (long long ib = 0; ib < nb; ib++) {
+        const int slot = (int)(ib & 1);
+        const long long s0 = ib * B, b = std::min(B, p - s0);
+        if (ib + 1 < nb) CRM_CHECK(stage_host_block(h, G, ldg, s0 + B, std::min(B, p - s0 - B), Bp, h->gchunk[slot ^ 1], slot ^ 1, st));
+        CRM_CUDA(cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
+        CRM_CHECK(interaction_batch(h, h->gchunk[slot].as<double>(), Bp, b, nullptr, 0, b, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, s0, st));
+        CRM_CUDA(cudaEventRecord(h->ev_done[slot], st));
+    }
+    if (Gtest) { set_error("idx_G with host-resident genotypes is not implemented"); return CRM_ERR_UNSUPPORTED; }
+    return CRM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// association scans
+// ------------------------------------------------------------------------------------------------
+static int do_scan_association(Handle* h, const double* G, long long ldg, long long p, int g_on_host, int fast, double* out_pv,
+                               double* out_alt, double* info4, double* out_null, cudaStream_t st) {
+    if (!h->ready) { set_error("crm_scan_association: handle is not set up"); return CRM_ERR_STATE; }
+    if (!G || p < 0 || ldg < p || !out_pv || !info4) { set_error("crm_scan_association: bad arguments"); return CRM_ERR_INVALID; }
+    const int R = h->R, mp = h->mp, m = h->m, c = h->c, ldH = h->ldH, Mx = h->Mx;
+    long long B = pick_batch(h, std::max<long long>(p, 1), false);
+    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->n))));
+    CRM_CHECK(reserve_scan(h, std::max<long long>(B, 1), false));
+    // ---- null model: ML fit of y ~ W for every rho, best by strict '>' ----
+    FitArgs fa{};
+    fa.S = h->S.as<double>(); fa.yr = h->yr.as<double>(); fa.Wr = h->Wr.as<double>();
+    fa.gr = nullptr; fa.stats = h->stats.as<double>();
+    fa.m = m; fa.mp = mp; fa.R = R; fa.c = c; fa.p = 1; fa.n = (double)h->n; fa.restricted = 0; fa.fixed_x = nullptr;
+    fa.lml = h->fit_lml.as<double>(); fa.delta = h->fit_delta.as<double>(); fa.scale = h->fit_scale.as<double>();
+    fa.beta = h->fit_beta.as<double>(); fa.xopt = h->fit_x.as<double>(); fa.nfev = h->fit_nfev.as<int>(); fa.flags = h->fit_flags.as<int>();
+    CRM_CHECK(launch_fit(fa, false, st));
+    std::vector<double> lml(R), delta(R), scale(R), xopt(R);
+    CRM_CUDA(cudaMemcpyAsync(lml.data(), fa.lml, R * 8, cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaMemcpyAsync(delta.data(), fa.delta, R * 8, cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaMemcpyAsync(scale.data(), fa.scale, R * 8, cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaMemcpyAsync(xopt.data(), fa.xopt, R * 8, cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaStreamSynchronize(st));
+    int rb = 0; double best = -INFINITY;
+    for (int r = 0; r < R; r++) if (lml[r] > best) { best = lml[r]; rb = r; }
+    const double v0 = scale[rb] * (1.0 - delta[rb]), v1 = scale[rb] * delta[rb], rho = h->rho[rb];
+    const double info_host[4] = {rho, v0 * rho, v0 * (1.0 - rho), v1};
+    CRM_CUDA(cudaMemcpyAsync(info4, info_host, 32, cudaMemcpyHostToDevice, st));
+    if (out_null) CRM_CUDA(cudaMemcpyAsync(out_null, &best, 8, cudaMemcpyHostToDevice, st));
+    double* xfix = h->scratch.as<double>() + R + 1;
+    CRM_CUDA(cudaMemcpyAsync(xfix, &xopt[rb], 8, cudaMemcpyHostToDevice, st));
+    CRM_CUDA(cudaStreamSynchronize(st));   // host temporaries above go out of scope
+    if (p == 0) return CRM_OK;
+    if (g_on_host) CRM_CHECK(ensure_streams(h));
+    const long long Bp = round_up(B, 2);
+    const long long nb = (p + B - 1) / B;
+    if (g_on_host) {
+        CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
+        CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
+        CRM_CHECK(stage_host_block(h, G, ldg, 0, std::min(B, p), Bp, h->gchunk[0], 0, st));
+    }
+    const bool aligned = ((reinterpret_cast<uintptr_t>(G) & 15) == 0) && (ldg % 2 == 0);
+    for (long long ib = 0; ib < nb; ib++) {
+        const int slot = (int)(ib & 1);
+        const long long s0 = ib * B, b = std::min(B, p - s0);
+        const double* Gd; long long ld, cols;
+        if (g_on_host) {
+            if (ib + 1 < nb) CRM_CHECK(stage_host_block(h, G, ldg, s0 + B, std::min(B, p - s0 - B), Bp, h->gchunk[slot ^ 1], slot ^ 1, st));
+            CRM_CUDA(cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
+            Gd = h->gchunk[slot].as<double>(); ld = Bp; cols = b;
+        } else if (!aligned || (s0 & 1)) {
+            const long long bp = round_up(b, 2);
+            CRM_CHECK(h->gchunk[0].reserve((size_t)h->n * bp * 8));
+            CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+            Gd = h->gchunk[0].as<double>(); ld = bp; cols = b;
+        } else { Gd = G + s0; ld = ldg; cols = p - s0; }
+        double* C = h->C.as<double>();
+        double* sq = h->sq.as<double>();
+        GemmOperands op{};
+        op.A = h->Hx.as<double>(); op.lda = ldH; op.a_cols = Mx;
+        op.B = Gd; op.ldb = ld; op.b_cols = cols; op.B2 = Gd; op.ldb2 = ld; op.b2_cols = cols;
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, Mx, 0, (int)b, C, ldH, 1, st));
+        GemmOperands op2{};
+        op2.A = h->A2.as<double>(); op2.lda = h->ld2; op2.a_cols = h->M2;
+        op2.B = Gd; op2.ldb = ld; op2.b_cols = cols; op2.B2 = Gd; op2.ldb2 = ld; op2.b2_cols = cols;
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, op2, (int)h->n, 0, 1, 0, (int)b, sq, 2, 1, st));
+        const long long ldhg = round_up(b, 2);
+        CRM_CHECK(launch_gather_transpose(C, ldH, nullptr, 1, 0, 1, b, m, h->Hg.as<double>(), ldhg, st));
+        GemmOperands op3{};
+        op3.A = h->Tt.as<double>(); op3.lda = (long long)R * mp; op3.a_cols = (long long)R * mp;
+        op3.B = h->Hg.as<double>(); op3.ldb = ldhg; op3.b_cols = b; op3.B2 = op3.B; op3.ldb2 = ldhg; op3.b2_cols = b;
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op3, m, rb * mp, mp, 0, (int)b, h->gr.as<double>(), mp, 1, st));
+        FitArgs fb = fa;
+        fb.S = h->S.as<double>() + (long long)rb * mp; fb.yr = h->yr.as<double>() + (long long)rb * mp; fb.Wr = h->Wr.as<double>() + (long long)rb * c * mp;
+        fb.gr = h->gr.as<double>(); fb.gr_ld = mp;
+        fb.gy = C + m; fb.gy_ld = ldH; fb.gW = C + m + 1; fb.gW_ld = ldH; fb.gg = sq; fb.gg_ld = 2;
+        fb.R = 1; fb.p = (int)b; fb.restricted = 0; fb.fixed_x = fast ? xfix : nullptr;
+        fb.lml = out_alt ? out_alt + s0 : h->best_lml.as<double>();
+        CRM_CHECK(launch_fit(fb, true, st));
+        CRM_CHECK(launch_lrt(fb.lml, best, b, out_pv + s0, st));
+        if (g_on_host) CRM_CUDA(cudaEventRecord(h->ev_done[slot], st));
+    }
+    return CRM_OK;
+}
+
+}  // namespace crm
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+using namespace crm;
+
+struct crm_handle_s { Handle impl; };
+
+extern "C" {
+
+int crm_version(void) { return 100; }
+const char* crm_last_error(void) { return g_err; }
+
+int crm_create(crm_handle_t* out, int device) {
+    if (!out) { set_error("crm_create: null output"); return CRM_ERR_INVALID; }
+    int count = 0;
+    CRM_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) { set_error("crm_create: device %d not available (%d visible)", device, count); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CRM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_error("libcrm_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor); return CRM_ERR_UNSUPPORTED; }
+    crm_handle_s* h = new crm_handle_s();
+    h->impl.device = device;
+    *out = h;
+    return CRM_OK;
+}
+
+int crm_destroy(crm_handle_t h) {
+    if (!h) return CRM_OK;
+    cudaSetDevice(h->impl.device);
+    h->impl.free_all();
+    if (h->impl.solver) cusolverDnDestroy(h->impl.solver);
+    if (h->impl.copy_stream) {
+        cudaStreamDestroy(h->impl.copy_stream);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(h->impl.ev_copy[i]); cudaEventDestroy(h->impl.ev_done[i]); }
+    }
+    delete h;
+    return CRM_OK;
+}
+
+int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t ldw, const double* E0, int64_t lde0, const double* E1,
+              int64_t lde1, const double* L, int64_t ldl, int64_t n, int c, int k0, int k1, int64_t mL, const double* rho_host, int R,
+              void* stream) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    return do_setup(&h->impl, y, W, ldw, E0, lde0, E1, lde1, L, ldl, n, c, k0, k1, mL, rho_host, R, (cudaStream_t)stream);
+}
+
+int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream) {
+    if (!h || !h->impl.ready || !E0) { set_error("crm_set_test_contexts: handle not set up"); return CRM_ERR_STATE; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    return build_test_contexts(&h->impl, E0, lde0, (cudaStream_t)stream);
+}
+
+long long crm_launch_count(void) { return g_launches.load(); }
+
+int crm_profile(crm_handle_t h, int enable, double* rot_ms, double* rot_flops, int64_t* rot_launches) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    Handle& H = h->impl;
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < H.prof_events.size(); i += 2) {
+        float t = 0.f;
+        CRM_CUDA(cudaEventSynchronize(H.prof_events[i + 1]));
+        CRM_CUDA(cudaEventElapsedTime(&t, H.prof_events[i], H.prof_events[i + 1]));
+        ms += t;
+    }
+    if (rot_ms) *rot_ms = ms;
+    if (rot_flops) *rot_flops = H.prof_flops;
+    if (rot_launches) *rot_launches = (int64_t)(H.prof_events.size() / 2);
+    for (cudaEvent_t e : H.prof_events) cudaEventDestroy(e);
+    H.prof_events.clear();
+    H.prof_flops = 0.0;
+    H.prof_on = enable != 0;
+    return CRM_OK;
+}
+
+int crm_get_dims(crm_handle_t h, int64_t* d) {
+    if (!h || !h->impl.ready || !d) { set_error("crm_get_dims: handle not set up"); return CRM_ERR_STATE; }
+    d[0] = h->impl.n; d[1] = h->impl.c; d[2] = h->impl.k0; d[3] = h->impl.m; d[4] = h->impl.R; d[5] = h->impl.mp; d[6] = h->impl.max_rank;
+    return CRM_OK;
+}
+
+int crm_get_spectrum(crm_handle_t h, int r, double* out, void* stream) {
+    if (!h || !h->impl.ready || !out || r < 0 || r >= h->impl.R) { set_error("crm_get_spectrum: bad arguments"); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaMemcpyAsync(out, h->impl.S.as<double>() + (long long)r * h->impl.mp, (size_t)h->impl.mp * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CRM_OK;
+}
+
+int crm_scan_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, const double* Gtest, int64_t ldgt,
+                         double* out_pv, double* out_rho1, double* out_e2, double* out_g2, double* out_eps2, const crm_scan_diag_t* diag,
+                         void* stream) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    return do_scan_interaction(&h->impl, G, ldg, p, g_on_host, Gtest, ldgt, out_pv, out_rho1, out_e2, out_g2, out_eps2, diag, (cudaStream_t)stream);
+}
+
+int crm_scan_association(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, int fast, double* out_pv,
+                         double* out_alt_lml, double* info4, double* out_null_lml, void* stream) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    return do_scan_association(&h->impl, G, ldg, p, g_on_host, fast, out_pv, out_alt_lml, info4, out_null_lml, (cudaStream_t)stream);
+}
+
+int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const double* B, int64_t ldb, int64_t b_cols, const double* B2,
+             int64_t ldb2, int64_t b2_cols, int64_t K, int m_begin, int m_count, int64_t n_begin, int64_t n_count, double* out, int64_t ldc,
+             int kexp, void* stream) {
+    if (!A || !B || !out || K <= 0 || mode < 0 || mode > 2 || (mode != 0 && !B2)) { set_error("crm_gemm: bad arguments"); return CRM_ERR_INVALID; }
+    GemmOperands op{};
+    op.A = A; op.lda = lda; op.a_cols = a_cols; op.B = B; op.ldb = ldb; op.b_cols = b_cols;
+    op.B2 = B2 ? B2 : B; op.ldb2 = B2 ? ldb2 : ldb; op.b2_cols = B2 ? b2_cols : b_cols;
+    return launch_gemm(mode, op, (int)K, m_begin, m_count, (int)n_begin, (int)n_count, out, ldc, kexp, (cudaStream_t)stream);
+}
+
+int crm_lmm_fit_rotated(const double* S, const double* yr, const double* Wr, const double* gr, const double* gy, const double* gW,
+                        const double* gg, const double* stats, int m, int mp, int R, int c, int64_t p, double n, int restricted,
+                        double* lml, double* delta, double* scale, double* beta, int32_t* nfev, int32_t* flags, void* stream) {
+    if (!S || !yr || !Wr || !stats || !lml || !delta || !scale || !beta || !nfev || !flags || p <= 0) { set_error("crm_lmm_fit_rotated: bad arguments"); return CRM_ERR_INVALID; }
+    FitArgs fa{};
+    fa.S = S; fa.yr = yr; fa.Wr = Wr; fa.gr = gr; fa.gr_ld = (long long)R * mp;
+    fa.gy = gy; fa.gy_ld = 1; fa.gW = gW; fa.gW_ld = c; fa.gg = gg; fa.gg_ld = 1; fa.stats = stats;
+    fa.m = m; fa.mp = mp; fa.R = R; fa.c = c; fa.p = (int)p; fa.n = n; fa.restricted = restricted; fa.fixed_x = nullptr;
+    fa.lml = lml; fa.delta = delta; fa.scale = scale; fa.beta = beta; fa.xopt = nullptr; fa.nfev = nfev; fa.flags = flags;
+    return launch_fit(fa, gr != nullptr, (cudaStream_t)stream);
+}
+
+int crm_davies_pvalues(const double* Q, const double* lam, const int32_t* nlam, int lam_ld, int64_t count, int lim, double acc, double* pv,
+                       double* liu, int32_t* ifault, int32_t* converged, double* trace8, void* stream) {
+    if (!Q || !lam || !nlam || !pv || count < 0) { set_error("crm_davies_pvalues: bad arguments"); return CRM_ERR_INVALID; }
+    if (count == 0) return CRM_OK;
+    PvalArgs pa{};
+    pa.Q = Q; pa.lam = lam; pa.nlam = nlam; pa.lam_ld = lam_ld; pa.count = (int)count; pa.lim = lim; pa.acc = acc;
+    pa.pv = pv; pa.liu = liu; pa.ifault = ifault; pa.converged = converged; pa.trace = trace8;
+    return launch_pvalues(pa, (cudaStream_t)stream);
+}
+
+int crm_lrt_pvalues(const double* alt_lml, double null_lml, int64_t count, double* pv, void* stream) {
+    if (!alt_lml || !pv || count < 0) { set_error("crm_lrt_pvalues: bad arguments"); return CRM_ERR_INVALID; }
+    if (count == 0) return CRM_OK;
+    return launch_lrt(alt_lml, null_lml, count, pv, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// Argument blocks of the kernels (shared between the kernel translation units and the host orchestration).
+#pragma once
+#include "common.cuh"
+
+namespace crm {
+
+struct FitArgs {
+    // shared per rho1 (padded leading dimension mp; entries beyond the kept rank are zero)
+    const double* S;    // [R][mp]
+    const double* yr;   // [R][mp]
+    const double* Wr;   // [R][c][mp]
+    // per SNP
+    const double* gr;   // [p][R*mp]   rotated genotype, row stride gr_ld
+    long long gr_ld;
+    const double* gy;   // g'y per SNP, element stride gy_ld
+    long long gy_ld;
+    const double* gW;   // g'W_a per SNP at gW[s * gW_ld + a]
+    long long gW_ld;
+    const double* gg;   // g'g per SNP, element stride gg_ld
+    long long gg_ld;
+    // plain statistics of the null design: [y'y, W'y (c), W'W (c*c)]
+    const double* stats;
+    int m, mp, R, c, p;
+    double n;           // number of samples
+    int restricted;
+    const double* fixed_x;   // when non-null: no search, evaluate at logit(delta) = *fixed_x (FastScanner semantics)
+    // outputs, [p][R] (beta: [p][R][P]); xopt may be null
+    double* lml; double* delta; double* scale; double* beta; double* xopt; int* nfev; int* flags;
+};
+
+struct ScoreArgs {
+    // per-rho shared rotated quantities
+    const double* S; const double* yr; const double* Wr;   // [R][mp], [R][mp], [R][c][mp]
+    int m, mp, R, c, k, kexp, p;
+    // per SNP
+    const int* perm;        // sorted position -> SNP
+    const int* rho_idx;     // [p]
+    const double* v0; const double* v1;   // [p]
+    const double* gr; long long gr_ld;    // rotated genotype [p][R*mp]
+    const double* GEr;      // rotated g.E0 in sorted order: [(pos*k + j)][mp]
+    const double* rot; long long rot_ld;  // K1 output rows (s*kexp + j), columns col_y / col_W + a
+    int col_y, col_W;
+    const double* sq; long long sq_ld;    // squared-genotype Grams per SNP: [gg | GE'g (k) | GE'GE pairs (k(k+1)/2)]
+    const double* stats;    // [y'y, W'y (c), W'W (c*c)]
+    // outputs (indexed by SNP)
+    double* Q; double* lam; int lam_ld; int* nlam; int* flags;
+    double* Mout;           // optional [p][k*k] weight matrices (diagnostics / stage parity), may be null
+};
+
+constexpr int SCORE_MAX_NZ = 63;
+
+struct PvalArgs {
+    const double* Q;        // [count]
+    const double* lam;      // [count][lam_ld] eigenvalues, any order, nlam[i] valid entries
+    const int* nlam;        // [count]
+    int lam_ld;
+    int count;
+    int lim; double acc;
+    double* pv;             // [count]
+    double* liu;            // [count] modified-Liu p-value (may be null)
+    int* ifault;            // [count] (may be null)
+    int* converged;         // [count] (may be null)
+    double* trace;          // [count][8]: qfval, trace[0..6] (may be null)
+};
+
+constexpr int PV_MAXLAM = 128;
+
+}  // namespace crm

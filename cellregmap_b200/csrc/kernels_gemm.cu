@@ -1,0 +1,117 @@
+// Host-side launcher of K1 (tensor-map construction + launch).
+#pragma once
+#include "gemm.cuh"
+#include "launch.cuh"
+
+namespace crm {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major f64 matrix (rows x cols, leading dimension ld doubles) -> tiled tensor map with box (box_cols x box_rows).
+inline int make_map_2d(CUtensorMap* map, const double* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return CRM_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 1)) {
+        set_error("TMA operand must be 16-byte aligned with an even leading dimension (ptr=%p ld=%lld)", (const void*)ptr, ld);
+        return CRM_ERR_INVALID;
+    }
+    if (box_cols > 256 || box_rows > 256 || (box_cols & 1)) { set_error("bad TMA box %d x %d", box_cols, box_rows); return CRM_ERR_INVALID; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%dx%d)", (int)r, rows, cols, ld, box_cols, box_rows); return CRM_ERR_CUDA; }
+    return CRM_OK;
+}
+
+// smallest even pitch >= w whose multiples {0,p,2p,3p} mod 16 are pairwise >= 2 apart (bank-conflict-free fragment reads)
+inline int conflict_free_pitch(int w) {
+    for (int p = (w + 1) & ~1;; p += 2) {
+        int r[4] = {0, p % 16, (2 * p) % 16, (3 * p) % 16};
+        bool ok = true;
+        for (int i = 0; i < 4 && ok; i++)
+            for (int j = i + 1; j < 4; j++) {
+                int d = abs(r[i] - r[j]);
+                d = d < 16 - d ? d : 16 - d;
+                if (d < 2) { ok = false; break; }
+            }
+        if (ok) return p;
+    }
+}
+inline int expand_box_width(int kexp) { return conflict_free_pitch((GEMM_BN - 1 + kexp - 1) / kexp + 2); }   // +1: even-aligned box start
+
+
+template <int MODE>
+int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream) {
+    CUtensorMap tmA, tmB, tmB2;
+    CRM_CHECK(make_map_2d(&tmA, op.A, args.K, op.a_cols, op.lda, GEMM_APITCH, GEMM_BK));
+    int stage_bytes = GEMM_BK * GEMM_APITCH * 8;
+    if (MODE == GEMM_EXPAND) {
+        CRM_CHECK(make_map_2d(&tmB, op.B, args.K, op.b_cols, op.ldb, args.gpitch, GEMM_BK));
+        CRM_CHECK(make_map_2d(&tmB2, op.B2, args.K, op.b2_cols, op.ldb2, args.epitch, GEMM_BK));
+        stage_bytes += GEMM_BK * (args.gpitch + args.epitch) * 8;
+    } else {
+        CRM_CHECK(make_map_2d(&tmB, op.B, args.K, op.b_cols, op.ldb, GEMM_APITCH, GEMM_BK));
+        stage_bytes += GEMM_BK * GEMM_APITCH * 8;
+        if (MODE == GEMM_PRODUCT) {
+            CRM_CHECK(make_map_2d(&tmB2, op.B2, args.K, op.b2_cols, op.ldb2, GEMM_APITCH, GEMM_BK));
+            stage_bytes += GEMM_BK * GEMM_APITCH * 8;
+        } else {
+            tmB2 = tmB;
+        }
+    }
+    const int max_smem = 227 * 1024;
+    int stages = (max_smem - 256) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) { set_error("GEMM stage of %d bytes does not fit shared memory twice", stage_bytes); return CRM_ERR_UNSUPPORTED; }
+    args.stages = stages;
+    args.stage_bytes = stage_bytes;
+    size_t smem = (size_t)stages * stage_bytes + 2 * stages * sizeof(uint64_t);
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[MODE]) {
+        CRM_CUDA(cudaFuncSetAttribute(crm_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set[MODE] = true;
+    }
+    const int m_span = args.m_count + (args.m_begin & 1), n_span = args.n_count + (MODE == GEMM_EXPAND ? 0 : (args.n_begin & 1));
+    dim3 grid((m_span + GEMM_BM - 1) / GEMM_BM, (n_span + GEMM_BN - 1) / GEMM_BN, 1);
+    if (grid.x == 0 || grid.y == 0) return CRM_OK;
+    if (grid.y > 65535) { set_error("GEMM N extent %d too large for one launch", args.n_count); return CRM_ERR_UNSUPPORTED; }
+    crm_gemm_kernel<MODE><<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, args);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
+// C[n_count][m_count] (ldc) = B[:, n_begin:+n_count]^T A[:, m_begin:+m_count], B built according to `mode`.
+int launch_gemm(int mode, const GemmOperands& op, int K, int m_begin, int m_count, int n_begin, int n_count,
+                       double* out, long long ldc, int kexp, cudaStream_t stream) {
+    GemmArgs a{};
+    a.K = K; a.m_begin = m_begin; a.m_count = m_count; a.n_begin = n_begin; a.n_count = n_count;
+    a.out = out; a.ldc = ldc; a.kexp = kexp > 0 ? kexp : 1;
+    a.gpitch = GEMM_APITCH; a.epitch = GEMM_APITCH;
+    if (mode == GEMM_EXPAND) {
+        a.gpitch = expand_box_width(a.kexp);
+        a.epitch = (int)op.ldb2;
+        if (a.epitch < a.kexp + 1) { set_error("Eext needs at least kexp+1 columns"); return CRM_ERR_INVALID; }
+        return launch_gemm_mode<GEMM_EXPAND>(op, a, stream);
+    }
+    if (mode == GEMM_PRODUCT) return launch_gemm_mode<GEMM_PRODUCT>(op, a, stream);
+    return launch_gemm_mode<GEMM_PLAIN>(op, a, stream);
+}
+
+}  // namespace crm

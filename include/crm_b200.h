@@ -1,0 +1,123 @@
+/*
+ * crm_b200.h -- C ABI of libcrm_b200.so, the B200 (sm_100a) implementation of CellRegMap's per-variant scans.
+ *
+ * The reference (limix/CellRegMap) is pure Python and has no FFI of its own; this ABI is the thin layer the
+ * Python mirror (cellregmap_b200/_cellregmap.py) binds with ctypes.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions: all matrices are float64, row-major, with an explicit leading dimension in elements; every data
+ * pointer is a DEVICE pointer unless the parameter name ends in `_host`; sizes are int64_t / int; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream); the caller owns inputs and outputs (outputs must be
+ * allocated by the caller), internal workspaces are owned by the handle.  Return value: 0 ok, <0 invalid
+ * argument / unsupported shape / bad state, >0 CUDA or cuSOLVER failure; crm_last_error() gives the message of
+ * the last failure on the calling thread.  No exceptions cross the boundary.  A handle is not thread-safe;
+ * different handles may be used from different threads.
+ */
+#ifndef CRM_B200_H
+#define CRM_B200_H
+#include <stdint.h>
+#if defined(__GNUC__)
+#define CRM_API __attribute__((visibility("default")))
+#else
+#define CRM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crm_handle_s* crm_handle_t;
+
+CRM_API int crm_version(void);
+CRM_API const char* crm_last_error(void);
+
+/* Model object: replaces CellRegMap.__init__ state (cellregmap/_cellregmap.py:63-131). */
+CRM_API int crm_create(crm_handle_t* out, int device);
+CRM_API int crm_destroy(crm_handle_t h);
+
+/*
+ * Constructor set-up (cellregmap/_cellregmap.py:93-131 + numpy_sugar.economic_qs_linear, semantics in
+ * cellregmap/_math.py:204-256): eigendecomposition of rho*E1 E1' + (1-rho)*L L' for every rho of the grid,
+ * done in the column space of the shared half-basis H = [E1 | L].
+ *   y (n), W (n x c, ldw), E0 (n x k0, lde0) contexts of the tested GxC term, E1 (n x k1, lde1) contexts of the
+ *   background, L (n x mL, ldl) = concatenated Ls / hK (NULL with mL = 0 for the E1-only background),
+ *   rho_host[R] the rho1 grid (host memory).
+ */
+CRM_API int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t ldw, const double* E0, int64_t lde0,
+              const double* E1, int64_t lde1, const double* L, int64_t ldl, int64_t n, int c, int k0, int k1,
+              int64_t mL, const double* rho_host, int R, void* stream);
+
+/* Replaces the tested-context matrix E0 (row-permuted contexts: idx_E of scan_interaction, _cellregmap.py:398-401). */
+CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream);
+
+/* Sizes fixed by crm_setup: [0]=n [1]=c [2]=k0 [3]=m (columns of H) [4]=R [5]=padded m [6]=max kept rank. */
+CRM_API int crm_get_dims(crm_handle_t h, int64_t* dims7);
+/* Copies S0 of grid point r (padded to dims[5], zeros beyond the kept rank) into out (device). */
+CRM_API int crm_get_spectrum(crm_handle_t h, int r, double* out, void* stream);
+
+/*
+ * Interaction scan: replaces CellRegMap.scan_interaction (cellregmap/_cellregmap.py:317-440) for p SNPs.
+ *   G: n x p genotypes, leading dimension ldg; device memory, or pinned/pageable host memory when g_on_host != 0
+ *      (then the columns are streamed to the device in chunks, overlapped with compute).
+ *   Gtest: optional n x p genotypes used only in the tested design g.E0 (idx_G permutation, :410-413), else NULL.
+ *   out_pv, out_rho1, out_e2, out_g2, out_eps2: p doubles each (device).
+ *   Optional diagnostics (device, may be NULL): d_lml/d_delta/d_scale [p][R], d_Q [p], d_lam [p][k0],
+ *   d_nlam [p] (int32), d_M [p][k0*k0], d_liu [p], d_ifault [p] (int32), d_flags [p] (int32: bit0 no eigenvalue
+ *   > 0, bit1 rank-deficient design, bit2 det(H) <= 0 in a fit), d_nfev [p][R] (int32).
+ *   Optional overrides (device, may be NULL): fix the selected grid index and variance components per SNP
+ *   (stage-injected parity tests): ov_rho_idx [p] (int32), ov_v0 [p], ov_v1 [p].
+ */
+typedef struct {
+    double* lml; double* delta; double* scale; double* Q; double* lam; int32_t* nlam; double* M; double* liu;
+    int32_t* ifault; int32_t* flags; int32_t* nfev;
+    const int32_t* ov_rho_idx; const double* ov_v0; const double* ov_v1;
+} crm_scan_diag_t;
+
+CRM_API int crm_scan_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, const double* Gtest,
+                         int64_t ldgt, double* out_pv, double* out_rho1, double* out_e2, double* out_g2,
+                         double* out_eps2, const crm_scan_diag_t* diag, void* stream);
+
+/*
+ * Association scans: replace CellRegMap.scan_association / scan_association_fast
+ * (cellregmap/_cellregmap.py:246-281, 284-314) and lrt_pvalues (:443-469).  info4 (device) receives
+ * rho1, e2, g2, eps2 of the null model; out_null_lml (device, 1 double, may be NULL).
+ */
+CRM_API int crm_scan_association(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, int fast,
+                         double* out_pv, double* out_alt_lml, double* info4, double* out_null_lml, void* stream);
+
+/* Number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches). */
+CRM_API long long crm_launch_count(void);
+/* Event timing of the rotation kernel (K1) on the launching stream: returns the totals accumulated since the last
+ * call (ms, algorithmic flop = 2 n m (1+k0) per SNP, launches), resets them, and switches the timing on/off. */
+CRM_API int crm_profile(crm_handle_t h, int enable, double* rot_ms, double* rot_flops, int64_t* rot_launches);
+
+/* ---- stage-level entry points (used by the parity tests and by the Python mirror) ---- */
+
+/* K1: out[n_count][m_count] (ldc) = B[:, n_begin:+n_count]' A[:, m_begin:+m_count] over K rows.
+ * mode 0: B as given; 1: B .* B2; 2: B[k][s*kexp+j] = G[k][s] * Eext[k][j] with G = B, Eext = B2 (ldb2 = its width). */
+CRM_API int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const double* B, int64_t ldb, int64_t b_cols,
+             const double* B2, int64_t ldb2, int64_t b2_cols, int64_t K, int m_begin, int m_count, int64_t n_begin,
+             int64_t n_count, double* out, int64_t ldc, int kexp, void* stream);
+
+/* K2 on caller-supplied rotated statistics: replaces glimix_core LMM(y, X, QS, restricted).fit() for p x R problems.
+ * S, yr [R][mp]; Wr [R][c][mp]; gr [p][R*mp] (NULL: design is W only, p must be 1); gy [p], gW [p][c], gg [p];
+ * stats = [y'y, W'y (c), W'W (c*c)].  Outputs [p][R] (beta [p][R][c + has_g]). */
+CRM_API int crm_lmm_fit_rotated(const double* S, const double* yr, const double* Wr, const double* gr, const double* gy,
+                        const double* gW, const double* gg, const double* stats, int m, int mp, int R, int c, int64_t p,
+                        double n, int restricted, double* lml, double* delta, double* scale, double* beta,
+                        int32_t* nfev, int32_t* flags, void* stream);
+
+/* K4: Davies p-values with modified-Liu fall-backs: replaces chiscore.davies_pvalue's _pvalue_lambda for `count`
+ * (Q, eigenvalue list) pairs.  lam [count][lam_ld], nlam [count] valid entries each.  Optional outputs may be NULL;
+ * trace8 [count][8] = qfval, trace[0..6] of the published routine. */
+CRM_API int crm_davies_pvalues(const double* Q, const double* lam, const int32_t* nlam, int lam_ld, int64_t count, int lim,
+                       double acc, double* pv, double* liu, int32_t* ifault, int32_t* converged, double* trace8,
+                       void* stream);
+
+/* lrt_pvalues (cellregmap/_cellregmap.py:443-469) with dof = 1. */
+CRM_API int crm_lrt_pvalues(const double* alt_lml, double null_lml, int64_t count, double* pv, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,177 @@
+"""Stage-level parity of the CUDA kernels against the oracle (through the C ABI)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(x, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _gemm(mode, A, B, B2, m_begin, m_count, n_begin, n_count, kexp, dev):
+    import torch
+    from cellregmap_b200 import _lib
+    At, Bt = _t(A, dev), _t(B, dev)
+    B2t = _t(B2, dev) if B2 is not None else None
+    out = torch.full((n_count, m_count + 2), -7.0, dtype=torch.float64, device=dev)
+    _lib.call("crm_gemm", mode, _p(At), A.shape[1], A.shape[1], _p(Bt), B.shape[1], B.shape[1],
+              _p(B2t) if B2t is not None else ctypes.c_void_p(0), 0 if B2 is None else B2.shape[1], 0 if B2 is None else B2.shape[1],
+              A.shape[0], m_begin, m_count, n_begin, n_count, _p(out), m_count + 2, kexp, ctypes.c_void_p(0))
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.all(o[:, m_count:] == -7.0)      # nothing written outside the requested block
+    return o[:, :m_count]
+
+
+@pytest.mark.parametrize("K,M,N", [(1, 2, 2), (37, 130, 6), (1000, 222, 300), (4099, 64, 129)])
+def test_gemm_plain(cuda_device, K, M, N):
+    rng = np.random.default_rng(K + M + N)
+    Mp, Np = M + (M & 1), N + (N & 1)
+    A = rng.standard_normal((K, Mp)); B = rng.standard_normal((K, Np))
+    got = _gemm(0, A, B, None, 0, M, 0, N, 1, cuda_device)
+    want = B[:, :N].T @ A[:, :M]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12 * np.sqrt(K))
+
+
+def test_gemm_sub_blocks(cuda_device):
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((513, 300)); B = rng.standard_normal((513, 400))
+    got = _gemm(0, A, B, None, 37, 150, 11, 260, 1, cuda_device)
+    want = B[:, 11:271].T @ A[:, 37:187]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-11)
+
+
+def test_gemm_product(cuda_device):
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((777, 232)); G = rng.integers(0, 3, (777, 150)).astype(float)
+    got = _gemm(1, A, G, G, 0, 231, 0, 149, 1, cuda_device)
+    want = (G[:, :149] ** 2).T @ A[:, :231]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-11)
+
+
+@pytest.mark.parametrize("k", [1, 3, 10, 20, 41])
+def test_gemm_expand(cuda_device, k):
+    rng = np.random.default_rng(k)
+    K, M, S = 1531, 200, 57
+    kexp = 1 + k
+    pitch = (kexp + 2) & ~1
+    while pitch % 16 not in (4, 12):
+        pitch += 2
+    A = rng.standard_normal((K, M)); G = rng.integers(0, 3, (K, S + (S & 1))).astype(float)
+    E = rng.standard_normal((K, k))
+    Eext = np.zeros((K, pitch)); Eext[:, 0] = 1.0; Eext[:, 1:kexp] = E
+    got = _gemm(2, A, G, Eext, 0, M, 0, S * kexp, kexp, cuda_device)
+    cols = []
+    for s in range(S):
+        cols.append(G[:, s]); cols += [G[:, s] * E[:, j] for j in range(k)]
+    want = np.stack(cols, axis=1).T @ A
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-11)
+
+
+def _davies_gpu(Q, lams, dev):
+    import torch
+    from cellregmap_b200 import _lib
+    count = len(Q)
+    ld = max(len(l) for l in lams)
+    lam = np.zeros((count, ld)); nlam = np.zeros(count, np.int32)
+    for i, l in enumerate(lams):
+        lam[i, :len(l)] = l; nlam[i] = len(l)
+    Qt, lt, nt = _t(np.asarray(Q, float), dev), _t(lam, dev), _t(nlam, dev)
+    pv = torch.empty(count, dtype=torch.float64, device=dev); liu = torch.empty_like(pv)
+    ifault = torch.empty(count, dtype=torch.int32, device=dev); conv = torch.empty_like(ifault)
+    trace = torch.empty((count, 8), dtype=torch.float64, device=dev)
+    _lib.call("crm_davies_pvalues", _p(Qt), _p(lt), _p(nt), ld, count, 10000, 1e-6, _p(pv), _p(liu), _p(ifault), _p(conv), _p(trace), ctypes.c_void_p(0))
+    torch.cuda.synchronize()
+    return pv.cpu().numpy(), liu.cpu().numpy(), ifault.cpu().numpy(), conv.cpu().numpy(), trace.cpu().numpy()
+
+
+def test_davies_matches_oracle(cuda_device):
+    from oracle import chiscore_port as cp
+    rng = np.random.default_rng(11)
+    Q, lams = [], []
+    for i in range(300):
+        r = int(rng.integers(1, 25))
+        lam = np.sort(rng.gamma(0.7, 1.0, r))[::-1] + 1e-6
+        q = lam.sum() * float(rng.choice([0.05, 0.5, 1.0, 2.0, 4.0, 8.0, 16.0, 40.0]))
+        Q.append(q); lams.append(lam)
+    pv, liu, ifault, conv, trace = _davies_gpu(Q, lams, cuda_device)
+    for i in range(len(Q)):
+        p, info = cp.pvalue_from_lambda(lams[i], Q[i])
+        assert ifault[i] == info["ifault"], (i, ifault[i], info["ifault"])
+        assert conv[i] == info["Is_Converged"]
+        assert trace[i, 7] == info["trace"][6]            # same number of bound evaluations
+        assert trace[i, 2] == info["trace"][1]            # same number of integration terms
+        assert abs(np.log10(liu[i]) - np.log10(info["liu_pval"])) < 1e-6
+        if p >= 1e-12:
+            assert abs(np.log10(pv[i]) - np.log10(p)) <= 1e-4, (i, pv[i], p)
+        else:
+            assert abs(np.log10(pv[i]) - np.log10(p)) <= 1e-3
+
+
+def test_davies_edge_cases(cuda_device):
+    pv, liu, ifault, conv, _ = _davies_gpu([1.0, 1.0], [np.array([0.5]), np.array([])], cuda_device)
+    from scipy.stats import chi2
+    assert abs(pv[0] - chi2.sf(2.0, 1)) < 1e-8       # single eigenvalue -> Liu, exact for one chi2_1
+    assert np.isnan(pv[1]) and ifault[1] == -1       # no eigenvalue -> flagged
+
+
+def test_lrt_pvalues(cuda_device):
+    from cellregmap_b200 import lrt_pvalues
+    from oracle.crm_port import lrt_pvalues as ref
+    alt = np.array([-100.0, -99.0, -90.0, -50.0, -100.5, -100.0 + 1e-9, 700.0])
+    got = lrt_pvalues(-100.0, alt)
+    want = ref(-100.0, alt)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("restricted", [True, False])
+@pytest.mark.parametrize("c", [1, 3])
+def test_lmm_fit_rotated_matches_oracle(cuda_device, restricted, c):
+    import torch
+    from cellregmap_b200 import _lib
+    from oracle.lmm_port import LMM
+    from oracle.sugar_port import economic_qs_linear
+    rng = np.random.default_rng(100 + c)
+    n, r, p, R = 300, 40, 12, 3
+    y = rng.standard_normal(n)
+    W = np.column_stack([np.ones(n)] + [rng.standard_normal(n) for _ in range(c - 1)])
+    G = rng.integers(0, 3, (n, p)).astype(float)
+    mp_ = r + (r & 1)
+    S = np.zeros((R, mp_)); yr = np.zeros((R, mp_)); Wr = np.zeros((R, c, mp_)); gr = np.zeros((p, R, mp_))
+    QSs = []
+    for k in range(R):
+        Gh = rng.standard_normal((n, r)) * (0.3 + 0.4 * k)
+        if k == 0:
+            y = y + 0.5 * Gh @ rng.standard_normal(r) / np.sqrt(r)
+        QSs.append(economic_qs_linear(Gh, return_q1=False))
+    for k in range(R):
+        Q0, S0 = QSs[k][0][0], QSs[k][1]
+        S[k, :r] = S0; yr[k, :r] = Q0.T @ y; Wr[k, :, :r] = (Q0.T @ W).T; gr[:, k, :r] = (Q0.T @ G).T
+    stats = np.concatenate([[y @ y], W.T @ y, (W.T @ W).ravel()])
+    dev = cuda_device
+    args = [_t(a, dev) for a in (S, yr, Wr, gr, G.T @ y, G.T @ W, (G * G).sum(0), stats)]
+    P = c + 1
+    lml = torch.empty((p, R), dtype=torch.float64, device=dev); delta = torch.empty_like(lml); scale = torch.empty_like(lml)
+    beta = torch.empty((p, R, P), dtype=torch.float64, device=dev)
+    nfev = torch.empty((p, R), dtype=torch.int32, device=dev); flags = torch.empty_like(nfev)
+    _lib.call("crm_lmm_fit_rotated", *[_p(a) for a in args], r, mp_, R, c, p, float(n), int(restricted),
+              _p(lml), _p(delta), _p(scale), _p(beta), _p(nfev), _p(flags), ctypes.c_void_p(0))
+    torch.cuda.synchronize()
+    lml, delta, scale, beta, nfev = [a.cpu().numpy() for a in (lml, delta, scale, beta, nfev)]
+    for s in range(p):
+        for k in range(R):
+            ref = LMM(y, np.column_stack([W, G[:, s]]), QSs[k], restricted=restricted)
+            ref.fit(verbose=False)
+            assert abs(lml[s, k] - ref.lml()) <= 1e-6 * abs(ref.lml())
+            np.testing.assert_allclose(delta[s, k], ref.delta, rtol=1e-6)
+            np.testing.assert_allclose(scale[s, k], ref.scale, rtol=1e-6)
+            np.testing.assert_allclose(beta[s, k], ref.beta, rtol=1e-5, atol=1e-8)
+            assert nfev[s, k] == ref.nfev - 1 or nfev[s, k] == ref.nfev

@@ -1,0 +1,139 @@
+"""End-to-end parity of the public API (CUDA path through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+
+from cellregmap_b200.synth import make_data
+
+pytestmark = pytest.mark.gpu
+
+# tolerances of BASELINE.json north_star
+RTOL_VC = 1e-6       # lml and variance components
+RTOL_Q = 1e-9        # score statistic, with the oracle's variance components injected
+DLOG10_P = 1e-4      # |delta log10 p| for p >= 1e-12
+
+
+def _check_interaction(d, oracle_out, stages, model, G, **kw):
+    import torch
+    pv_ref, info_ref = oracle_out
+    out = model._scan_interaction_device(G, diagnostics=True, **kw)
+    pv = out["pv"].cpu().numpy()
+    rho_grid = np.asarray(model._rho1)
+    # selected rho1 identical
+    np.testing.assert_array_equal(out["rho1"].cpu().numpy(), info_ref["rho1"])
+    # lml grid and variance components
+    lml_ref = np.array([[f[1] for f in fits] for fits in stages["fits"]])
+    np.testing.assert_allclose(out["lml"].cpu().numpy(), lml_ref, rtol=RTOL_VC)
+    for key in ("e2", "g2", "eps2"):
+        np.testing.assert_allclose(out[key].cpu().numpy(), info_ref[key], rtol=RTOL_VC, atol=1e-12)
+    # p-values and ranking
+    big = pv_ref >= 1e-12
+    assert np.max(np.abs(np.log10(pv[big]) - np.log10(pv_ref[big]))) <= DLOG10_P
+    np.testing.assert_array_equal(np.argsort(pv, kind="stable"), np.argsort(pv_ref, kind="stable"))
+    # score statistic and weights with the oracle's fitted values injected
+    ridx = np.array([int(np.argmin(np.abs(rho_grid - r))) for r in info_ref["rho1"]], dtype=np.int32)
+    inj = model._scan_interaction_device(G, diagnostics=True, overrides={"rho_idx": ridx, "v0": np.array(stages["v0"]), "v1": np.array(stages["v1"])}, **kw)
+    np.testing.assert_allclose(inj["Q"].cpu().numpy(), np.array(stages["Q"]), rtol=RTOL_Q)
+    M = inj["M"].cpu().numpy()
+    for i in range(len(pv_ref)):
+        scale = np.abs(stages["M"][i]).max()
+        np.testing.assert_allclose(M[i], stages["M"][i], rtol=0, atol=1e-9 * scale)
+        nl = int(inj["nlam"][i])
+        assert nl == len(stages["lambdas"][i])
+        np.testing.assert_allclose(inj["lam"][i, :nl].cpu().numpy(), stages["lambdas"][i], rtol=1e-8, atol=1e-12 * scale)
+    pvi = inj["pv"].cpu().numpy()
+    assert np.max(np.abs(np.log10(pvi[big]) - np.log10(pv_ref[big]))) <= DLOG10_P
+    return out
+
+
+def test_run_interaction_config1_like(cuda_device):
+    """BASELINE configs[0]: n=500 cells, 50 donors, k=10, 100 SNPs (hK with q=50 -> wide branch m=510 > n)."""
+    from cellregmap_b200 import run_interaction
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    from oracle import crm_port
+    d = make_data(n=500, donors=50, k=10, p=100, q=50, seed=20)
+    stages = {}
+    ref = crm_port.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK, stages=stages)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    _check_interaction(d, ref, stages, model, d.G)
+    pv, info = run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    assert pv.shape == (100,) and info["rho1"].shape == (100,)
+    big = ref[0] >= 1e-12
+    assert np.max(np.abs(np.log10(pv[big]) - np.log10(ref[0][big]))) <= DLOG10_P
+
+
+def test_run_interaction_tall_lowrank(cuda_device):
+    """Tall branch (n > m), two covariates, low-rank hK."""
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    from oracle import crm_port
+    d = make_data(n=1200, donors=60, k=6, p=40, q=5, seed=3, n_covariates=2)
+    stages = {}
+    ref = crm_port.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK, stages=stages)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    _check_interaction(d, ref, stages, model, d.G)
+
+
+def test_interaction_without_background_and_default_W(cuda_device):
+    """No hK / Ls: rho1 = [1.0] (reference :103-106); W defaults to an intercept (:70-71)."""
+    from cellregmap_b200 import CellRegMap
+    from oracle import crm_port
+    d = make_data(n=400, donors=40, k=5, p=25, q=4, seed=5)
+    stages = {}
+    ref = crm_port.CellRegMapOracle(d.y, d.E).scan_interaction(d.G, stages=stages)
+    model = CellRegMap(d.y, d.E)
+    _check_interaction(d, ref, stages, model, d.G)
+
+
+def test_interaction_permuted_contexts(cuda_device):
+    """run_interaction's idx_G lands on idx_E (reference :586): rows of E0 permuted in the tested design only."""
+    from cellregmap_b200 import run_interaction
+    from oracle import crm_port
+    d = make_data(n=300, donors=30, k=4, p=20, q=3, seed=9)
+    idx = np.random.default_rng(1).permutation(300)
+    ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK, idx_G=idx)
+    pv, info = run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK, idx_G=idx)
+    np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+    assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= DLOG10_P
+    # and the un-permuted call afterwards is unaffected
+    pv2, _ = run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    ref2, _ = crm_port.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    assert np.max(np.abs(np.log10(pv2) - np.log10(ref2))) <= DLOG10_P
+
+
+def test_host_and_device_genotypes_agree_bitwise(cuda_device):
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    d = make_data(n=700, donors=50, k=8, p=333, q=6, seed=11)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    pv_host, info_host = model.scan_interaction(d.G)
+    pv_dev, info_dev = model.scan_interaction(torch.from_numpy(d.G).cuda())
+    np.testing.assert_array_equal(pv_host, pv_dev)
+    for k in info_host:
+        np.testing.assert_array_equal(info_host[k], info_dev[k])
+    # column sub-blocks (what an SNP shard sees) give the same per-SNP numbers
+    pv_a, _ = model.scan_interaction(np.ascontiguousarray(d.G[:, :100]))
+    pv_b, _ = model.scan_interaction(np.ascontiguousarray(d.G[:, 100:]))
+    np.testing.assert_array_equal(np.concatenate([pv_a, pv_b]), pv_host)
+
+
+def test_association_scans(cuda_device):
+    from cellregmap_b200 import run_association, run_association_fast
+    from oracle import crm_port
+    d = make_data(n=600, donors=50, k=6, p=60, q=8, seed=13)
+    ref_pv, ref_info = crm_port.run_association(d.y, d.W, d.E, d.G, hK=d.hK)
+    pv, info = run_association(d.y, d.W, d.E, d.G, hK=d.hK)
+    for key in ("rho1", "e2", "g2", "eps2"):
+        assert info[key].shape == (1,)
+        np.testing.assert_allclose(info[key], ref_info[key], rtol=RTOL_VC, atol=1e-12)
+    assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= DLOG10_P
+    ref_pf, _ = crm_port.run_association_fast(d.y, d.W, d.E, d.G, hK=d.hK)
+    pf, _ = run_association_fast(d.y, d.W, d.E, d.G, hK=d.hK)
+    assert np.max(np.abs(np.log10(pf) - np.log10(ref_pf))) <= DLOG10_P
+
+
+def test_input_validation(cuda_device):
+    from cellregmap_b200 import CellRegMap
+    d = make_data(n=100, donors=10, k=3, p=5, q=2, seed=1)
+    with pytest.raises(AssertionError):
+        CellRegMap(d.y, d.E[:50])
+    with pytest.raises(AssertionError):
+        CellRegMap(d.y, d.E, W=d.W[:, 0])
