@@ -18,6 +18,9 @@ from . import _lib
 
 EPS_SMALL = float(np.sqrt(np.finfo(float).eps))
 
+# bench.py switches this on to time the rotation kernel with CUDA events inside the library
+PROFILE = {"on": False, "rot_ms": 0.0, "rot_flops": 0.0, "rot_launches": 0}
+
 
 def _device(device=None):
     if not torch.cuda.is_available():
@@ -198,6 +201,8 @@ class CellRegMap:
             idx = torch.as_tensor(np.asarray(idx_E), device=dev)
             Etest = self._E0[idx, :].contiguous()
             _lib.call("crm_set_test_contexts", self._handle, _ptr(Etest), Etest.stride(0), _stream())
+        if PROFILE["on"]:
+            _lib.call("crm_profile", self._handle, 1, None, None, None)
         try:
             _lib.call("crm_scan_interaction", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, p, geno.on_host,
                       ctypes.c_void_p(0), 0, _ptr(out["pv"]), _ptr(out["rho1"]), _ptr(out["e2"]), _ptr(out["g2"]),
@@ -205,6 +210,12 @@ class CellRegMap:
         finally:
             if idx_E is not None:
                 _lib.call("crm_set_test_contexts", self._handle, _ptr(self._E0), self._E0.stride(0), _stream())
+        if PROFILE["on"]:
+            ms, fl, nl = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
+            _lib.call("crm_profile", self._handle, 0, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(nl))
+            PROFILE["rot_ms"] += ms.value
+            PROFILE["rot_flops"] += fl.value
+            PROFILE["rot_launches"] += nl.value
         out.update(extra)
         return out
 

@@ -41,10 +41,20 @@ def compute_maf(X):
     return np.minimum(s0, 1.0 - s0)
 
 
+def _qs_via_gram(hS):
+    ev, V = np.linalg.eigh(hS.T @ hS)
+    keep = ev > 1e-12 * ev[-1]
+    ev, V = ev[keep][::-1], V[:, keep][:, ::-1]
+    return ((hS @ V) / np.sqrt(ev),), ev
+
+
 class CellRegMapOracle:
     """_cellregmap.py:23-440."""
 
-    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None):
+    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None, qs_method="svd"):
+        """`qs_method="gram"` obtains the same (Q0, S0) from the eigendecomposition of hS'hS instead of a thin SVD
+        of hS; it exists only to bound the set-up time of the CPU baseline at n = 1e5 (bench.py) and is not the
+        reference's route (numpy_sugar.economic_qs_linear)."""
         self.y = np.asarray(y, float).flatten()
         self.E0 = np.asarray(E, float)
         n = self.y.shape[0]
@@ -68,7 +78,7 @@ class CellRegMapOracle:
                 hS = self.E1
             else:
                 hS = np.concatenate([np.sqrt(rho) * self.E1] + [np.sqrt(1 - rho) * B for B in blocks], axis=1)
-            self.QS[rho] = economic_qs_linear(hS, return_q1=False)
+            self.QS[rho] = economic_qs_linear(hS, return_q1=False) if qs_method == "svd" else _qs_via_gram(hS)
 
     @property
     def n_samples(self):
@@ -171,12 +181,12 @@ class CellRegMapOracle:
         return np.asarray(beta_g_s), np.stack(beta_gxe_s).T
 
 
-def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None, stages=None):
+def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None, stages=None, qs_method="svd"):
     """_cellregmap.py:547-587  (idx_G lands on scan_interaction's idx_E, :586)."""
     E1 = E if E1 is None else E1
     E2 = E if E2 is None else E2
     Ls = None if hK is None else get_L_values(hK, E2)
-    crm = CellRegMapOracle(y=y, E=E, W=W, E1=E1, Ls=Ls)
+    crm = CellRegMapOracle(y=y, E=E, W=W, E1=E1, Ls=Ls, qs_method=qs_method)
     return crm.scan_interaction(G, idx_G, stages=stages)
 
 
