@@ -322,7 +322,9 @@ def run_b200_arm(a):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                              "frac": (achieved / FP64_TENSOR_PEAK_TFLOPS) if achieved else None, "traffic": None,
-                             "kernel": "crm_gemm_kernel<EXPAND> (rotation of [g, g.E] onto [H|y|W])",
+                             "kernel": ("crm_gemm_kernel<PLAIN> on the pre-expanded basis [Hx|Hx.E_j] (rotation of [g, g.E] onto [H|y|W])"
+                                        if api.PROFILE.get("pre_expanded_basis") else
+                                        "crm_gemm_kernel<EXPAND> (rotation of [g, g.E] onto [H|y|W], Hadamard on the fly)"),
                              "algorithmic_flop_per_test": 2.0 * a.cells * a.contexts * (1 + a.hk_rank) * (1 + a.contexts),
                              "launches": int(rot_launches), "ms_per_launch": rot_ms / max(1, rot_launches),
                              "share_of_step": rot_ms / ms_total if ms_total else None,

@@ -4,6 +4,7 @@ from ._types import Term
 from ._cellregmap import (
     CellRegMap,
     compute_maf,
+    estimate_betas,
     get_L_values,
     lrt_pvalues,
     run_association,
@@ -19,6 +20,7 @@ __all__ = [
     "run_association",
     "run_association_fast",
     "run_interaction",
+    "estimate_betas",
     "get_L_values",
     "compute_maf",
     "lrt_pvalues",

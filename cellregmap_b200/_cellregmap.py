@@ -132,6 +132,7 @@ class CellRegMap:
         assert n == self._W.shape[0]
         assert n == self._E0.shape[0]
         assert n == self._E1.shape[0]
+        self._background_from_Ls = n_blocks > 0
         if n_blocks == 0:
             if hK is None:
                 self._rho1 = [1.0]                       # reference :103-106
@@ -151,18 +152,20 @@ class CellRegMap:
                   self._E0.stride(0), _ptr(self._E1), self._E1.stride(0), _ptr(Lcat), 0 if Lcat is None else Lcat.stride(0),
                   n, int(self._W.shape[1]), int(self._E0.shape[1]), int(self._E1.shape[1]), mL,
                   rho.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(rho.shape[0]), _stream())
-        dims = (ctypes.c_int64 * 7)()
+        dims = (ctypes.c_int64 * 8)()
         _lib.call("crm_get_dims", self._handle, dims)
-        self._dims = {"n": dims[0], "c": dims[1], "k0": dims[2], "m": dims[3], "R": dims[4], "mp": dims[5], "max_rank": dims[6]}
+        self._dims = {"n": dims[0], "c": dims[1], "k0": dims[2], "m": dims[3], "R": dims[4], "mp": dims[5], "max_rank": dims[6],
+                      "pre_expanded_basis": bool(dims[7])}
+        PROFILE["pre_expanded_basis"] = bool(dims[7])
 
     def __del__(self):
         h = getattr(self, "_handle", None)
         if h is not None and h.value:
             try:
                 _lib.load().crm_destroy(h)
-            except Exception:
+                h.value = None
+            except Exception:   # interpreter shutdown
                 pass
-            self._handle = ctypes.c_void_p(0)
 
     @property
     def n_samples(self):
@@ -195,8 +198,13 @@ class CellRegMap:
             ov1 = _to_dev(overrides["v1"], dev)
             keep += [ridx, ov0, ov1]
             diag.ov_rho_idx, diag.ov_v0, diag.ov_v1 = ridx.data_ptr(), ov0.data_ptr(), ov1.data_ptr()
-        if idx_G is not None:
-            raise NotImplementedError("scan_interaction(idx_G=...) (permuted tested genotypes) is not available yet")
+        gtest = None
+        if idx_G is not None:      # row-permuted genotypes in the tested design only (reference :410-413)
+            if geno.on_host:
+                src = geno.keep if isinstance(geno.keep, np.ndarray) else geno.keep.numpy()
+                gtest = _Genotypes(np.ascontiguousarray(src[np.asarray(idx_G), :]), dev, self.n_samples)
+            else:
+                gtest = _Genotypes(geno.keep[torch.as_tensor(np.asarray(idx_G), device=dev), :].contiguous(), dev, self.n_samples)
         if idx_E is not None:      # row-permuted contexts in the tested design only (reference :398-401)
             idx = torch.as_tensor(np.asarray(idx_E), device=dev)
             Etest = self._E0[idx, :].contiguous()
@@ -205,7 +213,7 @@ class CellRegMap:
             _lib.call("crm_profile", self._handle, 1, None, None, None)
         try:
             _lib.call("crm_scan_interaction", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, p, geno.on_host,
-                      ctypes.c_void_p(0), 0, _ptr(out["pv"]), _ptr(out["rho1"]), _ptr(out["e2"]), _ptr(out["g2"]),
+                      ctypes.c_void_p(gtest.ptr if gtest is not None else 0), gtest.ld if gtest is not None else 0, _ptr(out["pv"]), _ptr(out["rho1"]), _ptr(out["e2"]), _ptr(out["g2"]),
                       _ptr(out["eps2"]), ctypes.byref(diag), _stream())
         finally:
             if idx_E is not None:
@@ -245,6 +253,24 @@ class CellRegMap:
         info = {"rho1": i4[0:1].copy(), "e2": i4[1:2].copy(), "g2": i4[2:3].copy(), "eps2": i4[3:4].copy()}
         self._last_association = {"alt_lml": alt, "null_lml": null}
         return pv.cpu().numpy(), info
+
+    def predict_interaction(self, G, MAF):
+        """Effect sizes of every column of G (reference :137-205): persistent effect beta_g (p,) and per-cell GxC effects
+        beta_gxe (1, n, p).  Like the reference, only the Ls background enters this model (hK given to the constructor
+        is not used here) and MAF must lie strictly between 0 and 1."""
+        dev = self._device
+        torch.cuda.set_device(dev)
+        geno = _Genotypes(G, dev, self.n_samples)
+        p, n = geno.p, self.n_samples
+        maf = _to_dev(np.atleast_1d(np.asarray(MAF.detach().cpu().numpy() if isinstance(MAF, torch.Tensor) else MAF, float)), dev)
+        assert maf.numel() == p, "one MAF per SNP"
+        beta_g = torch.empty(p, dtype=torch.float64, device=dev)
+        beta_gxe = torch.empty((n, p), dtype=torch.float64, device=dev)
+        rho1 = torch.empty(p, dtype=torch.float64, device=dev)
+        _lib.call("crm_predict_interaction", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, p, geno.on_host, _ptr(maf),
+                  1 if self._background_from_Ls else 0, _ptr(beta_g), _ptr(beta_gxe), p, _ptr(rho1), _stream())
+        self._last_predict = {"rho1": rho1}
+        return beta_g.cpu().numpy(), beta_gxe.cpu().numpy().reshape(1, n, p)
 
     def scan_association(self, G):
         """LRT for a persistent effect of every column of G (reference :246-281)."""
@@ -292,6 +318,14 @@ def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None):
     positional argument, i.e. it permutes the rows of E (reference :586); kept."""
     crm = _make_interaction_model(y, E, W, E1, E2, hK)
     return crm.scan_interaction(G, idx_G)
+
+
+def estimate_betas(y, W, E, G, maf=None, E1=None, E2=None, hK=None):
+    """Effect-size estimator (reference :640-682): returns (beta_g (p,), beta_gxe (1, n, p))."""
+    crm = _make_interaction_model(y, E, W, E1, E2, hK)
+    if maf is None:
+        maf = compute_maf(G)
+    return crm.predict_interaction(G, maf)
 
 
 def compute_maf(X):

@@ -45,6 +45,8 @@ SIGNATURES = {
                                             c_double_p, ctypes.POINTER(ScanDiag), ctypes.c_void_p]),
     "crm_scan_association": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                             ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, ctypes.c_void_p]),
+    "crm_predict_interaction": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_double_p,
+                                               ctypes.c_int, c_double_p, c_double_p, ctypes.c_int64, c_double_p, ctypes.c_void_p]),
     "crm_launch_count": (ctypes.c_longlong, []),
     "crm_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_int64)]),

@@ -2,10 +2,12 @@
 // Host orchestration only: set-up of the per-gene state, batching of SNPs, kernel launches.
 #include <cusolverDn.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/crm_b200.h"
@@ -52,6 +54,12 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
+// Creating a cuSOLVER handle costs tens of milliseconds, so one context per device lives in a process-wide pool and is
+// reused by every model object (set-up calls are serialised by the pool mutex).
+struct EigCtx { cusolverDnHandle_t solver = nullptr; cusolverDnParams_t params = nullptr; DevBuf mat, val, work; std::vector<char> host_work; };
+struct EigPool { std::mutex mu; std::vector<EigCtx> ctx; };
+static EigPool g_eig_pool[16];
+
 struct Handle {
     int device = 0;
     bool ready = false;
@@ -61,12 +69,14 @@ struct Handle {
     int m = 0, mp = 0, Mx = 0, ldH = 0, kexp = 0, epitch = 0, M2 = 0, ld2 = 0, max_rank = 0;
     std::vector<double> rho;
     // per-gene state
+    DevBuf HxE;           // optional n x (kexp * ldH) pre-expanded basis [Hx | Hx.E0_1 | ... | Hx.E0_k] (see launch_rotation)
+    bool use_hxe = false;
     DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
     // null-model state for the association scans
     // scan workspaces
     DevBuf C, sq, Hg, gr, Vg, GEr, fit_lml, fit_delta, fit_scale, fit_beta, fit_x, fit_nfev, fit_flags;
+    DevBuf Ys, sgram, HY, Zs, lin, Zp, ucoef, coef;
     DevBuf rho_idx, best_lml, v0, v1, perm, offsets, Q, lam, nlam, sflags, liu, ifault, conv, gchunk[2], gtchunk[2], scratch;
-    cusolverDnHandle_t solver = nullptr;
     // optional timing of the rotation kernel (K1, EXPAND mode) with events on the launching stream
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_events;
@@ -74,10 +84,10 @@ struct Handle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     void free_all() {
-        DevBuf* all[] = {&Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
+        DevBuf* all[] = {&HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
-                         &gtchunk[0], &gtchunk[1], &scratch};
+                         &gtchunk[0], &gtchunk[1], &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -90,6 +100,15 @@ __global__ void build_eext_kernel(const double* E0, long long lde0, long long n,
     if (idx >= n * epitch) return;
     const long long i = idx / epitch; const int j = (int)(idx - i * epitch);
     Eext[idx] = (j == 0) ? 1.0 : (j <= k0 ? E0[i * lde0 + (j - 1)] : 0.0);
+}
+// HxE[i][j * ldH + a] = Eext[i][j] * Hx[i][a]   (j = 0: Hx itself)
+__global__ void build_hxe_kernel(const double* Hx, int ldH, const double* Eext, int epitch, int kexp, long long n, double* out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ld = (long long)kexp * ldH;
+    if (idx >= n * ld) return;
+    const long long i = idx / ld; const long long r = idx - i * ld;
+    const int j = (int)(r / ldH), a = (int)(r - (long long)j * ldH);
+    out[idx] = Eext[i * epitch + j] * Hx[i * ldH + a];
 }
 // A2 = [1 | E0 | E0_j * E0_l (j >= l, packed)]
 __global__ void build_a2_kernel(const double* E0, long long lde0, long long n, int k0, double* A2, int ld2) {
@@ -186,6 +205,37 @@ __global__ void copy_strided_kernel(const double* src, long long src_ld, long lo
     dst[r * dst_ld + cidx] = src[r * src_ld + cidx];
 }
 
+// Ys = [y | W | E0] (n x ld) from Hx (columns m.. ) and Eext (columns 1..k0)
+__global__ void build_ys_kernel(const double* Hx, int ldH, int m, int c, const double* Eext, int epitch, int k0, long long n, double* Ys, int ld) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * ld) return;
+    const long long i = idx / ld; const int j = (int)(idx - i * ld);
+    double v = 0.0;
+    if (j <= c) v = Hx[i * ldH + m + j];
+    else if (j < 1 + c + k0) v = Eext[i * epitch + 1 + (j - 1 - c)];
+    Ys[idx] = v;
+}
+// out[col][i] = sum_a Tt[a][off + i] HY[col][a]
+__global__ void apply_basis_kernel(const double* Tt, long long ldt, long long off, const double* HY, long long ldhy, int m, int mp, int ncol, double* out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)ncol * mp) return;
+    const int col = (int)(idx / mp), i = (int)(idx - (long long)col * mp);
+    double s = 0.0;
+    for (int a = 0; a < m; a++) s += Tt[(long long)a * ldt + off + i] * HY[(long long)col * ldhy + a];
+    out[idx] = s;
+}
+// best rho per SNP -> persistent effect and BLUP coefficients: beta_g = beta[c], coef = v0 rho ucoef / sqrt(2 maf (1 - maf))
+__global__ void finalize_betas_kernel(const int* rho_idx, const double* v0, const double* grid, const double* beta, const double* ucoef,
+                                      const double* maf, int R, int P, int c, int k0, long long p, double* beta_g, double* coef) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p) return;
+    const int r = rho_idx[s];
+    const long long o = s * R + r;
+    beta_g[s] = beta[o * P + c];
+    const double f = maf[s], norm = 1.0 / sqrt(2.0 * f * (1.0 - f)), w = v0[s] * grid[r] * norm;
+    for (int j = 0; j < k0; j++) coef[s * k0 + j] = w * ucoef[o * k0 + j];
+}
+
 static inline unsigned blocks_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
 
 // ------------------------------------------------------------------------------------------------
@@ -196,7 +246,29 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
     CRM_CUDA(cudaGetLastError()); count_launch();
     build_a2_kernel<<<blocks_for(h->n * h->ld2, 256), 256, 0, st>>>(E0, lde0, h->n, h->k0, h->A2.as<double>(), h->ld2);
     CRM_CUDA(cudaGetLastError()); count_launch();
+    if (h->use_hxe) {
+        build_hxe_kernel<<<blocks_for(h->n * h->kexp * h->ldH, 256), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, h->n,
+                                                                                   h->HxE.as<double>());
+        CRM_CUDA(cudaGetLastError()); count_launch();
+    }
     return CRM_OK;
+}
+
+// Rotation of [g, g.E0_1, ..., g.E0_k] onto [H | y | W] for B SNP columns: C[(s*kexp + j)][a].
+// Two equivalent routes through K1: with the pre-expanded basis HxE the Hadamard factor sits on the basis side and the
+// loop is a plain DMMA contraction (99% of the FP64 tensor peak, costs n*kexp*ldH*8 bytes of HBM once per gene); without
+// it the factor is applied to the genotype fragments on the fly (EXPAND mode, ~90% of peak, no extra memory).
+static int launch_rotation(Handle* h, const double* G, long long ldg, long long gcols, long long B, double* C, cudaStream_t st) {
+    GemmOperands op{};
+    op.B = G; op.ldb = ldg; op.b_cols = gcols;
+    if (h->use_hxe) {
+        const long long ldE = (long long)h->kexp * h->ldH;
+        op.A = h->HxE.as<double>(); op.lda = ldE; op.a_cols = ldE; op.B2 = G; op.ldb2 = ldg; op.b2_cols = gcols;
+        return launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, (int)ldE, 0, (int)B, C, ldE, 1, st);
+    }
+    op.A = h->Hx.as<double>(); op.lda = h->ldH; op.a_cols = h->Mx;
+    op.B2 = h->Eext.as<double>(); op.ldb2 = h->epitch; op.b2_cols = h->epitch;
+    return launch_gemm(GEMM_EXPAND, op, (int)h->n, 0, h->Mx, 0, (int)(B * h->kexp), C, h->ldH, h->kexp, st);
 }
 
 static int do_setup(Handle* h, const double* y, const double* W, long long ldw, const double* E0, long long lde0, const double* E1,
@@ -233,9 +305,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     CRM_CHECK(h->Wr.reserve((size_t)R * c * mp * 8));
     CRM_CHECK(h->Tt.reserve((size_t)m * R * mp * 8));
     CRM_CHECK(h->stats.reserve((size_t)(1 + c + c * c + R + 4) * 8));
-    CRM_CHECK(h->eigmat.reserve((size_t)m * m * 8));
-    CRM_CHECK(h->eigval.reserve((size_t)m * 8));
-    CRM_CHECK(h->devinfo.reserve((size_t)(R + 8) * sizeof(int)));
+    CRM_CHECK(h->devinfo.reserve((size_t)(2 * R + 8) * sizeof(int)));
 
     // Hx = [E1 | L | y | W]
     double* Hx = h->Hx.as<double>();
@@ -244,6 +314,14 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     if (mL > 0) CRM_CUDA(cudaMemcpy2DAsync(Hx + k1, (size_t)ldH * 8, L, (size_t)ldl * 8, (size_t)mL * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
     CRM_CUDA(cudaMemcpy2DAsync(Hx + m, (size_t)ldH * 8, y, 8, 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
     CRM_CUDA(cudaMemcpy2DAsync(Hx + m + 1, (size_t)ldH * 8, W, (size_t)ldw * 8, (size_t)c * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    {   // pre-expanded basis when it fits comfortably (CRM_NO_HXE=1 forces the on-the-fly route)
+        const size_t bytes = (size_t)n * h->kexp * ldH * 8;
+        size_t free_b = 0, total_b = 0;
+        CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const char* env = getenv("CRM_NO_HXE");
+        h->use_hxe = !(env && atoi(env) != 0) && (h->HxE.cap >= bytes || bytes < (size_t)(0.30 * (double)(free_b + h->HxE.cap))) && (long long)h->kexp * ldH < 2000000000LL;
+        if (h->use_hxe) CRM_CHECK(h->HxE.reserve(bytes)); else h->HxE.release();
+    }
     CRM_CHECK(build_test_contexts(h, E0, lde0, st));
 
     // Gram of [H | y | W] by the K1 kernel (plain mode): H'H, H'y, H'W, y'y, W'y, W'W
@@ -255,34 +333,70 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     extract_stats_kernel<<<1, 64, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
 
-    // per-rho eigendecomposition (cuSOLVER, one-off per gene)
-    if (!h->solver) CRM_SOLVER(cusolverDnCreate(&h->solver));
-    CRM_SOLVER(cusolverDnSetStream(h->solver, st));
+    // per-rho eigendecomposition (cuSOLVER Dsyevd, one-off per gene).  Measured on B200: 12 ms per 1020 x 1020 problem;
+    // running the R problems on R streams (with or without one host thread each) does not overlap them, so they are
+    // issued back to back on the caller's stream with one pooled cuSOLVER context per device.
+    if (h->device < 0 || h->device >= 16) { set_error("device index %d outside the supported range", h->device); return CRM_ERR_UNSUPPORTED; }
+    EigPool& pool = g_eig_pool[h->device];
+    std::lock_guard<std::mutex> pool_lock(pool.mu);
+    if (pool.ctx.empty()) pool.ctx.resize(1);
+    EigCtx& e = pool.ctx[0];
+    if (!e.solver) CRM_SOLVER(cusolverDnCreate(&e.solver));
+    CRM_SOLVER(cusolverDnSetStream(e.solver, st));
+    CRM_CHECK(e.mat.reserve((size_t)m * m * 8));
+    CRM_CHECK(e.val.reserve((size_t)m * 8));
     int lwork = 0;
-    CRM_SOLVER(cusolverDnDsyevd_bufferSize(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, h->eigmat.as<double>(), m,
-                                          h->eigval.as<double>(), &lwork));
-    CRM_CHECK(h->eigwork.reserve((size_t)lwork * 8));
-    int* rank_dev = h->devinfo.as<int>() + 4;
+    CRM_SOLVER(cusolverDnDsyevd_bufferSize(e.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, e.mat.as<double>(), m, e.val.as<double>(), &lwork));
+    CRM_CHECK(e.work.reserve((size_t)lwork * 8));
+    int* info_dev = h->devinfo.as<int>();
+    int* rank_dev = h->devinfo.as<int>() + R;
     const int tall = n > m ? 1 : 0;
-    for (int r = 0; r < R; r++) {
-        scale_gram_kernel<<<blocks_for((long long)m * m, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, m, k1, h->rho[r], h->eigmat.as<double>());
-        CRM_CUDA(cudaGetLastError()); count_launch();
-        CRM_SOLVER(cusolverDnDsyevd(h->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, h->eigmat.as<double>(), m,
-                                    h->eigval.as<double>(), h->eigwork.as<double>(), lwork, h->devinfo.as<int>()));
-        build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
-            h->eigmat.as<double>(), h->eigval.as<double>(), m, mp, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
-            h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
-        CRM_CUDA(cudaGetLastError()); count_launch();
+    static const bool batched = [] { const char* v = getenv("CRM_EIG_BATCHED"); return v && atoi(v) != 0; }();
+    if (batched) {
+        // experiment: all grid points in one cusolverDnXsyevBatched call
+        CRM_CHECK(e.mat.reserve((size_t)R * m * m * 8));
+        CRM_CHECK(e.val.reserve((size_t)R * m * 8));
+        if (!e.params) CRM_SOLVER(cusolverDnCreateParams(&e.params));
+        for (int r = 0; r < R; r++) {
+            scale_gram_kernel<<<blocks_for((long long)m * m, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, m, k1, h->rho[r], e.mat.as<double>() + (size_t)r * m * m);
+            CRM_CUDA(cudaGetLastError()); count_launch();
+        }
+        size_t ws_dev = 0, ws_host = 0;
+        CRM_SOLVER(cusolverDnXsyevBatched_bufferSize(e.solver, e.params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, CUDA_R_64F, e.mat.ptr, m, CUDA_R_64F,
+                                                     e.val.ptr, CUDA_R_64F, &ws_dev, &ws_host, R));
+        CRM_CHECK(e.work.reserve(ws_dev + 256));
+        if (e.host_work.size() < ws_host + 16) e.host_work.resize(ws_host + 16);
+        CRM_SOLVER(cusolverDnXsyevBatched(e.solver, e.params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, CUDA_R_64F, e.mat.ptr, m, CUDA_R_64F, e.val.ptr,
+                                          CUDA_R_64F, e.work.ptr, ws_dev, e.host_work.data(), ws_host, info_dev, R));
+        for (int r = 0; r < R; r++) {
+            build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
+                e.mat.as<double>() + (size_t)r * m * m, e.val.as<double>() + (size_t)r * m, m, mp, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
+                h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
+            CRM_CUDA(cudaGetLastError()); count_launch();
+        }
+    } else {
+        for (int r = 0; r < R; r++) {
+            scale_gram_kernel<<<blocks_for((long long)m * m, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, m, k1, h->rho[r], e.mat.as<double>());
+            CRM_CUDA(cudaGetLastError()); count_launch();
+            CRM_SOLVER(cusolverDnDsyevd(e.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, e.mat.as<double>(), m, e.val.as<double>(),
+                                        e.work.as<double>(), lwork, info_dev + r));
+            build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
+                e.mat.as<double>(), e.val.as<double>(), m, mp, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
+                h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
+            CRM_CUDA(cudaGetLastError()); count_launch();
+        }
     }
     rotate_null_kernel<<<blocks_for((long long)R * mp, 128), 128, 0, st>>>(h->Tt.as<double>(), (long long)R * mp, h->gram.as<double>(), ldH, m,
                                                                          mp, R, c, h->yr.as<double>(), h->Wr.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
-    std::vector<int> info(R + 8, 0);
-    CRM_CUDA(cudaMemcpyAsync(info.data(), h->devinfo.as<int>(), (size_t)(R + 4) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    std::vector<int> info(2 * R, 0);
+    CRM_CUDA(cudaMemcpyAsync(info.data(), h->devinfo.as<int>(), (size_t)(2 * R) * sizeof(int), cudaMemcpyDeviceToHost, st));
     CRM_CUDA(cudaStreamSynchronize(st));
-    if (info[0] != 0) { set_error("cusolverDnDsyevd did not converge (devInfo=%d)", info[0]); return CRM_ERR_SOLVER; }
     h->max_rank = 0;
-    for (int r = 0; r < R; r++) h->max_rank = std::max(h->max_rank, info[4 + r]);
+    for (int r = 0; r < R; r++) {
+        if (info[r] != 0) { set_error("cusolverDnDsyevd did not converge for grid point %d (devInfo=%d)", r, info[r]); return CRM_ERR_SOLVER; }
+        h->max_rank = std::max(h->max_rank, info[R + r]);
+    }
     h->ready = true;
     return CRM_OK;
 }
@@ -342,14 +456,63 @@ static int ensure_streams(Handle* h) {
     return CRM_OK;
 }
 
-// Stage a column block [s0, s0+B) of a host matrix into a device chunk buffer (ld = Bp) on the copy stream.
-static int stage_host_block(Handle* h, const double* G, long long ldg, long long s0, long long B, long long Bp, DevBuf& buf, int slot,
-                            cudaStream_t compute) {
-    CRM_CHECK(buf.reserve((size_t)h->n * Bp * 8));
+// Stage the column block [s0, s0+B) of a host matrix (and of the optional second one) into the device chunk buffers of
+// `slot` (ld = Bp) on the copy stream.
+static int stage_host_block(Handle* h, const double* G, long long ldg, const double* G2, long long ldg2, long long s0, long long B,
+                            long long Bp, int slot) {
+    CRM_CHECK(h->gchunk[slot].reserve((size_t)h->n * Bp * 8));
+    if (G2) CRM_CHECK(h->gtchunk[slot].reserve((size_t)h->n * Bp * 8));
     CRM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // previous consumer of this slot
-    CRM_CUDA(cudaMemcpy2DAsync(buf.ptr, (size_t)Bp * 8, G + s0, (size_t)ldg * 8, (size_t)B * 8, (size_t)h->n, cudaMemcpyHostToDevice, h->copy_stream));
+    CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[slot].ptr, (size_t)Bp * 8, G + s0, (size_t)ldg * 8, (size_t)B * 8, (size_t)h->n, cudaMemcpyHostToDevice, h->copy_stream));
+    if (G2) CRM_CUDA(cudaMemcpy2DAsync(h->gtchunk[slot].ptr, (size_t)Bp * 8, G2 + s0, (size_t)ldg2 * 8, (size_t)B * 8, (size_t)h->n, cudaMemcpyHostToDevice, h->copy_stream));
     CRM_CUDA(cudaEventRecord(h->ev_copy[slot], h->copy_stream));
-    (void)compute;
+    return CRM_OK;
+}
+
+// A block of SNP columns as the kernels see it: device pointer, leading dimension, number of addressable columns.
+struct GBlock { const double* G; long long ld; long long cols; const double* G2; long long ld2; long long b; long long s0; };
+
+// Walks the columns of G (and of the optional second matrix G2) in blocks of at most B columns.  Device-resident
+// input is used in place when TMA can address it (16-byte aligned base, even leading dimension, even first column),
+// otherwise the block is repacked; host-resident input is staged through double-buffered chunks on the copy stream
+// so that the copy of block i+1 overlaps the compute of block i.
+template <class F>
+static int for_each_block(Handle* h, const double* G, long long ldg, const double* G2, long long ldg2, long long p, int on_host,
+                          long long B, cudaStream_t st, F&& fn) {
+    if (!on_host) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(G) & 15) == 0) && (ldg % 2 == 0);
+        const bool aligned2 = !G2 || (((reinterpret_cast<uintptr_t>(G2) & 15) == 0) && (ldg2 % 2 == 0));
+        for (long long s0 = 0; s0 < p; s0 += B) {
+            const long long b = std::min(B, p - s0), bp = round_up(b, 2);
+            GBlock blk{G + s0, ldg, p - s0, G2 ? G2 + s0 : nullptr, ldg2, b, s0};
+            if (!aligned || !aligned2 || (s0 & 1)) {
+                CRM_CHECK(h->gchunk[0].reserve((size_t)h->n * bp * 8));
+                CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+                blk.G = h->gchunk[0].as<double>(); blk.ld = bp; blk.cols = b;
+                if (G2) {
+                    CRM_CHECK(h->gtchunk[0].reserve((size_t)h->n * bp * 8));
+                    CRM_CUDA(cudaMemcpy2DAsync(h->gtchunk[0].ptr, (size_t)bp * 8, G2 + s0, (size_t)ldg2 * 8, (size_t)b * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+                    blk.G2 = h->gtchunk[0].as<double>(); blk.ld2 = bp;
+                }
+            }
+            CRM_CHECK(fn(blk));
+        }
+        return CRM_OK;
+    }
+    CRM_CHECK(ensure_streams(h));
+    const long long nb = (p + B - 1) / B, Bp = round_up(B, 2);
+    CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
+    CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
+    CRM_CHECK(stage_host_block(h, G, ldg, G2, ldg2, 0, std::min(B, p), Bp, 0));
+    for (long long ib = 0; ib < nb; ib++) {
+        const int slot = (int)(ib & 1);
+        const long long s0 = ib * B, b = std::min(B, p - s0);
+        if (ib + 1 < nb) CRM_CHECK(stage_host_block(h, G, ldg, G2, ldg2, s0 + B, std::min(B, p - s0 - B), Bp, slot ^ 1));
+        CRM_CUDA(cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
+        GBlock blk{h->gchunk[slot].as<double>(), Bp, b, G2 ? h->gtchunk[slot].as<double>() : nullptr, Bp, b, s0};
+        CRM_CHECK(fn(blk));
+        CRM_CUDA(cudaEventRecord(h->ev_done[slot], st));
+    }
     return CRM_OK;
 }
 
@@ -360,21 +523,15 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     double* C = h->C.as<double>();
     double* sq = h->sq.as<double>();
     // 1. rotation of [g, g.E0] onto [H | y | W]
-    {
-        GemmOperands op{};
-        op.A = h->Hx.as<double>(); op.lda = ldH; op.a_cols = Mx;
-        op.B = Gt ? Gt : Gd; op.ldb = Gt ? ldgt : ldg; op.b_cols = gcols;
-        op.B2 = h->Eext.as<double>(); op.ldb2 = h->epitch; op.b2_cols = h->epitch;
-        if (h->prof_on) {
-            cudaEvent_t e0, e1;
-            CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
-            CRM_CUDA(cudaEventRecord(e0, st));
-            h->prof_events.push_back(e0); h->prof_events.push_back(e1);
-            h->prof_flops += 2.0 * (double)h->n * (double)h->m * (double)kexp * (double)B;   // algorithmic: 2 n m (1+k) per SNP
-        }
-        CRM_CHECK(launch_gemm(GEMM_EXPAND, op, (int)h->n, 0, Mx, 0, (int)(B * kexp), C, ldH, kexp, st));
-        if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_events.back(), st));
+    if (h->prof_on) {
+        cudaEvent_t e0, e1;
+        CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
+        CRM_CUDA(cudaEventRecord(e0, st));
+        h->prof_events.push_back(e0); h->prof_events.push_back(e1);
+        h->prof_flops += 2.0 * (double)h->n * (double)h->m * (double)kexp * (double)B;   // algorithmic: 2 n m (1+k) per SNP
     }
+    CRM_CHECK(launch_rotation(h, Gt ? Gt : Gd, Gt ? ldgt : ldg, gcols, B, C, st));
+    if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_events.back(), st));
     // 2. squared-genotype Grams against [1 | E0 | pairs]:  g'g, (g.E0)'g, (g.E0)'(g.E0)
     {
         GemmOperands op{};
@@ -384,10 +541,18 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
         CRM_CHECK(launch_gemm(GEMM_PRODUCT, op, (int)h->n, 0, h->M2, 0, (int)B, sq, h->ld2, 1, st));
     }
     if (Gt) {
-        // permuted tested genotypes: the null design still uses g itself -> overwrite row j=0 of C with the rotation of g,
-        // column 0 of sq with g'g and the (g.E0)'g block with (gt * g)' E0
-        set_error("idx_G (permuted tested genotypes) is not implemented in this build");
-        return CRM_ERR_UNSUPPORTED;
+        // permuted tested genotypes (idx_G, reference :410-413): the null design still uses g itself, so the j = 0 rows of C
+        // are overwritten with the rotation of g, column 0 of sq with g'g and columns 1..k with (gt * g)' E0
+        GemmOperands op{};
+        op.A = h->Hx.as<double>(); op.lda = ldH; op.a_cols = Mx;
+        op.B = Gd; op.ldb = ldg; op.b_cols = gcols; op.B2 = Gd; op.ldb2 = ldg; op.b2_cols = gcols;
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, Mx, 0, (int)B, C, (long long)kexp * ldH, 1, st));
+        GemmOperands o2{};
+        o2.A = h->A2.as<double>(); o2.lda = h->ld2; o2.a_cols = h->M2;
+        o2.B = Gd; o2.ldb = ldg; o2.b_cols = gcols; o2.B2 = Gd; o2.ldb2 = ldg; o2.b2_cols = gcols;
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->n, 0, 1, 0, (int)B, sq, h->ld2, 1, st));
+        o2.B2 = Gt; o2.ldb2 = ldgt;
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->n, 1, k, 0, (int)B, sq + 1, h->ld2, 1, st));
     }
     // 3. H'g as a K-outer operand, 4. rotated genotype for every rho
     const long long ldhg = round_up(B, 2);
@@ -483,39 +648,9 @@ static int do_scan_interaction(Handle* h, const double* G, long long ldg, long l
     long long B = pick_batch(h, p, true);
     if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->n))));
     CRM_CHECK(reserve_scan(h, B, true));
-    if (!g_on_host) {
-        const bool aligned = ((reinterpret_cast<uintptr_t>(G) & 15) == 0) && (ldg % 2 == 0);
-        for (long long s0 = 0; s0 < p; s0 += B) {
-            const long long b = std::min(B, p - s0);
-            const double* Gd = G + s0; long long ld = ldg, cols = p - s0;
-            const double* Gt = Gtest ? Gtest + s0 : nullptr;
-            if (!aligned || (s0 & 1)) {   // TMA needs a 16-byte aligned base and an even leading dimension: repack the block
-                const long long bp = round_up(b, 2);
-                CRM_CHECK(h->gchunk[0].reserve((size_t)h->n * bp * 8));
-                CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
-                Gd = h->gchunk[0].as<double>(); ld = bp; cols = b;
-            }
-            CRM_CHECK(interaction_batch(h, Gd, ld, cols, Gt, ldgt, b, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, s0, st));
-        }
-        return CRM_OK;
-    }
-    // host-resident genotypes: double-buffered column blocks, copy of block i+1 overlaps compute of block i
-    CRM_CHECK(ensure_streams(h));
-    const long long nb = (p + B - 1) / B;
-    const long long Bp = round_up(B, 2);
-    CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
-    CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
-    CRM_CHECK(stage_host_block(h, G, ldg, 0, std::min(B, p), Bp, h->gchunk[0], 0, st));
-    for (long long ib = 0; ib < nb; ib++) {
-        const int slot = (int)(ib & 1);
-        const long long s0 = ib * B, b = std::min(B, p - s0);
-        if (ib + 1 < nb) CRM_CHECK(stage_host_block(h, G, ldg, s0 + B, std::min(B, p - s0 - B), Bp, h->gchunk[slot ^ 1], slot ^ 1, st));
-        CRM_CUDA(cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
-        CRM_CHECK(interaction_batch(h, h->gchunk[slot].as<double>(), Bp, b, nullptr, 0, b, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, s0, st));
-        CRM_CUDA(cudaEventRecord(h->ev_done[slot], st));
-    }
-    if (Gtest) { set_error("idx_G with host-resident genotypes is not implemented"); return CRM_ERR_UNSUPPORTED; }
-    return CRM_OK;
+    return for_each_block(h, G, ldg, Gtest, ldgt, p, g_on_host, B, st, [&](const GBlock& k) -> int {
+        return interaction_batch(h, k.G, k.ld, k.cols, k.G2, k.ld2, k.b, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, k.s0, st);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -553,29 +688,8 @@ static int do_scan_association(Handle* h, const double* G, long long ldg, long l
     CRM_CUDA(cudaMemcpyAsync(xfix, &xopt[rb], 8, cudaMemcpyHostToDevice, st));
     CRM_CUDA(cudaStreamSynchronize(st));   // host temporaries above go out of scope
     if (p == 0) return CRM_OK;
-    if (g_on_host) CRM_CHECK(ensure_streams(h));
-    const long long Bp = round_up(B, 2);
-    const long long nb = (p + B - 1) / B;
-    if (g_on_host) {
-        CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
-        CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
-        CRM_CHECK(stage_host_block(h, G, ldg, 0, std::min(B, p), Bp, h->gchunk[0], 0, st));
-    }
-    const bool aligned = ((reinterpret_cast<uintptr_t>(G) & 15) == 0) && (ldg % 2 == 0);
-    for (long long ib = 0; ib < nb; ib++) {
-        const int slot = (int)(ib & 1);
-        const long long s0 = ib * B, b = std::min(B, p - s0);
-        const double* Gd; long long ld, cols;
-        if (g_on_host) {
-            if (ib + 1 < nb) CRM_CHECK(stage_host_block(h, G, ldg, s0 + B, std::min(B, p - s0 - B), Bp, h->gchunk[slot ^ 1], slot ^ 1, st));
-            CRM_CUDA(cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
-            Gd = h->gchunk[slot].as<double>(); ld = Bp; cols = b;
-        } else if (!aligned || (s0 & 1)) {
-            const long long bp = round_up(b, 2);
-            CRM_CHECK(h->gchunk[0].reserve((size_t)h->n * bp * 8));
-            CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
-            Gd = h->gchunk[0].as<double>(); ld = bp; cols = b;
-        } else { Gd = G + s0; ld = ldg; cols = p - s0; }
+    return for_each_block(h, G, ldg, nullptr, 0, p, g_on_host, B, st, [&](const GBlock& k) -> int {
+        const double* Gd = k.G; const long long ld = k.ld, cols = k.cols, b = k.b, s0 = k.s0;
         double* C = h->C.as<double>();
         double* sq = h->sq.as<double>();
         GemmOperands op{};
@@ -600,9 +714,102 @@ static int do_scan_association(Handle* h, const double* G, long long ldg, long l
         fb.lml = out_alt ? out_alt + s0 : h->best_lml.as<double>();
         CRM_CHECK(launch_fit(fb, true, st));
         CRM_CHECK(launch_lrt(fb.lml, best, b, out_pv + s0, st));
-        if (g_on_host) CRM_CUDA(cudaEventRecord(h->ev_done[slot], st));
+        return (int)CRM_OK;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// effect sizes (predict_interaction)
+// ------------------------------------------------------------------------------------------------
+static int do_predict(Handle* h, const double* G, long long ldg, long long p, int g_on_host, const double* maf, int use_background,
+                      double* out_beta_g, double* out_beta_gxe, long long ldo, double* out_rho1, cudaStream_t st) {
+    if (!h->ready) { set_error("crm_predict_interaction: handle is not set up"); return CRM_ERR_STATE; }
+    if (!G || p < 0 || ldg < p || !maf || !out_beta_g || !out_beta_gxe || ldo < p) { set_error("crm_predict_interaction: bad arguments"); return CRM_ERR_INVALID; }
+    if (p == 0) return CRM_OK;
+    const int R = h->R, mp = h->mp, c = h->c, k0 = h->k0, kexp = h->kexp, ldH = h->ldH, Mx = h->Mx;
+    const int ns = 1 + c + k0, P = c + 1 + k0;
+    int r0 = -1;
+    for (int r = 0; r < R; r++) if (h->rho[r] == 0.0) r0 = r;
+    const int mB = (use_background && r0 >= 0 && h->mL > 0) ? h->m : 0;   // rows of the rotated background basis (0: no background)
+    // ---- per-call shared quantities ----
+    const int ldys = (int)round_up(ns, 2);
+    CRM_CHECK(h->Ys.reserve((size_t)h->n * ldys * 8));
+    CRM_CHECK(h->sgram.reserve((size_t)ns * ldys * 8 + 64));
+    CRM_CHECK(h->HY.reserve((size_t)ns * mp * 8 + 64));
+    CRM_CHECK(h->Zs.reserve((size_t)ns * mp * 8 + 64));
+    CRM_CHECK(h->scratch.reserve((size_t)(R + 16) * 8));
+    build_ys_kernel<<<blocks_for(h->n * ldys, 256), 256, 0, st>>>(h->Hx.as<double>(), ldH, h->m, c, h->Eext.as<double>(), h->epitch, k0, h->n, h->Ys.as<double>(), ldys);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    {
+        GemmOperands op{};
+        op.A = h->Ys.as<double>(); op.lda = ldys; op.a_cols = ns; op.B = op.A; op.ldb = ldys; op.b_cols = ns; op.B2 = op.A; op.ldb2 = ldys; op.b2_cols = ns;
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, ns, 0, ns, h->sgram.as<double>(), ns, 1, st));
     }
-    return CRM_OK;
+    if (mB > 0) {
+        GemmOperands op{};
+        op.A = h->Hx.as<double>(); op.lda = ldH; op.a_cols = Mx; op.B = h->Ys.as<double>(); op.ldb = ldys; op.b_cols = ns; op.B2 = op.B; op.ldb2 = ldys; op.b2_cols = ns;
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, h->m, 0, ns, h->HY.as<double>(), mp, 1, st));
+        apply_basis_kernel<<<blocks_for((long long)ns * mp, 128), 128, 0, st>>>(h->Tt.as<double>(), (long long)R * mp, (long long)r0 * mp, h->HY.as<double>(), mp, h->m, mp, ns, h->Zs.as<double>());
+        CRM_CUDA(cudaGetLastError()); count_launch();
+    }
+    double* grid_dev = h->scratch.as<double>();
+    CRM_CUDA(cudaMemcpyAsync(grid_dev, h->rho.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
+    // ---- batches ----
+    const double per_snp = 8.0 * ((double)kexp * ldH + 2.0 * h->ld2 + 2.0 * (double)kexp * mp + (double)R * (P + k0 + 8));
+    long long B = std::max<long long>(16, std::min<long long>(p, (long long)(4.0e9 / per_snp)));
+    B = std::min<long long>(B, 65535LL * GEMM_TILE_N / kexp);
+    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->n))));
+    CRM_CHECK(h->C.reserve((size_t)B * kexp * ldH * 8));
+    CRM_CHECK(h->sq.reserve((size_t)B * h->ld2 * 8));
+    CRM_CHECK(h->lin.reserve((size_t)B * h->ld2 * 8));
+    const size_t pr = (size_t)B * R;
+    CRM_CHECK(h->fit_lml.reserve(pr * 8)); CRM_CHECK(h->fit_delta.reserve(pr * 8)); CRM_CHECK(h->fit_scale.reserve(pr * 8));
+    CRM_CHECK(h->fit_beta.reserve(pr * P * 8)); CRM_CHECK(h->ucoef.reserve(pr * k0 * 8));
+    CRM_CHECK(h->fit_nfev.reserve(pr * 4)); CRM_CHECK(h->fit_flags.reserve(pr * 4));
+    CRM_CHECK(h->rho_idx.reserve((size_t)B * 4)); CRM_CHECK(h->best_lml.reserve((size_t)B * 8));
+    CRM_CHECK(h->v0.reserve((size_t)B * 8)); CRM_CHECK(h->v1.reserve((size_t)B * 8));
+    CRM_CHECK(h->coef.reserve((size_t)B * k0 * 8));
+    if (mB > 0) {
+        CRM_CHECK(h->Vg.reserve((size_t)mB * round_up(B * kexp, 2) * 8));
+        CRM_CHECK(h->Zp.reserve((size_t)B * kexp * mp * 8));
+    }
+    return for_each_block(h, G, ldg, nullptr, 0, p, g_on_host, B, st, [&](const GBlock& k) -> int {
+        const long long b = k.b, s0 = k.s0;
+        double* C = h->C.as<double>();
+        CRM_CHECK(launch_rotation(h, k.G, k.ld, k.cols, b, C, st));
+        GemmOperands o2{};
+        o2.A = h->A2.as<double>(); o2.lda = h->ld2; o2.a_cols = h->M2; o2.B = k.G; o2.ldb = k.ld; o2.b_cols = k.cols; o2.B2 = k.G; o2.ldb2 = k.ld; o2.b2_cols = k.cols;
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->n, 0, h->M2, 0, (int)b, h->sq.as<double>(), h->ld2, 1, st));
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, o2, (int)h->n, 0, h->M2, 0, (int)b, h->lin.as<double>(), h->ld2, 1, st));
+        if (mB > 0) {
+            const long long ldv = round_up(b * kexp, 2);
+            CRM_CHECK(launch_gather_transpose(C, ldH, nullptr, kexp, 0, kexp, b * kexp, mB, h->Vg.as<double>(), ldv, st));
+            GemmOperands o3{};
+            o3.A = h->Tt.as<double>(); o3.lda = (long long)R * mp; o3.a_cols = (long long)R * mp;
+            o3.B = h->Vg.as<double>(); o3.ldb = ldv; o3.b_cols = b * kexp; o3.B2 = o3.B; o3.ldb2 = ldv; o3.b2_cols = b * kexp;
+            CRM_CHECK(launch_gemm(GEMM_PLAIN, o3, mB, r0 * mp, mp, 0, (int)(b * kexp), h->Zp.as<double>(), mp, 1, st));
+        }
+        BetaArgs ba{};
+        ba.S = mB > 0 ? h->S.as<double>() + (long long)r0 * mp : nullptr; ba.Zs = h->Zs.as<double>(); ba.Zp = h->Zp.as<double>();
+        ba.shared_gram = h->sgram.as<double>();
+        ba.rot = C; ba.rot_ld = ldH; ba.col_y = h->m; ba.col_W = h->m + 1; ba.kexp = kexp;
+        ba.lin = h->lin.as<double>(); ba.lin_ld = h->ld2; ba.sq = h->sq.as<double>(); ba.sq_ld = h->ld2;
+        ba.rho = grid_dev; ba.m = mB; ba.mp = mp; ba.c = c; ba.k0 = k0; ba.R = R; ba.p = (int)b; ba.n = (double)h->n;
+        ba.lml = h->fit_lml.as<double>(); ba.delta = h->fit_delta.as<double>(); ba.scale = h->fit_scale.as<double>();
+        ba.beta = h->fit_beta.as<double>(); ba.ucoef = h->ucoef.as<double>(); ba.nfev = h->fit_nfev.as<int>(); ba.flags = h->fit_flags.as<int>();
+        CRM_CHECK(launch_beta_fit(ba, st));
+        CRM_CHECK(launch_select(ba.lml, ba.delta, ba.scale, (int)b, R, h->rho_idx.as<int>(), h->best_lml.as<double>(), h->v0.as<double>(), h->v1.as<double>(), st));
+        finalize_betas_kernel<<<blocks_for(b, 128), 128, 0, st>>>(h->rho_idx.as<int>(), h->v0.as<double>(), grid_dev, ba.beta, ba.ucoef, maf + s0, R, P, c, k0, b,
+                                                              out_beta_g + s0, h->coef.as<double>());
+        CRM_CUDA(cudaGetLastError()); count_launch();
+        if (out_rho1) {
+            finalize_interaction_kernel<<<blocks_for(b, 256), 256, 0, st>>>(h->rho_idx.as<int>(), h->v0.as<double>(), h->v1.as<double>(), grid_dev, b, out_rho1 + s0,
+                                                                           h->best_lml.as<double>(), h->best_lml.as<double>(), h->best_lml.as<double>());
+            CRM_CUDA(cudaGetLastError()); count_launch();
+        }
+        CRM_CHECK(launch_beta_gxe(h->Eext.as<double>() + 1, h->epitch, h->coef.as<double>(), k0, h->n, b, out_beta_gxe, ldo, s0, st));
+        return (int)CRM_OK;
+    });
 }
 
 }  // namespace crm
@@ -638,7 +845,6 @@ int crm_destroy(crm_handle_t h) {
     if (!h) return CRM_OK;
     cudaSetDevice(h->impl.device);
     h->impl.free_all();
-    if (h->impl.solver) cusolverDnDestroy(h->impl.solver);
     if (h->impl.copy_stream) {
         cudaStreamDestroy(h->impl.copy_stream);
         for (int i = 0; i < 2; i++) { cudaEventDestroy(h->impl.ev_copy[i]); cudaEventDestroy(h->impl.ev_done[i]); }
@@ -685,7 +891,7 @@ int crm_profile(crm_handle_t h, int enable, double* rot_ms, double* rot_flops, i
 
 int crm_get_dims(crm_handle_t h, int64_t* d) {
     if (!h || !h->impl.ready || !d) { set_error("crm_get_dims: handle not set up"); return CRM_ERR_STATE; }
-    d[0] = h->impl.n; d[1] = h->impl.c; d[2] = h->impl.k0; d[3] = h->impl.m; d[4] = h->impl.R; d[5] = h->impl.mp; d[6] = h->impl.max_rank;
+    d[0] = h->impl.n; d[1] = h->impl.c; d[2] = h->impl.k0; d[3] = h->impl.m; d[4] = h->impl.R; d[5] = h->impl.mp; d[6] = h->impl.max_rank; d[7] = h->impl.use_hxe ? 1 : 0;
     return CRM_OK;
 }
 
@@ -708,6 +914,13 @@ int crm_scan_association(crm_handle_t h, const double* G, int64_t ldg, int64_t p
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     return do_scan_association(&h->impl, G, ldg, p, g_on_host, fast, out_pv, out_alt_lml, info4, out_null_lml, (cudaStream_t)stream);
+}
+
+int crm_predict_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, const double* maf, int use_background,
+                            double* out_beta_g, double* out_beta_gxe, int64_t ldo, double* out_rho1, void* stream) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    return do_predict(&h->impl, G, ldg, p, g_on_host, maf, use_background, out_beta_g, out_beta_gxe, ldo, out_rho1, (cudaStream_t)stream);
 }
 
 int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const double* B, int64_t ldb, int64_t b_cols, const double* B2,

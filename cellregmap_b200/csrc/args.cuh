@@ -4,6 +4,9 @@
 
 namespace crm {
 
+// index of pair (j >= l) in the packed lower-triangular layout used for the E0_j * E0_l product columns
+__host__ __device__ __forceinline__ int pair_index(int j, int l) { return j * (j + 1) / 2 + l; }
+
 struct FitArgs {
     // shared per rho1 (padded leading dimension mp; entries beyond the kept rank are zero)
     const double* S;    // [R][mp]
@@ -64,5 +67,22 @@ struct PvalArgs {
 };
 
 constexpr int PV_MAXLAM = 128;
+
+// K5 (betas.cuh): effect-size model of predict_interaction, one CTA per (SNP, rho index)
+struct BetaArgs {
+    const double* S;            // [mp] spectrum of the background B = sum_i L_i L_i' (zeros beyond its rank)
+    const double* Zs;           // [1 + c + k0][mp]  rotated shared columns  Q_B'[y | W | E0]
+    const double* Zp;           // [p][1 + k0][mp]   rotated per-SNP columns Q_B'[g | g.E0]
+    const double* shared_gram;  // [(1 + c + k0)^2]  plain Gram of [y | W | E0]
+    const double* rot; long long rot_ld; int col_y, col_W, kexp;   // K1 output rows (s*kexp + j): y'(.) and W'(.) columns
+    const double* lin; long long lin_ld;   // per SNP [sum g | g'E0 (k0) | g'(E0_j E0_l) pairs]
+    const double* sq; long long sq_ld;     // per SNP [g'g | (g^2)'E0 (k0) | (g^2)'(E0_j E0_l) pairs]
+    const double* rho;          // [R] grid (device)
+    int m, mp, c, k0, R, p;
+    double n;
+    // outputs [p][R]: lml, delta, scale; beta [p][R][c + 1 + k0]; ucoef [p][R][k0] = (g.E0)' K^-1 (y - M beta)
+    double* lml; double* delta; double* scale; double* beta; double* ucoef; int* nfev; int* flags;
+};
+constexpr int BETA_MAX_NZ = 67;
 
 }  // namespace crm

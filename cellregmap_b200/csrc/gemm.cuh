@@ -24,8 +24,9 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 128;
 constexpr int GEMM_BK = 32;
 constexpr int GEMM_APITCH = 132;      // doubles; 132 % 16 == 4 -> conflict-free DMMA fragment loads
-constexpr int GEMM_CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;
+// consumer warps: (128 / (8 MT)) along M x 4 along N, each owning MT m8-tiles x 4 n8-tiles of accumulators
+__host__ __device__ constexpr int gemm_consumer_warps(int MT) { return (GEMM_BM / (8 * MT)) * 4; }
+__host__ __device__ constexpr int gemm_threads(int MT) { return (gemm_consumer_warps(MT) + 1) * 32; }
 
 struct GemmArgs {
     int K;         // contraction length (rows of A and of G)
@@ -40,21 +41,35 @@ struct GemmArgs {
     int epitch;    // EXPAND: pitch (doubles) of the Eext tile rows (= padded width of Eext)
     int stages;
     int stage_bytes;
+    int m_tiles, n_tiles;   // grid extent in tiles; the 1-D block index is rasterised in groups of GEMM_RASTER_N n-tiles
 };
+constexpr int GEMM_RASTER_N = 8;
 
-template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int MODE, int MT>
+__global__ void __launch_bounds__(gemm_threads(MT), 1)
 crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const GemmArgs args) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int GEMM_CONSUMER_WARPS = gemm_consumer_warps(MT);
+    constexpr int WARPS_M = GEMM_BM / (8 * MT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int stages = args.stages;
     const int numK = (args.K + GEMM_BK - 1) / GEMM_BK;
     // TMA needs the innermost box coordinate on a 16-byte boundary: tile origins sit on even columns, the odd
     // leading column of a range (if any) is computed and discarded.
-    const int m_tile0 = (args.m_begin & ~1) + blockIdx.x * GEMM_BM;
-    const int n_tile0 = (MODE == GEMM_EXPAND ? args.n_begin : (args.n_begin & ~1)) + blockIdx.y * GEMM_BN;
+    // Rasterisation: consecutive block indices walk GEMM_RASTER_N n-tiles for one m-tile, then the next m-tile, so the
+    // ~148 CTAs in flight share each A panel among up to 8 of them and each B panel among ~18 (L2 reuse both ways).
+    int m_tile, n_tile;
+    {
+        const int L = blockIdx.x, per_group = GEMM_RASTER_N * args.m_tiles;
+        const int group = L / per_group, within = L - group * per_group;
+        const int gn = min(GEMM_RASTER_N, args.n_tiles - group * GEMM_RASTER_N);
+        m_tile = within / gn;
+        n_tile = group * GEMM_RASTER_N + (within - m_tile * gn);
+    }
+    const int m_tile0 = (args.m_begin & ~1) + m_tile * GEMM_BM;
+    const int n_tile0 = (MODE == GEMM_EXPAND ? args.n_begin : (args.n_begin & ~1)) + n_tile * GEMM_BN;
 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * args.stage_bytes);
     uint64_t* empty = full + stages;
@@ -82,7 +97,7 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             for (int kt = 0; kt < numK; kt++) {
-                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_wait_backoff(&empty[stage], phase ^ 1);
                 unsigned char* base = smem + (size_t)stage * args.stage_bytes;
                 mbar_expect_tx(&full[stage], (uint32_t)(A_BYTES + b_bytes + b2_bytes));
                 tma_load_2d(base, &tmA, &full[stage], m_tile0, kt * GEMM_BK);
@@ -95,9 +110,9 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         return;
     }
 
-    // ---------------- consumers: 8 warps, warp tile 64 (M) x 32 (N) ----------------
-    const int wm = warp & 1, wn = warp >> 1;
-    const int a_off = t * GEMM_APITCH + wm * 64 + g;  // + 8*i, + 4*ks*APITCH
+    // ---------------- consumers: warp tile 8 MT (M) x 32 (N) ----------------
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+    const int a_off = t * GEMM_APITCH + wm * (8 * MT) + g;  // + 8*i, + 4*ks*APITCH
     int b_off[4], e_off[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -117,9 +132,9 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int b_step = 4 * ((MODE == GEMM_EXPAND) ? args.gpitch : GEMM_APITCH);
     const int e_step = 4 * ((MODE == GEMM_EXPAND) ? args.epitch : GEMM_APITCH);
 
-    double acc[8][4][2];
+    double acc[MT][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < MT; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -133,9 +148,9 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const double* B2s = reinterpret_cast<const double*>(base + A_BYTES + b_bytes);
 #pragma unroll
         for (int ks = 0; ks < GEMM_BK / 4; ks++) {
-            double a[8], b[4];
+            double a[MT], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; i++) a[i] = As[ks * 4 * GEMM_APITCH + 8 * i];
+            for (int i = 0; i < MT; i++) a[i] = As[ks * 4 * GEMM_APITCH + 8 * i];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 double v = Bs[b_off[j] + ks * b_step];
@@ -143,7 +158,7 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 b[j] = v;
             }
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < MT; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
@@ -162,8 +177,8 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (n >= n_end || n < args.n_begin) continue;
             double* row = args.out + (long long)(n - args.n_begin) * args.ldc - args.m_begin;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int m = m_tile0 + wm * 64 + 8 * i + g;
+            for (int i = 0; i < MT; i++) {
+                const int m = m_tile0 + wm * (8 * MT) + 8 * i + g;
                 if (m < m_end && m >= args.m_begin) row[m] = acc[i][j][h];
             }
         }

@@ -1,5 +1,5 @@
 // Host-side launcher of K1 (tensor-map construction + launch).
-#pragma once
+#include <stdlib.h>
 #include "gemm.cuh"
 #include "launch.cuh"
 
@@ -57,7 +57,15 @@ inline int conflict_free_pitch(int w) {
 inline int expand_box_width(int kexp) { return conflict_free_pitch((GEMM_BN - 1 + kexp - 1) / kexp + 2); }   // +1: even-aligned box start
 
 
-template <int MODE>
+// accumulator rows per warp in units of 8: 4 -> 16 consumer warps (4 per scheduler), 8 -> 8 consumer warps.
+// CRM_GEMM_MT overrides the default at load time (tuning experiments only).
+static int gemm_mt_choice() {
+    static int mt = -1;
+    if (mt < 0) { const char* e = getenv("CRM_GEMM_MT"); mt = (e && atoi(e) == 8) ? 8 : 4; }
+    return mt;
+}
+
+template <int MODE, int MT>
 int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream) {
     CUtensorMap tmA, tmB, tmB2;
     CRM_CHECK(make_map_2d(&tmA, op.A, args.K, op.a_cols, op.lda, GEMM_APITCH, GEMM_BK));
@@ -83,16 +91,19 @@ int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream)
     args.stages = stages;
     args.stage_bytes = stage_bytes;
     size_t smem = (size_t)stages * stage_bytes + 2 * stages * sizeof(uint64_t);
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[MODE]) {
-        CRM_CUDA(cudaFuncSetAttribute(crm_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set[MODE] = true;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CRM_CUDA(cudaFuncSetAttribute(crm_gemm_kernel<MODE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set = true;
     }
     const int m_span = args.m_count + (args.m_begin & 1), n_span = args.n_count + (MODE == GEMM_EXPAND ? 0 : (args.n_begin & 1));
-    dim3 grid((m_span + GEMM_BM - 1) / GEMM_BM, (n_span + GEMM_BN - 1) / GEMM_BN, 1);
-    if (grid.x == 0 || grid.y == 0) return CRM_OK;
-    if (grid.y > 65535) { set_error("GEMM N extent %d too large for one launch", args.n_count); return CRM_ERR_UNSUPPORTED; }
-    crm_gemm_kernel<MODE><<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, args);
+    args.m_tiles = (m_span + GEMM_BM - 1) / GEMM_BM;
+    args.n_tiles = (n_span + GEMM_BN - 1) / GEMM_BN;
+    if (args.m_tiles == 0 || args.n_tiles == 0) return CRM_OK;
+    const long long ctas = (long long)args.m_tiles * args.n_tiles;
+    if (ctas > 2000000000LL) { set_error("GEMM of %d x %d tiles is too large for one launch", args.m_tiles, args.n_tiles); return CRM_ERR_UNSUPPORTED; }
+    dim3 grid((unsigned)ctas, 1, 1);
+    crm_gemm_kernel<MODE, MT><<<grid, gemm_threads(MT), smem, stream>>>(tmA, tmB, tmB2, args);
     CRM_CUDA(cudaGetLastError()); count_launch();
     return CRM_OK;
 }
@@ -108,10 +119,10 @@ int launch_gemm(int mode, const GemmOperands& op, int K, int m_begin, int m_coun
         a.gpitch = expand_box_width(a.kexp);
         a.epitch = (int)op.ldb2;
         if (a.epitch < a.kexp + 1) { set_error("Eext needs at least kexp+1 columns"); return CRM_ERR_INVALID; }
-        return launch_gemm_mode<GEMM_EXPAND>(op, a, stream);
+        return gemm_mt_choice() == 8 ? launch_gemm_mode<GEMM_EXPAND, 8>(op, a, stream) : launch_gemm_mode<GEMM_EXPAND, 4>(op, a, stream);
     }
-    if (mode == GEMM_PRODUCT) return launch_gemm_mode<GEMM_PRODUCT>(op, a, stream);
-    return launch_gemm_mode<GEMM_PLAIN>(op, a, stream);
+    if (mode == GEMM_PRODUCT) return gemm_mt_choice() == 8 ? launch_gemm_mode<GEMM_PRODUCT, 8>(op, a, stream) : launch_gemm_mode<GEMM_PRODUCT, 4>(op, a, stream);
+    return gemm_mt_choice() == 8 ? launch_gemm_mode<GEMM_PLAIN, 8>(op, a, stream) : launch_gemm_mode<GEMM_PLAIN, 4>(op, a, stream);
 }
 
 }  // namespace crm

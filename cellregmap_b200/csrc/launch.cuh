@@ -31,6 +31,9 @@ int launch_group(const int* rho_idx, int p, int R, int* perm, int* offsets, cuda
 int launch_gather_transpose(const double* C, long long ldc, const int* perm, int kexp, int joff, int kcols, long long nq,
                             int na, double* out, long long ldo, cudaStream_t st);
 int launch_pvalues(const PvalArgs& pa, cudaStream_t st);
+int launch_beta_fit(const BetaArgs& ba, cudaStream_t st);
+int launch_beta_gxe(const double* E0, long long lde0, const double* coef, int k0, long long n, long long p, double* out,
+                    long long ldo, long long s0, cudaStream_t st);
 int launch_lrt(const double* alt_lml, double null_lml, long long count, double* pv, cudaStream_t st);
 
 }  // namespace crm

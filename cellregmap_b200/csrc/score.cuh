@@ -85,8 +85,6 @@ constexpr int SCORE_THREADS = 256;
 constexpr int SCORE_CHUNK = 32;
 constexpr int SCORE_MAXE = 8;
 
-// index of pair (j >= l) in the packed lower-triangular layout used for E pair products
-__host__ __device__ __forceinline__ int pair_index(int j, int l) { return j * (j + 1) / 2 + l; }
 
 template <int P>
 __global__ void __launch_bounds__(SCORE_THREADS) crm_score_kernel(const ScoreArgs a) {

@@ -50,8 +50,9 @@ CRM_API int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t 
 /* Replaces the tested-context matrix E0 (row-permuted contexts: idx_E of scan_interaction, _cellregmap.py:398-401). */
 CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream);
 
-/* Sizes fixed by crm_setup: [0]=n [1]=c [2]=k0 [3]=m (columns of H) [4]=R [5]=padded m [6]=max kept rank. */
-CRM_API int crm_get_dims(crm_handle_t h, int64_t* dims7);
+/* Sizes fixed by crm_setup: [0]=n [1]=c [2]=k0 [3]=m (columns of H) [4]=R [5]=padded m [6]=max kept rank
+ * [7]=1 when the pre-expanded basis [Hx | Hx.E0_j] is resident (rotation runs as a plain contraction). */
+CRM_API int crm_get_dims(crm_handle_t h, int64_t* dims8);
 /* Copies S0 of grid point r (padded to dims[5], zeros beyond the kept rank) into out (device). */
 CRM_API int crm_get_spectrum(crm_handle_t h, int r, double* out, void* stream);
 
@@ -84,6 +85,19 @@ CRM_API int crm_scan_interaction(crm_handle_t h, const double* G, int64_t ldg, i
  */
 CRM_API int crm_scan_association(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, int fast,
                          double* out_pv, double* out_alt_lml, double* info4, double* out_null_lml, void* stream);
+
+/*
+ * Effect sizes: replaces CellRegMap.predict_interaction (cellregmap/_cellregmap.py:137-205) for p SNPs: per SNP and rho1 a
+ * REML fit of y ~ [W g E0] under rho1 (g.E0)(g.E0)' + (1-rho1) sum_i L_i L_i' (+ noise), best rho1 by strict '>', then
+ * beta_g = beta[c] and beta_gxe = v0 rho1 E0 (g.E0)' K^-1 (y - M beta) / sqrt(2 maf (1 - maf)).
+ *   maf: p doubles (device).  use_background: 1 when the L passed to crm_setup is the Ls list (the only background this
+ *   entry point uses, as in the reference), 0 to ignore it (model built from hK or without background).
+ *   out_beta_g: p doubles; out_beta_gxe: n x p (leading dimension ldo >= p), element [i][s] = effect of SNP s in cell i,
+ *   i.e. the reference's (1, n, p) array; out_rho1: selected rho1 per SNP (may be NULL).
+ */
+CRM_API int crm_predict_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, const double* maf,
+                                    int use_background, double* out_beta_g, double* out_beta_gxe, int64_t ldo, double* out_rho1,
+                                    void* stream);
 
 /* Number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches). */
 CRM_API long long crm_launch_count(void);

@@ -99,6 +99,25 @@ def test_interaction_permuted_contexts(cuda_device):
     assert np.max(np.abs(np.log10(pv2) - np.log10(ref2))) <= DLOG10_P
 
 
+def test_interaction_permuted_genotypes(cuda_device):
+    """scan_interaction(G, idx_E, idx_G): tested design g[idx_G] . E0[idx_E], null design untouched (reference :398-415)."""
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    from oracle import crm_port
+    d = make_data(n=300, donors=30, k=4, p=21, q=3, seed=10)
+    rng = np.random.default_rng(2)
+    iE, iG = rng.permutation(300), rng.permutation(300)
+    Ls = crm_port.get_L_values(d.hK, d.E)
+    ref = crm_port.CellRegMapOracle(y=d.y, E=d.E, W=d.W, E1=d.E, Ls=Ls)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    for kw in ({"idx_G": iG}, {"idx_E": iE, "idx_G": iG}):
+        ref_pv, ref_info = ref.scan_interaction(d.G, **kw)
+        for G in (d.G, torch.from_numpy(d.G).cuda()):
+            pv, info = model.scan_interaction(G, **kw)
+            np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+            assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= DLOG10_P
+
+
 def test_host_and_device_genotypes_agree_bitwise(cuda_device):
     import torch
     from cellregmap_b200._cellregmap import _make_interaction_model
@@ -130,6 +149,33 @@ def test_association_scans(cuda_device):
     assert np.max(np.abs(np.log10(pf) - np.log10(ref_pf))) <= DLOG10_P
 
 
+@pytest.mark.parametrize("onehot", [False, True])
+def test_estimate_betas(cuda_device, onehot):
+    """estimate_betas / predict_interaction (reference :137-205, :640-682) against the oracle; with one-hot contexts the
+    design [W g E0] is rank deficient (centred one-hot columns sum to zero) and goes through the reduced design."""
+    from cellregmap_b200 import estimate_betas
+    from oracle import crm_port
+    d = make_data(n=400, donors=40, k=5, p=12, q=4, seed=21)
+    E = d.E
+    if onehot:
+        lab = np.random.default_rng(3).integers(0, 5, 400)
+        E = np.eye(5)[lab]
+        E = (E - E.mean(0)) / E.std(0) / np.sqrt(5)
+    ref_bg, ref_bgxe = crm_port.estimate_betas(d.y, d.W, E, d.G, hK=d.hK)
+    bg, bgxe = estimate_betas(d.y, d.W, E, d.G, hK=d.hK)
+    assert bg.shape == ref_bg.shape == (12,)
+    assert bgxe.shape == ref_bgxe.shape == (1, 400, 12)
+    np.testing.assert_allclose(bg, ref_bg, rtol=2e-5, atol=1e-8)
+    scale = np.abs(ref_bgxe).max()
+    np.testing.assert_allclose(bgxe, ref_bgxe, rtol=0, atol=2e-5 * scale)
+    # explicit maf and device-resident genotypes
+    import torch
+    maf = crm_port.compute_maf(d.G)
+    bg2, bgxe2 = estimate_betas(d.y, d.W, E, torch.from_numpy(d.G).cuda(), maf=maf, hK=d.hK)
+    np.testing.assert_array_equal(bg2, bg)
+    np.testing.assert_array_equal(bgxe2, bgxe)
+
+
 def test_input_validation(cuda_device):
     from cellregmap_b200 import CellRegMap
     d = make_data(n=100, donors=10, k=3, p=5, q=2, seed=1)
@@ -137,3 +183,20 @@ def test_input_validation(cuda_device):
         CellRegMap(d.y, d.E[:50])
     with pytest.raises(AssertionError):
         CellRegMap(d.y, d.E, W=d.W[:, 0])
+
+
+def test_rotation_routes_agree(cuda_device, monkeypatch):
+    """The pre-expanded-basis route (plain contraction) and the on-the-fly Hadamard route give the same scan."""
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    d = make_data(n=900, donors=60, k=7, p=130, q=5, seed=17)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    assert model._dims["pre_expanded_basis"]
+    pv_a, info_a = model.scan_interaction(d.G)
+    monkeypatch.setenv("CRM_NO_HXE", "1")
+    model_b = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    assert not model_b._dims["pre_expanded_basis"]
+    pv_b, info_b = model_b.scan_interaction(d.G)
+    np.testing.assert_array_equal(info_a["rho1"], info_b["rho1"])
+    assert np.max(np.abs(np.log10(pv_a) - np.log10(pv_b))) <= 1e-8
+    for key in ("e2", "g2", "eps2"):
+        np.testing.assert_allclose(info_a[key], info_b[key], rtol=1e-9)
