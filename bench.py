@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-snps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-donor-level", action="store_true")
     return ap.parse_args()
 
 
@@ -237,9 +238,17 @@ def run_b200_arm(a):
 
     gathered = torch.empty((world * 5, p), dtype=torch.float64, device=dev) if world > 1 else None
 
+    debug = bool(os.environ.get("CRM_BENCH_DEBUG"))
+
     def step_device():
+        t0 = time.time()
         model = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev)
+        if debug:
+            torch.cuda.synchronize(); t1 = time.time()
         out = model._scan_interaction_device(G_d)
+        if debug:
+            torch.cuda.synchronize(); t2 = time.time()
+            print(f"[debug] rank {rank}: model {1e3 * (t1 - t0):.1f} ms, scan {1e3 * (t2 - t1):.1f} ms", file=sys.stderr)
         res = torch.stack([out["pv"], out["rho1"], out["e2"], out["g2"], out["eps2"]])
         if world > 1:   # the path's one exchange step: all-gather of the 5 per-SNP outputs
             dist.all_gather_into_tensor(gathered, res)
@@ -279,6 +288,24 @@ def run_b200_arm(a):
     achieved = rot_flops / (rot_ms * 1e-3) / 1e12 if rot_ms > 0 else None
     pv = res[0]
     top = torch.argsort(pv)[:4].tolist()
+
+    # ---- extension: donor-level genotype ingress (same job, G given as donors x SNPs + donor index) ----
+    donor_level = None
+    if not a.no_donor_level:
+        Gdon_d = torch.from_numpy(Gd).to(dev)
+
+        def step_donor():
+            model = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev)
+            out = model._scan_interaction_device(Gdon_d, donor_index=donor_d)
+            return torch.stack([out["pv"], out["rho1"], out["e2"], out["g2"], out["eps2"]])
+
+        step_donor()
+        ms_d, wall_d, res_d = timed(step_donor, a.steps)
+        ms_d = max(ms_d, wall_d * 1e3) / a.steps
+        dl = float((torch.log10(res_d[0]) - torch.log10(res[0][:p] if world > 1 else res[0])).abs().max()) if world == 1 else None
+        donor_level = {"value": world * p / (ms_d / 1e3), "unit": UNIT, "ms_per_step": ms_d, "max_abs_dlog10p_vs_expanded": dl,
+                       "note": "same job with genotypes passed as a (donors x SNPs) matrix + donor index (keyword-only extension of the "
+                               "reference API); the per-SNP contraction runs over donors instead of cells; not the headline value"}
 
     # ---- e2e through the public API with (pinned) host buffers ----
     e2e = None
@@ -329,7 +356,7 @@ def run_b200_arm(a):
                              "launches": int(rot_launches), "ms_per_launch": rot_ms / max(1, rot_launches),
                              "share_of_step": rot_ms / ms_total if ms_total else None,
                              "peak_source": "FP64 DMMA issue-rate peak measured on this pool (profiles/r01_dmma_probe.txt); cuBLAS DGEMM 35.4"},
-                "cpu_baseline": cpu, "top_hits": top}
+                "cpu_baseline": cpu, "donor_level_ingress": donor_level, "top_hits": top}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

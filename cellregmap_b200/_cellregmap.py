@@ -172,10 +172,44 @@ class CellRegMap:
         return int(self._y.shape[0])
 
     # ------------------------------------------------------------------------------------------
-    def _scan_interaction_device(self, G, idx_E=None, idx_G=None, diagnostics=False, overrides=None):
+    def _genotypes(self, G, donor_index):
+        """(genotype descriptor, flag bits for the C ABI).  With `donor_index` (n,) G is the d x p donor-level matrix
+        (G_cells = G[donor_index]); the model then contracts over donors instead of cells (extension, not in the
+        reference API)."""
+        dev = self._device
+        if donor_index is None:
+            geno = _Genotypes(G, dev, self.n_samples)
+            return geno, geno.on_host
+        idx = torch.as_tensor(np.asarray(donor_index.cpu() if isinstance(donor_index, torch.Tensor) else donor_index), device=dev).long().flatten()
+        assert idx.numel() == self.n_samples, "donor_index needs one entry per cell"
+        d = int(G.shape[0])
+        assert idx.numel() == 0 or (int(idx.min()) >= 0 and int(idx.max()) < d), "donor_index out of range"
+        key = (d, hash(idx.cpu().numpy().tobytes()))
+        if getattr(self, "_donor_key", None) != key:
+            perm = torch.argsort(idx, stable=True).to(torch.int32).contiguous()
+            counts = torch.bincount(idx, minlength=d)
+            offsets = torch.zeros(d + 1, dtype=torch.int64, device=dev)
+            offsets[1:] = torch.cumsum(counts, 0)
+            offsets = offsets.to(torch.int32).contiguous()
+            _lib.call("crm_set_donors", self._handle, _ptr(perm), _ptr(offsets), d, _stream())
+            self._donor_key = key
+            self._donor_idx = idx
+        geno = _Genotypes(G, dev, d)
+        return geno, geno.on_host | 2
+
+    def _expand(self, G, donor_index):
+        idx = np.asarray(donor_index.cpu() if isinstance(donor_index, torch.Tensor) else donor_index).ravel()
+        if isinstance(G, torch.Tensor):
+            return G[torch.as_tensor(idx, device=G.device)]
+        return np.asarray(G, float)[idx]
+
+    # ------------------------------------------------------------------------------------------
+    def _scan_interaction_device(self, G, idx_E=None, idx_G=None, diagnostics=False, overrides=None, donor_index=None):
         dev = self._device
         torch.cuda.set_device(dev)
-        geno = _Genotypes(G, dev, self.n_samples)
+        if donor_index is not None and idx_G is not None:   # permuted genotypes break the donor grouping: expand
+            G, donor_index = self._expand(G, donor_index), None
+        geno, gflags = self._genotypes(G, donor_index)
         p, R, k = geno.p, len(self._rho1), int(self._E0.shape[1])
         out = {name: torch.empty(p, dtype=torch.float64, device=dev) for name in ("pv", "rho1", "e2", "g2", "eps2")}
         diag = _lib.ScanDiag()
@@ -212,7 +246,7 @@ class CellRegMap:
         if PROFILE["on"]:
             _lib.call("crm_profile", self._handle, 1, None, None, None)
         try:
-            _lib.call("crm_scan_interaction", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, p, geno.on_host,
+            _lib.call("crm_scan_interaction", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, p, gflags,
                       ctypes.c_void_p(gtest.ptr if gtest is not None else 0), gtest.ld if gtest is not None else 0, _ptr(out["pv"]), _ptr(out["rho1"]), _ptr(out["e2"]), _ptr(out["g2"]),
                       _ptr(out["eps2"]), ctypes.byref(diag), _stream())
         finally:
@@ -227,10 +261,11 @@ class CellRegMap:
         out.update(extra)
         return out
 
-    def scan_interaction(self, G, idx_E: Optional[any] = None, idx_G: Optional[any] = None):
+    def scan_interaction(self, G, idx_E: Optional[any] = None, idx_G: Optional[any] = None, *, donor_index=None):
         """Score test of H0: v3 = 0 for every column of G (reference :317-440).
-        Returns (pvalues (p,), {"rho1", "e2", "g2", "eps2": (p,)})."""
-        out = self._scan_interaction_device(G, idx_E, idx_G)
+        Returns (pvalues (p,), {"rho1", "e2", "g2", "eps2": (p,)}).
+        Extension: with `donor_index` (n,), G is the d x p donor-level genotype matrix (G_cells = G[donor_index])."""
+        out = self._scan_interaction_device(G, idx_E, idx_G, donor_index=donor_index)
         flags = out["flags"].cpu().numpy()
         if np.any(flags & 1):
             raise RuntimeError("No eigenvalue is bigger than 0!!")
@@ -239,46 +274,46 @@ class CellRegMap:
         info = {key: out[key].cpu().numpy() for key in ("rho1", "e2", "g2", "eps2")}
         return out["pv"].cpu().numpy(), info
 
-    def _scan_association(self, G, fast):
+    def _scan_association(self, G, fast, donor_index=None):
         dev = self._device
         torch.cuda.set_device(dev)
-        geno = _Genotypes(G, dev, self.n_samples)
+        geno, gflags = self._genotypes(G, donor_index)
         pv = torch.empty(geno.p, dtype=torch.float64, device=dev)
         alt = torch.empty(geno.p, dtype=torch.float64, device=dev)
         info4 = torch.empty(4, dtype=torch.float64, device=dev)
         null = torch.empty(1, dtype=torch.float64, device=dev)
-        _lib.call("crm_scan_association", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, geno.p, geno.on_host,
+        _lib.call("crm_scan_association", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, geno.p, gflags,
                   1 if fast else 0, _ptr(pv), _ptr(alt), _ptr(info4), _ptr(null), _stream())
         i4 = info4.cpu().numpy()
         info = {"rho1": i4[0:1].copy(), "e2": i4[1:2].copy(), "g2": i4[2:3].copy(), "eps2": i4[3:4].copy()}
         self._last_association = {"alt_lml": alt, "null_lml": null}
         return pv.cpu().numpy(), info
 
-    def predict_interaction(self, G, MAF):
+    def predict_interaction(self, G, MAF, *, donor_index=None):
         """Effect sizes of every column of G (reference :137-205): persistent effect beta_g (p,) and per-cell GxC effects
         beta_gxe (1, n, p).  Like the reference, only the Ls background enters this model (hK given to the constructor
         is not used here) and MAF must lie strictly between 0 and 1."""
         dev = self._device
         torch.cuda.set_device(dev)
-        geno = _Genotypes(G, dev, self.n_samples)
+        geno, gflags = self._genotypes(G, donor_index)
         p, n = geno.p, self.n_samples
         maf = _to_dev(np.atleast_1d(np.asarray(MAF.detach().cpu().numpy() if isinstance(MAF, torch.Tensor) else MAF, float)), dev)
         assert maf.numel() == p, "one MAF per SNP"
         beta_g = torch.empty(p, dtype=torch.float64, device=dev)
         beta_gxe = torch.empty((n, p), dtype=torch.float64, device=dev)
         rho1 = torch.empty(p, dtype=torch.float64, device=dev)
-        _lib.call("crm_predict_interaction", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, p, geno.on_host, _ptr(maf),
+        _lib.call("crm_predict_interaction", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, p, gflags, _ptr(maf),
                   1 if self._background_from_Ls else 0, _ptr(beta_g), _ptr(beta_gxe), p, _ptr(rho1), _stream())
         self._last_predict = {"rho1": rho1}
         return beta_g.cpu().numpy(), beta_gxe.cpu().numpy().reshape(1, n, p)
 
-    def scan_association(self, G):
+    def scan_association(self, G, *, donor_index=None):
         """LRT for a persistent effect of every column of G (reference :246-281)."""
-        return self._scan_association(G, fast=False)
+        return self._scan_association(G, fast=False, donor_index=donor_index)
 
-    def scan_association_fast(self, G):
+    def scan_association_fast(self, G, *, donor_index=None):
         """Same with delta frozen at the null fit (reference :284-314)."""
-        return self._scan_association(G, fast=True)
+        return self._scan_association(G, fast=True, donor_index=donor_index)
 
 
 def lrt_pvalues(null_lml, alt_lmls, dof=1):
@@ -292,17 +327,17 @@ def lrt_pvalues(null_lml, alt_lmls, dof=1):
     return pv.cpu().numpy()
 
 
-def run_association(y, W, E, G, hK=None):
+def run_association(y, W, E, G, hK=None, *, donor_index=None):
     """Association test (reference :471-500).  NB the reference passes (y, W, E) positionally to
     CellRegMap(y, E, W): W becomes the context/background matrix and E the covariates; kept."""
     crm = CellRegMap(y, W, E, hK=hK)
-    return crm.scan_association(G)
+    return crm.scan_association(G, donor_index=donor_index)
 
 
-def run_association_fast(y, W, E, G, hK=None):
+def run_association_fast(y, W, E, G, hK=None, *, donor_index=None):
     """Fast association test (reference :502-531); same positional quirk as run_association."""
     crm = CellRegMap(y, W, E, hK=hK)
-    return crm.scan_association_fast(G)
+    return crm.scan_association_fast(G, donor_index=donor_index)
 
 
 def _make_interaction_model(y, E, W, E1, E2, hK, device=None):
@@ -313,19 +348,20 @@ def _make_interaction_model(y, E, W, E1, E2, hK, device=None):
     return CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev)
 
 
-def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None):
+def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None, *, donor_index=None):
     """Interaction test (reference :547-587).  NB `idx_G` is forwarded as scan_interaction's second
-    positional argument, i.e. it permutes the rows of E (reference :586); kept."""
+    positional argument, i.e. it permutes the rows of E (reference :586); kept.
+    Extension: with `donor_index` (n,), G is the d x p donor-level genotype matrix (G_cells = G[donor_index])."""
     crm = _make_interaction_model(y, E, W, E1, E2, hK)
-    return crm.scan_interaction(G, idx_G)
+    return crm.scan_interaction(G, idx_G, donor_index=donor_index)
 
 
-def estimate_betas(y, W, E, G, maf=None, E1=None, E2=None, hK=None):
+def estimate_betas(y, W, E, G, maf=None, E1=None, E2=None, hK=None, *, donor_index=None):
     """Effect-size estimator (reference :640-682): returns (beta_g (p,), beta_gxe (1, n, p))."""
     crm = _make_interaction_model(y, E, W, E1, E2, hK)
-    if maf is None:
-        maf = compute_maf(G)
-    return crm.predict_interaction(G, maf)
+    if maf is None:      # reference: MAF of the expanded matrix
+        maf = compute_maf(G if donor_index is None else crm._expand(G, donor_index))
+    return crm.predict_interaction(G, maf, donor_index=donor_index)
 
 
 def compute_maf(X):

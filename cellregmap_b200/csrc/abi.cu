@@ -38,19 +38,34 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
-// grow-only device buffer
+// Grow-only device buffer.  Allocation goes through the device's default CUDA memory pool (cudaMallocAsync on the
+// legacy default stream) with an unlimited release threshold, so that creating and destroying model objects in a loop
+// (one per gene) reuses the same physical memory instead of paying cudaMalloc/cudaFree of tens of GB every time.
+static void configure_pool_once(int device) {
+    static std::atomic<unsigned> done{0};
+    if (device < 0 || device >= 32 || (done.load() >> device & 1u)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done.fetch_or(1u << device);
+}
 struct DevBuf {
     void* ptr = nullptr;
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return CRM_OK;
-        if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
-        cudaError_t e = cudaMalloc(&ptr, bytes);
-        if (e != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); ptr = nullptr; return CRM_ERR_CUDA; }
+        release();
+        int dev = 0;
+        cudaGetDevice(&dev);
+        configure_pool_once(dev);
+        cudaError_t e = cudaMallocAsync(&ptr, bytes, (cudaStream_t)0);
+        if (e != cudaSuccess) { set_error("cudaMallocAsync of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); ptr = nullptr; cudaGetLastError(); return CRM_ERR_CUDA; }
         cap = bytes;
         return CRM_OK;
     }
-    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+    void release() { if (ptr) cudaFreeAsync(ptr, (cudaStream_t)0); ptr = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
@@ -69,6 +84,14 @@ struct Handle {
     int m = 0, mp = 0, Mx = 0, ldH = 0, kexp = 0, epitch = 0, M2 = 0, ld2 = 0, max_rank = 0;
     std::vector<double> rho;
     // per-gene state
+    // Operands that are contracted against genotype rows.  `cells`: one row per cell (the reference's expanded G).
+    // `donors`: the same operands summed over the cells of each donor, for donor-level genotypes (G_cells = G_donors[donor]).
+    struct GenoSpace { long long K = 0; const double* HxE = nullptr; long long ldE = 0; const double* Hx = nullptr; long long ldHx = 0;
+                       const double* A2 = nullptr; int ld2 = 0; };
+    GenoSpace cells, donors;
+    const GenoSpace* gs = nullptr;   // space of the scan in flight
+    bool donors_set = false;
+    DevBuf HxE_D, A2_D, dperm, doff;
     DevBuf HxE;           // optional n x (kexp * ldH) pre-expanded basis [Hx | Hx.E0_1 | ... | Hx.E0_k] (see launch_rotation)
     bool use_hxe = false;
     DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
@@ -84,7 +107,7 @@ struct Handle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     void free_all() {
-        DevBuf* all[] = {&HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
+        DevBuf* all[] = {&HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
                          &gtchunk[0], &gtchunk[1], &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef};
@@ -109,6 +132,22 @@ __global__ void build_hxe_kernel(const double* Hx, int ldH, const double* Eext, 
     const long long i = idx / ld; const long long r = idx - i * ld;
     const int j = (int)(r / ldH), a = (int)(r - (long long)j * ldH);
     out[idx] = Eext[i * epitch + j] * Hx[i * ldH + a];
+}
+// donor-level pre-expanded basis: out[dn][j * ldH + a] = sum over the cells t of donor dn of Eext[t][j] * Hx[t][a]
+__global__ void aggregate_hxe_kernel(const double* Hx, int ldH, const double* Eext, int epitch, int kexp, const int* perm, const int* off, double* out) {
+    const int dn = blockIdx.x, j = blockIdx.y, a = blockIdx.z * blockDim.x + threadIdx.x;
+    if (a >= ldH) return;
+    double s = 0.0;
+    for (int t = off[dn]; t < off[dn + 1]; t++) { const long long i = perm[t]; s += Eext[i * epitch + j] * Hx[i * ldH + a]; }
+    out[(long long)dn * kexp * ldH + (long long)j * ldH + a] = s;
+}
+// out[dn][col] = sum over the cells of donor dn of src[cell][col]
+__global__ void aggregate_rows_kernel(const double* src, long long ld, int cols, const int* perm, const int* off, double* out, long long ldo) {
+    const int dn = blockIdx.x, col = blockIdx.y * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    double s = 0.0;
+    for (int t = off[dn]; t < off[dn + 1]; t++) s += src[(long long)perm[t] * ld + col];
+    out[(long long)dn * ldo + col] = s;
 }
 // A2 = [1 | E0 | E0_j * E0_l (j >= l, packed)]
 __global__ void build_a2_kernel(const double* E0, long long lde0, long long n, int k0, double* A2, int ld2) {
@@ -241,6 +280,22 @@ static inline unsigned blocks_for(long long work, int threads) { return (unsigne
 // ------------------------------------------------------------------------------------------------
 // set-up
 // ------------------------------------------------------------------------------------------------
+// donor-level operands from the current Hx / Eext / A2 and the stored cell -> donor grouping
+static int aggregate_donors(Handle* h, cudaStream_t st) {
+    const long long d = h->donors.K, ldE = (long long)h->kexp * h->ldH;
+    CRM_CHECK(h->HxE_D.reserve((size_t)d * ldE * 8));
+    CRM_CHECK(h->A2_D.reserve((size_t)d * h->ld2 * 8));
+    dim3 g1((unsigned)d, (unsigned)h->kexp, (unsigned)((h->ldH + 127) / 128));
+    aggregate_hxe_kernel<<<g1, 128, 0, st>>>(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, h->dperm.as<int>(), h->doff.as<int>(), h->HxE_D.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    dim3 g2((unsigned)d, (unsigned)((h->ld2 + 127) / 128), 1);
+    aggregate_rows_kernel<<<g2, 128, 0, st>>>(h->A2.as<double>(), h->ld2, h->ld2, h->dperm.as<int>(), h->doff.as<int>(), h->A2_D.as<double>(), h->ld2);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    h->donors.HxE = h->HxE_D.as<double>(); h->donors.ldE = ldE; h->donors.Hx = h->HxE_D.as<double>(); h->donors.ldHx = ldE;
+    h->donors.A2 = h->A2_D.as<double>(); h->donors.ld2 = h->ld2;
+    return CRM_OK;
+}
+
 static int build_test_contexts(Handle* h, const double* E0, long long lde0, cudaStream_t st) {
     build_eext_kernel<<<blocks_for(h->n * h->epitch, 256), 256, 0, st>>>(E0, lde0, h->n, h->k0, h->Eext.as<double>(), h->epitch);
     CRM_CUDA(cudaGetLastError()); count_launch();
@@ -251,6 +306,9 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
                                                                                    h->HxE.as<double>());
         CRM_CUDA(cudaGetLastError()); count_launch();
     }
+    h->cells.K = h->n; h->cells.HxE = h->use_hxe ? h->HxE.as<double>() : nullptr; h->cells.ldE = (long long)h->kexp * h->ldH;
+    h->cells.Hx = h->Hx.as<double>(); h->cells.ldHx = h->ldH; h->cells.A2 = h->A2.as<double>(); h->cells.ld2 = h->ld2;
+    if (h->donors_set) CRM_CHECK(aggregate_donors(h, st));
     return CRM_OK;
 }
 
@@ -259,12 +317,12 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
 // loop is a plain DMMA contraction (99% of the FP64 tensor peak, costs n*kexp*ldH*8 bytes of HBM once per gene); without
 // it the factor is applied to the genotype fragments on the fly (EXPAND mode, ~90% of peak, no extra memory).
 static int launch_rotation(Handle* h, const double* G, long long ldg, long long gcols, long long B, double* C, cudaStream_t st) {
+    const Handle::GenoSpace& gs = *h->gs;
     GemmOperands op{};
     op.B = G; op.ldb = ldg; op.b_cols = gcols;
-    if (h->use_hxe) {
-        const long long ldE = (long long)h->kexp * h->ldH;
-        op.A = h->HxE.as<double>(); op.lda = ldE; op.a_cols = ldE; op.B2 = G; op.ldb2 = ldg; op.b2_cols = gcols;
-        return launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, (int)ldE, 0, (int)B, C, ldE, 1, st);
+    if (gs.HxE) {
+        op.A = gs.HxE; op.lda = gs.ldE; op.a_cols = gs.ldE; op.B2 = G; op.ldb2 = ldg; op.b2_cols = gcols;
+        return launch_gemm(GEMM_PLAIN, op, (int)gs.K, 0, (int)gs.ldE, 0, (int)B, C, gs.ldE, 1, st);
     }
     op.A = h->Hx.as<double>(); op.lda = h->ldH; op.a_cols = h->Mx;
     op.B2 = h->Eext.as<double>(); op.ldb2 = h->epitch; op.b2_cols = h->epitch;
@@ -280,6 +338,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     if (R > 64) { set_error("rho grid too long"); return CRM_ERR_UNSUPPORTED; }
     if (k1 + mL > 30000) { set_error("background half-covariance has %lld columns; limit is 30000", (long long)(k1 + mL)); return CRM_ERR_UNSUPPORTED; }
     h->ready = false;
+    h->donors_set = false;
     h->n = n; h->c = c; h->k0 = k0; h->k1 = k1; h->mL = mL; h->R = R;
     h->m = (int)(k1 + mL);
     h->mp = (int)round_up(h->m, 2);
@@ -318,6 +377,13 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         const size_t bytes = (size_t)n * h->kexp * ldH * 8;
         size_t free_b = 0, total_b = 0;
         CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        {   // memory cached in the allocation pool is reusable as well
+            cudaMemPool_t mp_; unsigned long long reserved = 0, used = 0;
+            if (cudaDeviceGetDefaultMemPool(&mp_, h->device) == cudaSuccess &&
+                cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+                free_b += (size_t)(reserved - used);
+        }
         const char* env = getenv("CRM_NO_HXE");
         h->use_hxe = !(env && atoi(env) != 0) && (h->HxE.cap >= bytes || bytes < (size_t)(0.30 * (double)(free_b + h->HxE.cap))) && (long long)h->kexp * ldH < 2000000000LL;
         if (h->use_hxe) CRM_CHECK(h->HxE.reserve(bytes)); else h->HxE.release();
@@ -333,9 +399,9 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     extract_stats_kernel<<<1, 64, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
 
-    // per-rho eigendecomposition (cuSOLVER Dsyevd, one-off per gene).  Measured on B200: 12 ms per 1020 x 1020 problem;
-    // running the R problems on R streams (with or without one host thread each) does not overlap them, so they are
-    // issued back to back on the caller's stream with one pooled cuSOLVER context per device.
+    // per-rho eigendecomposition (cuSOLVER, one-off per gene) with one pooled cuSOLVER context per device.  Measured on
+    // B200: Dsyevd takes 12 ms per 1020 x 1020 problem and R of them on R streams (with or without one host thread each)
+    // do not overlap.
     if (h->device < 0 || h->device >= 16) { set_error("device index %d outside the supported range", h->device); return CRM_ERR_UNSUPPORTED; }
     EigPool& pool = g_eig_pool[h->device];
     std::lock_guard<std::mutex> pool_lock(pool.mu);
@@ -351,9 +417,10 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     int* info_dev = h->devinfo.as<int>();
     int* rank_dev = h->devinfo.as<int>() + R;
     const int tall = n > m ? 1 : 0;
+    // CRM_EIG_BATCHED=1 puts all grid points into one cusolverDnXsyevBatched call: 70 ms instead of 134 ms for
+    // 11 x 1020^2 on B200, but its first call in a process costs 54 s of one-time initialisation, so it is opt-in.
     static const bool batched = [] { const char* v = getenv("CRM_EIG_BATCHED"); return v && atoi(v) != 0; }();
     if (batched) {
-        // experiment: all grid points in one cusolverDnXsyevBatched call
         CRM_CHECK(e.mat.reserve((size_t)R * m * m * 8));
         CRM_CHECK(e.val.reserve((size_t)R * m * 8));
         if (!e.params) CRM_SOLVER(cusolverDnCreateParams(&e.params));
@@ -460,11 +527,12 @@ static int ensure_streams(Handle* h) {
 // `slot` (ld = Bp) on the copy stream.
 static int stage_host_block(Handle* h, const double* G, long long ldg, const double* G2, long long ldg2, long long s0, long long B,
                             long long Bp, int slot) {
-    CRM_CHECK(h->gchunk[slot].reserve((size_t)h->n * Bp * 8));
-    if (G2) CRM_CHECK(h->gtchunk[slot].reserve((size_t)h->n * Bp * 8));
+    const size_t rows = (size_t)h->gs->K;
+    CRM_CHECK(h->gchunk[slot].reserve(rows * Bp * 8));
+    if (G2) CRM_CHECK(h->gtchunk[slot].reserve(rows * Bp * 8));
     CRM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // previous consumer of this slot
-    CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[slot].ptr, (size_t)Bp * 8, G + s0, (size_t)ldg * 8, (size_t)B * 8, (size_t)h->n, cudaMemcpyHostToDevice, h->copy_stream));
-    if (G2) CRM_CUDA(cudaMemcpy2DAsync(h->gtchunk[slot].ptr, (size_t)Bp * 8, G2 + s0, (size_t)ldg2 * 8, (size_t)B * 8, (size_t)h->n, cudaMemcpyHostToDevice, h->copy_stream));
+    CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[slot].ptr, (size_t)Bp * 8, G + s0, (size_t)ldg * 8, (size_t)B * 8, rows, cudaMemcpyHostToDevice, h->copy_stream));
+    if (G2) CRM_CUDA(cudaMemcpy2DAsync(h->gtchunk[slot].ptr, (size_t)Bp * 8, G2 + s0, (size_t)ldg2 * 8, (size_t)B * 8, rows, cudaMemcpyHostToDevice, h->copy_stream));
     CRM_CUDA(cudaEventRecord(h->ev_copy[slot], h->copy_stream));
     return CRM_OK;
 }
@@ -486,12 +554,12 @@ static int for_each_block(Handle* h, const double* G, long long ldg, const doubl
             const long long b = std::min(B, p - s0), bp = round_up(b, 2);
             GBlock blk{G + s0, ldg, p - s0, G2 ? G2 + s0 : nullptr, ldg2, b, s0};
             if (!aligned || !aligned2 || (s0 & 1)) {
-                CRM_CHECK(h->gchunk[0].reserve((size_t)h->n * bp * 8));
-                CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+                CRM_CHECK(h->gchunk[0].reserve((size_t)h->gs->K * bp * 8));
+                CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)h->gs->K, cudaMemcpyDeviceToDevice, st));
                 blk.G = h->gchunk[0].as<double>(); blk.ld = bp; blk.cols = b;
                 if (G2) {
-                    CRM_CHECK(h->gtchunk[0].reserve((size_t)h->n * bp * 8));
-                    CRM_CUDA(cudaMemcpy2DAsync(h->gtchunk[0].ptr, (size_t)bp * 8, G2 + s0, (size_t)ldg2 * 8, (size_t)b * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+                    CRM_CHECK(h->gtchunk[0].reserve((size_t)h->gs->K * bp * 8));
+                    CRM_CUDA(cudaMemcpy2DAsync(h->gtchunk[0].ptr, (size_t)bp * 8, G2 + s0, (size_t)ldg2 * 8, (size_t)b * 8, (size_t)h->gs->K, cudaMemcpyDeviceToDevice, st));
                     blk.G2 = h->gtchunk[0].as<double>(); blk.ld2 = bp;
                 }
             }
@@ -535,24 +603,24 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     // 2. squared-genotype Grams against [1 | E0 | pairs]:  g'g, (g.E0)'g, (g.E0)'(g.E0)
     {
         GemmOperands op{};
-        op.A = h->A2.as<double>(); op.lda = h->ld2; op.a_cols = h->M2;
+        op.A = h->gs->A2; op.lda = h->gs->ld2; op.a_cols = h->M2;
         op.B = Gt ? Gt : Gd; op.ldb = Gt ? ldgt : ldg; op.b_cols = gcols;
         op.B2 = op.B; op.ldb2 = op.ldb; op.b2_cols = gcols;
-        CRM_CHECK(launch_gemm(GEMM_PRODUCT, op, (int)h->n, 0, h->M2, 0, (int)B, sq, h->ld2, 1, st));
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, op, (int)h->gs->K, 0, h->M2, 0, (int)B, sq, h->ld2, 1, st));
     }
     if (Gt) {
         // permuted tested genotypes (idx_G, reference :410-413): the null design still uses g itself, so the j = 0 rows of C
         // are overwritten with the rotation of g, column 0 of sq with g'g and columns 1..k with (gt * g)' E0
         GemmOperands op{};
-        op.A = h->Hx.as<double>(); op.lda = ldH; op.a_cols = Mx;
+        op.A = h->gs->Hx; op.lda = h->gs->ldHx; op.a_cols = Mx;
         op.B = Gd; op.ldb = ldg; op.b_cols = gcols; op.B2 = Gd; op.ldb2 = ldg; op.b2_cols = gcols;
-        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, Mx, 0, (int)B, C, (long long)kexp * ldH, 1, st));
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->gs->K, 0, Mx, 0, (int)B, C, (long long)kexp * ldH, 1, st));
         GemmOperands o2{};
-        o2.A = h->A2.as<double>(); o2.lda = h->ld2; o2.a_cols = h->M2;
+        o2.A = h->gs->A2; o2.lda = h->gs->ld2; o2.a_cols = h->M2;
         o2.B = Gd; o2.ldb = ldg; o2.b_cols = gcols; o2.B2 = Gd; o2.ldb2 = ldg; o2.b2_cols = gcols;
-        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->n, 0, 1, 0, (int)B, sq, h->ld2, 1, st));
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->gs->K, 0, 1, 0, (int)B, sq, h->ld2, 1, st));
         o2.B2 = Gt; o2.ldb2 = ldgt;
-        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->n, 1, k, 0, (int)B, sq + 1, h->ld2, 1, st));
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->gs->K, 1, k, 0, (int)B, sq + 1, h->ld2, 1, st));
     }
     // 3. H'g as a K-outer operand, 4. rotated genotype for every rho
     const long long ldhg = round_up(B, 2);
@@ -639,14 +707,22 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     return CRM_OK;
 }
 
-static int do_scan_interaction(Handle* h, const double* G, long long ldg, long long p, int g_on_host, const double* Gtest, long long ldgt,
+static int select_space(Handle* h, int donor_level, const char* who) {
+    if (donor_level && !h->donors_set) { set_error("%s: donor-level genotypes need crm_set_donors first", who); return CRM_ERR_STATE; }
+    h->gs = donor_level ? &h->donors : &h->cells;
+    return CRM_OK;
+}
+
+static int do_scan_interaction(Handle* h, int donor_level, const double* G, long long ldg, long long p, int g_on_host, const double* Gtest, long long ldgt,
                                double* out_pv, double* out_rho1, double* out_e2, double* out_g2, double* out_eps2,
                                const crm_scan_diag_t* dg, cudaStream_t st) {
     if (!h->ready) { set_error("crm_scan_interaction: handle is not set up"); return CRM_ERR_STATE; }
+    CRM_CHECK(select_space(h, donor_level, "crm_scan_interaction"));
+    if (donor_level && Gtest) { set_error("crm_scan_interaction: permuted tested genotypes are not supported with donor-level input"); return CRM_ERR_UNSUPPORTED; }
     if (!G || p < 0 || ldg < p || !out_pv || !out_rho1 || !out_e2 || !out_g2 || !out_eps2) { set_error("crm_scan_interaction: bad arguments"); return CRM_ERR_INVALID; }
     if (p == 0) return CRM_OK;
     long long B = pick_batch(h, p, true);
-    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->n))));
+    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->gs->K))));
     CRM_CHECK(reserve_scan(h, B, true));
     return for_each_block(h, G, ldg, Gtest, ldgt, p, g_on_host, B, st, [&](const GBlock& k) -> int {
         return interaction_batch(h, k.G, k.ld, k.cols, k.G2, k.ld2, k.b, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, k.s0, st);
@@ -656,13 +732,14 @@ static int do_scan_interaction(Handle* h, const double* G, long long ldg, long l
 // ------------------------------------------------------------------------------------------------
 // association scans
 // ------------------------------------------------------------------------------------------------
-static int do_scan_association(Handle* h, const double* G, long long ldg, long long p, int g_on_host, int fast, double* out_pv,
+static int do_scan_association(Handle* h, int donor_level, const double* G, long long ldg, long long p, int g_on_host, int fast, double* out_pv,
                                double* out_alt, double* info4, double* out_null, cudaStream_t st) {
     if (!h->ready) { set_error("crm_scan_association: handle is not set up"); return CRM_ERR_STATE; }
+    CRM_CHECK(select_space(h, donor_level, "crm_scan_association"));
     if (!G || p < 0 || ldg < p || !out_pv || !info4) { set_error("crm_scan_association: bad arguments"); return CRM_ERR_INVALID; }
     const int R = h->R, mp = h->mp, m = h->m, c = h->c, ldH = h->ldH, Mx = h->Mx;
     long long B = pick_batch(h, std::max<long long>(p, 1), false);
-    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->n))));
+    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->gs->K))));
     CRM_CHECK(reserve_scan(h, std::max<long long>(B, 1), false));
     // ---- null model: ML fit of y ~ W for every rho, best by strict '>' ----
     FitArgs fa{};
@@ -693,13 +770,13 @@ static int do_scan_association(Handle* h, const double* G, long long ldg, long l
         double* C = h->C.as<double>();
         double* sq = h->sq.as<double>();
         GemmOperands op{};
-        op.A = h->Hx.as<double>(); op.lda = ldH; op.a_cols = Mx;
+        op.A = h->gs->Hx; op.lda = h->gs->ldHx; op.a_cols = Mx;
         op.B = Gd; op.ldb = ld; op.b_cols = cols; op.B2 = Gd; op.ldb2 = ld; op.b2_cols = cols;
-        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, Mx, 0, (int)b, C, ldH, 1, st));
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->gs->K, 0, Mx, 0, (int)b, C, ldH, 1, st));
         GemmOperands op2{};
-        op2.A = h->A2.as<double>(); op2.lda = h->ld2; op2.a_cols = h->M2;
+        op2.A = h->gs->A2; op2.lda = h->gs->ld2; op2.a_cols = h->M2;
         op2.B = Gd; op2.ldb = ld; op2.b_cols = cols; op2.B2 = Gd; op2.ldb2 = ld; op2.b2_cols = cols;
-        CRM_CHECK(launch_gemm(GEMM_PRODUCT, op2, (int)h->n, 0, 1, 0, (int)b, sq, 2, 1, st));
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, op2, (int)h->gs->K, 0, 1, 0, (int)b, sq, 2, 1, st));
         const long long ldhg = round_up(b, 2);
         CRM_CHECK(launch_gather_transpose(C, ldH, nullptr, 1, 0, 1, b, m, h->Hg.as<double>(), ldhg, st));
         GemmOperands op3{};
@@ -721,9 +798,10 @@ static int do_scan_association(Handle* h, const double* G, long long ldg, long l
 // ------------------------------------------------------------------------------------------------
 // effect sizes (predict_interaction)
 // ------------------------------------------------------------------------------------------------
-static int do_predict(Handle* h, const double* G, long long ldg, long long p, int g_on_host, const double* maf, int use_background,
+static int do_predict(Handle* h, int donor_level, const double* G, long long ldg, long long p, int g_on_host, const double* maf, int use_background,
                       double* out_beta_g, double* out_beta_gxe, long long ldo, double* out_rho1, cudaStream_t st) {
     if (!h->ready) { set_error("crm_predict_interaction: handle is not set up"); return CRM_ERR_STATE; }
+    CRM_CHECK(select_space(h, donor_level, "crm_predict_interaction"));
     if (!G || p < 0 || ldg < p || !maf || !out_beta_g || !out_beta_gxe || ldo < p) { set_error("crm_predict_interaction: bad arguments"); return CRM_ERR_INVALID; }
     if (p == 0) return CRM_OK;
     const int R = h->R, mp = h->mp, c = h->c, k0 = h->k0, kexp = h->kexp, ldH = h->ldH, Mx = h->Mx;
@@ -758,7 +836,7 @@ static int do_predict(Handle* h, const double* G, long long ldg, long long p, in
     const double per_snp = 8.0 * ((double)kexp * ldH + 2.0 * h->ld2 + 2.0 * (double)kexp * mp + (double)R * (P + k0 + 8));
     long long B = std::max<long long>(16, std::min<long long>(p, (long long)(4.0e9 / per_snp)));
     B = std::min<long long>(B, 65535LL * GEMM_TILE_N / kexp);
-    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->n))));
+    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->gs->K))));
     CRM_CHECK(h->C.reserve((size_t)B * kexp * ldH * 8));
     CRM_CHECK(h->sq.reserve((size_t)B * h->ld2 * 8));
     CRM_CHECK(h->lin.reserve((size_t)B * h->ld2 * 8));
@@ -778,9 +856,9 @@ static int do_predict(Handle* h, const double* G, long long ldg, long long p, in
         double* C = h->C.as<double>();
         CRM_CHECK(launch_rotation(h, k.G, k.ld, k.cols, b, C, st));
         GemmOperands o2{};
-        o2.A = h->A2.as<double>(); o2.lda = h->ld2; o2.a_cols = h->M2; o2.B = k.G; o2.ldb = k.ld; o2.b_cols = k.cols; o2.B2 = k.G; o2.ldb2 = k.ld; o2.b2_cols = k.cols;
-        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->n, 0, h->M2, 0, (int)b, h->sq.as<double>(), h->ld2, 1, st));
-        CRM_CHECK(launch_gemm(GEMM_PLAIN, o2, (int)h->n, 0, h->M2, 0, (int)b, h->lin.as<double>(), h->ld2, 1, st));
+        o2.A = h->gs->A2; o2.lda = h->gs->ld2; o2.a_cols = h->M2; o2.B = k.G; o2.ldb = k.ld; o2.b_cols = k.cols; o2.B2 = k.G; o2.ldb2 = k.ld; o2.b2_cols = k.cols;
+        CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->gs->K, 0, h->M2, 0, (int)b, h->sq.as<double>(), h->ld2, 1, st));
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, o2, (int)h->gs->K, 0, h->M2, 0, (int)b, h->lin.as<double>(), h->ld2, 1, st));
         if (mB > 0) {
             const long long ldv = round_up(b * kexp, 2);
             CRM_CHECK(launch_gather_transpose(C, ldH, nullptr, kexp, 0, kexp, b * kexp, mB, h->Vg.as<double>(), ldv, st));
@@ -844,6 +922,7 @@ int crm_create(crm_handle_t* out, int device) {
 int crm_destroy(crm_handle_t h) {
     if (!h) return CRM_OK;
     cudaSetDevice(h->impl.device);
+    cudaDeviceSynchronize();   // every stream that may still read the buffers (they return to the pool in stream order)
     h->impl.free_all();
     if (h->impl.copy_stream) {
         cudaStreamDestroy(h->impl.copy_stream);
@@ -889,6 +968,21 @@ int crm_profile(crm_handle_t h, int enable, double* rot_ms, double* rot_flops, i
     return CRM_OK;
 }
 
+int crm_set_donors(crm_handle_t h, const int32_t* perm, const int32_t* offsets, int64_t d, void* stream) {
+    if (!h || !h->impl.ready) { set_error("crm_set_donors: handle not set up"); return CRM_ERR_STATE; }
+    if (!perm || !offsets || d <= 0 || d > 2000000000LL) { set_error("crm_set_donors: bad arguments"); return CRM_ERR_INVALID; }
+    Handle& H = h->impl;
+    CRM_CUDA(cudaSetDevice(H.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CRM_CHECK(H.dperm.reserve((size_t)H.n * 4));
+    CRM_CHECK(H.doff.reserve((size_t)(d + 1) * 4));
+    CRM_CUDA(cudaMemcpyAsync(H.dperm.ptr, perm, (size_t)H.n * 4, cudaMemcpyDeviceToDevice, st));
+    CRM_CUDA(cudaMemcpyAsync(H.doff.ptr, offsets, (size_t)(d + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    H.donors.K = d;
+    H.donors_set = true;
+    return aggregate_donors(&H, st);
+}
+
 int crm_get_dims(crm_handle_t h, int64_t* d) {
     if (!h || !h->impl.ready || !d) { set_error("crm_get_dims: handle not set up"); return CRM_ERR_STATE; }
     d[0] = h->impl.n; d[1] = h->impl.c; d[2] = h->impl.k0; d[3] = h->impl.m; d[4] = h->impl.R; d[5] = h->impl.mp; d[6] = h->impl.max_rank; d[7] = h->impl.use_hxe ? 1 : 0;
@@ -906,21 +1000,21 @@ int crm_scan_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p
                          void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
-    return do_scan_interaction(&h->impl, G, ldg, p, g_on_host, Gtest, ldgt, out_pv, out_rho1, out_e2, out_g2, out_eps2, diag, (cudaStream_t)stream);
+    return do_scan_interaction(&h->impl, (g_on_host >> 1) & 1, G, ldg, p, g_on_host & 1, Gtest, ldgt, out_pv, out_rho1, out_e2, out_g2, out_eps2, diag, (cudaStream_t)stream);
 }
 
 int crm_scan_association(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, int fast, double* out_pv,
                          double* out_alt_lml, double* info4, double* out_null_lml, void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
-    return do_scan_association(&h->impl, G, ldg, p, g_on_host, fast, out_pv, out_alt_lml, info4, out_null_lml, (cudaStream_t)stream);
+    return do_scan_association(&h->impl, (g_on_host >> 1) & 1, G, ldg, p, g_on_host & 1, fast, out_pv, out_alt_lml, info4, out_null_lml, (cudaStream_t)stream);
 }
 
 int crm_predict_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, const double* maf, int use_background,
                             double* out_beta_g, double* out_beta_gxe, int64_t ldo, double* out_rho1, void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
-    return do_predict(&h->impl, G, ldg, p, g_on_host, maf, use_background, out_beta_g, out_beta_gxe, ldo, out_rho1, (cudaStream_t)stream);
+    return do_predict(&h->impl, (g_on_host >> 1) & 1, G, ldg, p, g_on_host & 1, maf, use_background, out_beta_g, out_beta_gxe, ldo, out_rho1, (cudaStream_t)stream);
 }
 
 int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const double* B, int64_t ldb, int64_t b_cols, const double* B2,
@@ -953,6 +1047,16 @@ int crm_davies_pvalues(const double* Q, const double* lam, const int32_t* nlam, 
     pa.Q = Q; pa.lam = lam; pa.nlam = nlam; pa.lam_ld = lam_ld; pa.count = (int)count; pa.lim = lim; pa.acc = acc;
     pa.pv = pv; pa.liu = liu; pa.ifault = ifault; pa.converged = converged; pa.trace = trace8;
     return launch_pvalues(pa, (cudaStream_t)stream);
+}
+
+int crm_liu_params(const double* Q, const double* lam, const int32_t* nlam, int lam_ld, int64_t count, double* out4, void* stream) {
+    if (!Q || !lam || !nlam || !out4 || count < 0) { set_error("crm_liu_params: bad arguments"); return CRM_ERR_INVALID; }
+    return launch_liu_params(Q, lam, nlam, lam_ld, count, out4, (cudaStream_t)stream);
+}
+
+int crm_qmin(const double* params4, int nrho, int64_t count, double* out, void* stream) {
+    if (!params4 || !out || count < 0 || nrho <= 0) { set_error("crm_qmin: bad arguments"); return CRM_ERR_INVALID; }
+    return launch_qmin(params4, nrho, count, out, (cudaStream_t)stream);
 }
 
 int crm_lrt_pvalues(const double* alt_lml, double null_lml, int64_t count, double* pv, void* stream) {

@@ -17,4 +17,17 @@ int launch_lrt(const double* alt_lml, double null_lml, long long count, double* 
     return CRM_OK;
 }
 
+int launch_liu_params(const double* Q, const double* lam, const int* nlam, int lam_ld, long long count, double* out, cudaStream_t st) {
+    if (count <= 0) return CRM_OK;
+    crm_liu_params_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(Q, lam, nlam, lam_ld, (int)count, out);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+int launch_qmin(const double* params, int nrho, long long count, double* out, cudaStream_t st) {
+    if (count <= 0 || nrho <= 0) return CRM_OK;
+    crm_qmin_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(params, nrho, (int)count, out);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
 }  // namespace crm

@@ -34,6 +34,8 @@ int launch_pvalues(const PvalArgs& pa, cudaStream_t st);
 int launch_beta_fit(const BetaArgs& ba, cudaStream_t st);
 int launch_beta_gxe(const double* E0, long long lde0, const double* coef, int k0, long long n, long long p, double* out,
                     long long ldo, long long s0, cudaStream_t st);
+int launch_liu_params(const double* Q, const double* lam, const int* nlam, int lam_ld, long long count, double* out, cudaStream_t st);
+int launch_qmin(const double* params, int nrho, long long count, double* out, cudaStream_t st);
 int launch_lrt(const double* alt_lml, double null_lml, long long count, double* pv, cudaStream_t st);
 
 }  // namespace crm

@@ -57,6 +57,32 @@ __device__ inline double ncx2_sf(double x, double df, double nc) {
     return sum;
 }
 
+// chi-square quantile: x with P(df/2, x/2) = p  (scipy.stats.chi2.ppf as used by qmin, cellregmap/_math.py:195);
+// safeguarded Newton on the regularised lower incomplete gamma function
+__device__ inline double chi2_ppf(double p, double df) {
+    if (!(p > 0.0)) return 0.0;
+    if (!(p < 1.0)) return INFINITY;
+    const double a = 0.5 * df, lga = lgamma(a);
+    double lo = 0.0, hi = fmax(df, 1.0);
+    for (int it = 0; it < 200 && 1.0 - igamc(a, 0.5 * hi) < p; it++) { lo = hi; hi *= 2.0; }
+    double x;
+    {   // Wilson-Hilferty start, clipped into the bracket
+        const double z = normcdfinv(p), c = 2.0 / (9.0 * df), w = 1.0 - c + z * sqrt(c);
+        x = df * w * w * w;
+        if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
+    }
+    for (int it = 0; it < 100; it++) {
+        const double f = (1.0 - igamc(a, 0.5 * x)) - p;
+        if (f > 0.0) hi = x; else lo = x;
+        const double pdf = 0.5 * exp((a - 1.0) * log(0.5 * x) - 0.5 * x - lga);
+        double xn = x - f / pdf;
+        if (!(xn > lo && xn < hi) || !(pdf > 0.0)) xn = 0.5 * (lo + hi);
+        if (fabs(xn - x) <= 1e-15 * fabs(x)) { x = xn; break; }
+        x = xn;
+    }
+    return x;
+}
+
 struct LiuParams { double pv, dof_x, delta_x, mu_q, sigma_q; };
 
 // chiscore.liu_sf(q, lambda, dofs=1, deltas=0, kurtosis=True)
@@ -346,6 +372,29 @@ __global__ void __launch_bounds__(PV_WARPS * 32) crm_pvalue_kernel(const PvalArg
         if (a.ifault) a.ifault[i] = ifault;
         if (a.converged) a.converged[i] = conv;
         if (a.trace) { double* t = a.trace + (long long)i * 8; t[0] = qfval; for (int j = 0; j < 7; j++) t[1 + j] = tr[j]; }
+    }
+}
+
+// score_statistic_liu_params (cellregmap/_math.py:163-180), batched: out[i] = {pv, mu_q, sigma_q, dof_x}
+__global__ void crm_liu_params_kernel(const double* Q, const double* lam, const int* nlam, int lam_ld, int count, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const LiuParams lp = liu_mod(Q[i], lam + (long long)i * lam_ld, nlam[i]);
+    double* o = out + (long long)i * 4;
+    o[0] = lp.pv; o[1] = lp.mu_q; o[2] = lp.sigma_q; o[3] = lp.dof_x;
+}
+
+// qmin (cellregmap/_math.py:183-201), batched over `count` tests with `nrho` parameter sets {pv, mu_q, sigma_q, dof_x} each
+__global__ void crm_qmin_kernel(const double* params, int nrho, int count, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double* pr = params + (long long)i * nrho * 4;
+    double T = INFINITY;
+    for (int r = 0; r < nrho; r++) T = fmin(T, pr[r * 4]);
+    for (int r = 0; r < nrho; r++) {
+        const double mu_q = pr[r * 4 + 1], sigma_q = pr[r * 4 + 2], dof = pr[r * 4 + 3];
+        const double q = chi2_ppf(1.0 - T, dof);
+        out[(long long)i * nrho + r] = (q - dof) / sqrt(2.0 * dof) * sigma_q + mu_q;
     }
 }
 

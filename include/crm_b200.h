@@ -50,6 +50,16 @@ CRM_API int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t 
 /* Replaces the tested-context matrix E0 (row-permuted contexts: idx_E of scan_interaction, _cellregmap.py:398-401). */
 CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream);
 
+/*
+ * Donor-level genotype ingress (extension).  The reference always receives genotypes expanded from donors to
+ * cells, G_cells = G_donors[donor_of_cell].  After crm_set_donors the scan entry points also accept the d x p donor-level
+ * matrix (flag bit 1 of `g_on_host`, see below): every contraction over cells is then done once per gene on the basis side
+ * (sums over the cells of each donor) and the per-SNP work contracts over d donors instead of n cells.  Results equal the
+ * expanded call up to summation order.  perm [n]: cell indices grouped by donor; offsets [d+1]: start of each donor's group
+ * (both int32, device).  Must be called after crm_setup (and is refreshed by crm_set_test_contexts).
+ */
+CRM_API int crm_set_donors(crm_handle_t h, const int32_t* perm, const int32_t* offsets, int64_t d, void* stream);
+
 /* Sizes fixed by crm_setup: [0]=n [1]=c [2]=k0 [3]=m (columns of H) [4]=R [5]=padded m [6]=max kept rank
  * [7]=1 when the pre-expanded basis [Hx | Hx.E0_j] is resident (rotation runs as a plain contraction). */
 CRM_API int crm_get_dims(crm_handle_t h, int64_t* dims8);
@@ -58,8 +68,10 @@ CRM_API int crm_get_spectrum(crm_handle_t h, int r, double* out, void* stream);
 
 /*
  * Interaction scan: replaces CellRegMap.scan_interaction (cellregmap/_cellregmap.py:317-440) for p SNPs.
- *   G: n x p genotypes, leading dimension ldg; device memory, or pinned/pageable host memory when g_on_host != 0
- *      (then the columns are streamed to the device in chunks, overlapped with compute).
+ *   G: n x p genotypes, leading dimension ldg; device memory, or pinned/pageable host memory when bit 0 of g_on_host is
+ *      set (then the columns are streamed to the device in chunks, overlapped with compute).  Bit 1 of g_on_host set:
+ *      G is the d x p donor-level matrix (see crm_set_donors).  The same two bits apply to crm_scan_association and
+ *      crm_predict_interaction.
  *   Gtest: optional n x p genotypes used only in the tested design g.E0 (idx_G permutation, :410-413), else NULL.
  *   out_pv, out_rho1, out_e2, out_g2, out_eps2: p doubles each (device).
  *   Optional diagnostics (device, may be NULL): d_lml/d_delta/d_scale [p][R], d_Q [p], d_lam [p][k0],
@@ -127,6 +139,13 @@ CRM_API int crm_lmm_fit_rotated(const double* S, const double* yr, const double*
 CRM_API int crm_davies_pvalues(const double* Q, const double* lam, const int32_t* nlam, int lam_ld, int64_t count, int lim,
                        double acc, double* pv, double* liu, int32_t* ifault, int32_t* converged, double* trace8,
                        void* stream);
+
+/* Batched score_statistic_liu_params (cellregmap/_math.py:163-180): modified-Liu parameters of `count` (Q, eigenvalue list)
+ * pairs; out4 [count][4] = pv, mu_q, sigma_q, dof_x. */
+CRM_API int crm_liu_params(const double* Q, const double* lam, const int32_t* nlam, int lam_ld, int64_t count, double* out4,
+                           void* stream);
+/* Batched qmin (cellregmap/_math.py:183-201): params4 [count][nrho][4] = pv, mu_q, sigma_q, dof_x -> out [count][nrho]. */
+CRM_API int crm_qmin(const double* params4, int nrho, int64_t count, double* out, void* stream);
 
 /* lrt_pvalues (cellregmap/_cellregmap.py:443-469) with dof = 1. */
 CRM_API int crm_lrt_pvalues(const double* alt_lml, double null_lml, int64_t count, double* pv, void* stream);

@@ -175,3 +175,31 @@ def test_lmm_fit_rotated_matches_oracle(cuda_device, restricted, c):
             np.testing.assert_allclose(scale[s, k], ref.scale, rtol=1e-6)
             np.testing.assert_allclose(beta[s, k], ref.beta, rtol=1e-5, atol=1e-8)
             assert nfev[s, k] == ref.nfev - 1 or nfev[s, k] == ref.nfev
+
+
+def test_liu_params_and_qmin_goldens(cuda_device):
+    """Known answers of the reference (cellregmap/test/test_math.py:76-91) through the CUDA ops."""
+    from cellregmap_b200._math import liu_params_batch, qmin, qmin_batch, score_statistic_liu_params
+    from oracle import math_port as mp
+    w = np.array([4.55266277e-09, 3.46249449e-01])
+    got = score_statistic_liu_params(0.49961017073389324, w)
+    np.testing.assert_allclose(got["pv"], 0.22966744652848403, rtol=1e-7)
+    np.testing.assert_allclose(got["mu_q"], 0.34624945394475326, rtol=1e-7)
+    np.testing.assert_allclose(got["sigma_q"], 0.48967066729451103, rtol=1e-7)
+    np.testing.assert_allclose(got["dof_x"], 1.0, rtol=1e-7)
+    params = [{"pv": 0.22966742, "mu_q": 0.34945, "sigma_q": 0.48670, "dof_x": 1.5}, {"pv": 0.65, "mu_q": 0.695, "sigma_q": 0.1, "dof_x": 0.7}]
+    np.testing.assert_allclose(qmin(params), [0.5506645025120773, 0.7157125486956082], rtol=1e-7)
+    # random batch against the oracle
+    rng = np.random.default_rng(0)
+    ws = [np.sort(rng.gamma(0.8, 1.0, rng.integers(1, 15)))[::-1] + 1e-6 for _ in range(64)]
+    qs = np.array([w.sum() * rng.uniform(0.2, 6.0) for w in ws])
+    got = liu_params_batch(qs, ws)
+    for i in range(64):
+        ref = mp.score_statistic_liu_params(qs[i], ws[i])
+        np.testing.assert_allclose(got[i, 0], ref["pv"], rtol=1e-7)      # scipy's ncx2.sf vs the Poisson-mixture form
+        np.testing.assert_allclose(got[i, 1:], [ref["mu_q"], ref["sigma_q"], ref["dof_x"]], rtol=1e-9)
+    P = got.reshape(8, 8, 4)
+    out = qmin_batch(P)
+    for b in range(8):
+        ref = mp.qmin([{"pv": P[b, r, 0], "mu_q": P[b, r, 1], "sigma_q": P[b, r, 2], "dof_x": P[b, r, 3]} for r in range(8)])
+        np.testing.assert_allclose(out[b], ref, rtol=1e-8)

@@ -200,3 +200,34 @@ def test_rotation_routes_agree(cuda_device, monkeypatch):
     assert np.max(np.abs(np.log10(pv_a) - np.log10(pv_b))) <= 1e-8
     for key in ("e2", "g2", "eps2"):
         np.testing.assert_allclose(info_a[key], info_b[key], rtol=1e-9)
+
+
+def test_donor_level_genotypes_match_expanded(cuda_device):
+    """Extension: donor-level genotypes + donor_index give the results of the expanded call (all scans)."""
+    import torch
+    from cellregmap_b200 import estimate_betas, run_association, run_association_fast, run_interaction
+    d = make_data(n=800, donors=37, k=6, p=75, q=5, seed=23)
+    # recover the donor-level matrix of the generator
+    Gd = np.zeros((37, 75))
+    for i, dn in enumerate(d.donor):
+        Gd[dn] = d.G[i]
+    assert np.array_equal(Gd[d.donor], d.G)
+    pv_e, info_e = run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    for G in (Gd, torch.from_numpy(Gd).cuda()):
+        pv_d, info_d = run_interaction(d.y, d.E, G, W=d.W, hK=d.hK, donor_index=d.donor)
+        np.testing.assert_array_equal(info_d["rho1"], info_e["rho1"])
+        assert np.max(np.abs(np.log10(pv_d) - np.log10(pv_e))) <= 1e-7
+        for key in ("e2", "g2", "eps2"):
+            np.testing.assert_allclose(info_d[key], info_e[key], rtol=1e-8)
+    idx = np.random.default_rng(0).permutation(800)
+    pv_e2, _ = run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK, idx_G=idx)
+    pv_d2, _ = run_interaction(d.y, d.E, Gd, W=d.W, hK=d.hK, idx_G=idx, donor_index=d.donor)
+    assert np.max(np.abs(np.log10(pv_d2) - np.log10(pv_e2))) <= 1e-7
+    for fn in (run_association, run_association_fast):
+        pa_e, _ = fn(d.y, d.W, d.E, d.G, hK=d.hK)
+        pa_d, _ = fn(d.y, d.W, d.E, Gd, hK=d.hK, donor_index=d.donor)
+        assert np.max(np.abs(np.log10(pa_d) - np.log10(pa_e))) <= 1e-7
+    bg_e, bx_e = estimate_betas(d.y, d.W, d.E, d.G[:, :9], hK=d.hK)
+    bg_d, bx_d = estimate_betas(d.y, d.W, d.E, Gd[:, :9], hK=d.hK, donor_index=d.donor)
+    np.testing.assert_allclose(bg_d, bg_e, rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(bx_d, bx_e, rtol=0, atol=1e-6 * np.abs(bx_e).max())
