@@ -99,6 +99,7 @@ struct Handle {
     // scan workspaces
     DevBuf C, sq, Hg, gr, Vg, GEr, fit_lml, fit_delta, fit_scale, fit_beta, fit_x, fit_nfev, fit_flags;
     DevBuf Ys, sgram, HY, Zs, lin, Zp, ucoef, coef;
+    DevBuf YW, ywgram;    // [R][1 + c][mp] rotated [y | W] per rho and the (1 + c)^2 plain Gram of [y | W] (wide-design fits)
     DevBuf rho_idx, best_lml, v0, v1, perm, offsets, Q, lam, nlam, sflags, liu, ifault, conv, gchunk[2], gtchunk[2], scratch;
     // optional timing of the rotation kernel (K1, EXPAND mode) with events on the launching stream
     bool prof_on = false;
@@ -110,7 +111,7 @@ struct Handle {
         DevBuf* all[] = {&HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
-                         &gtchunk[0], &gtchunk[1], &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef};
+                         &gtchunk[0], &gtchunk[1], &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -211,11 +212,28 @@ __global__ void rotate_null_kernel(const double* Tt, long long ldt, const double
         if (col == 0) yr[idx] = s; else Wr[((long long)rho * c + (col - 1)) * mp + i] = s;
     }
 }
+// YW[rho][0][i] = yr[rho][i], YW[rho][1 + a][i] = Wr[rho][a][i];  ywgram = plain Gram of [y | W] from stats
+__global__ void build_yw_kernel(const double* yr, const double* Wr, const double* stats, int R, int c, int mp, double* YW, double* ywgram) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)R * (1 + c) * mp;
+    if (idx < total) {
+        const int i = (int)(idx % mp); const long long rc = idx / mp; const int col = (int)(rc % (1 + c)), rho = (int)(rc / (1 + c));
+        YW[idx] = col == 0 ? yr[(long long)rho * mp + i] : Wr[((long long)rho * c + (col - 1)) * mp + i];
+    }
+    if (idx < (long long)(1 + c) * (1 + c)) {
+        const int a = (int)(idx / (1 + c)), b = (int)(idx % (1 + c));
+        double v;
+        if (a == 0 && b == 0) v = stats[0];
+        else if (a == 0) v = stats[b];
+        else if (b == 0) v = stats[a];
+        else v = stats[1 + c + (a - 1) * c + (b - 1)];
+        ywgram[idx] = v;
+    }
+}
 __global__ void extract_stats_kernel(const double* gram, int ldg, int m, int c, double* stats) {
-    const int t = threadIdx.x;
-    if (t == 0) stats[0] = gram[(long long)m * ldg + m];
-    if (t < c) stats[1 + t] = gram[(long long)m * ldg + m + 1 + t];
-    if (t < c * c) { const int a = t / c, b = t - a * c; stats[1 + c + t] = gram[(long long)(m + 1 + a) * ldg + m + 1 + b]; }
+    if (threadIdx.x == 0) stats[0] = gram[(long long)m * ldg + m];
+    for (int t = threadIdx.x; t < c; t += blockDim.x) stats[1 + t] = gram[(long long)m * ldg + m + 1 + t];
+    for (int t = threadIdx.x; t < c * c; t += blockDim.x) { const int a = t / c, b = t - a * c; stats[1 + c + t] = gram[(long long)(m + 1 + a) * ldg + m + 1 + b]; }
 }
 __global__ void finalize_interaction_kernel(const int* rho_idx, const double* v0, const double* v1, const double* grid, long long p,
                                             double* rho1, double* e2, double* g2, double* eps2) {
@@ -334,7 +352,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
                     const double* rho_host, int R, cudaStream_t st) {
     if (!y || !W || !E0 || !E1 || n <= 0 || c <= 0 || k0 <= 0 || k1 <= 0 || mL < 0 || R <= 0 || (mL > 0 && !L)) { set_error("crm_setup: bad arguments"); return CRM_ERR_INVALID; }
     if (n > 2000000000LL) { set_error("n too large"); return CRM_ERR_UNSUPPORTED; }
-    if (c > 7) { set_error("at most 7 covariate columns are supported (got %d)", c); return CRM_ERR_UNSUPPORTED; }
+    if (c > 60) { set_error("at most 60 covariate columns are supported (got %d)", c); return CRM_ERR_UNSUPPORTED; }
     if (R > 64) { set_error("rho grid too long"); return CRM_ERR_UNSUPPORTED; }
     if (k1 + mL > 30000) { set_error("background half-covariance has %lld columns; limit is 30000", (long long)(k1 + mL)); return CRM_ERR_UNSUPPORTED; }
     h->ready = false;
@@ -396,7 +414,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     op.B = Hx; op.ldb = ldH; op.b_cols = Mx;
     op.B2 = Hx; op.ldb2 = ldH; op.b2_cols = Mx;
     CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)n, 0, Mx, 0, Mx, h->gram.as<double>(), ldH, 1, st));
-    extract_stats_kernel<<<1, 64, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
+    extract_stats_kernel<<<1, 1024, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
 
     // per-rho eigendecomposition (cuSOLVER, one-off per gene) with one pooled cuSOLVER context per device.  Measured on
@@ -456,6 +474,11 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     rotate_null_kernel<<<blocks_for((long long)R * mp, 128), 128, 0, st>>>(h->Tt.as<double>(), (long long)R * mp, h->gram.as<double>(), ldH, m,
                                                                          mp, R, c, h->yr.as<double>(), h->Wr.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
+    CRM_CHECK(h->YW.reserve((size_t)R * (1 + c) * mp * 8));
+    CRM_CHECK(h->ywgram.reserve((size_t)(1 + c) * (1 + c) * 8));
+    build_yw_kernel<<<blocks_for(std::max<long long>((long long)R * (1 + c) * mp, (long long)(1 + c) * (1 + c)), 256), 256, 0, st>>>(
+        h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
     std::vector<int> info(2 * R, 0);
     CRM_CUDA(cudaMemcpyAsync(info.data(), h->devinfo.as<int>(), (size_t)(2 * R) * sizeof(int), cudaMemcpyDeviceToHost, st));
     CRM_CUDA(cudaStreamSynchronize(st));
@@ -501,7 +524,7 @@ static int reserve_scan(Handle* h, long long B, bool interaction) {
     CRM_CHECK(h->Hg.reserve((size_t)m * round_up(B, 2) * 8));
     const size_t pr = (size_t)B * R;
     CRM_CHECK(h->fit_lml.reserve(pr * 8)); CRM_CHECK(h->fit_delta.reserve(pr * 8)); CRM_CHECK(h->fit_scale.reserve(pr * 8));
-    CRM_CHECK(h->fit_beta.reserve(pr * 8 * 8)); CRM_CHECK(h->fit_x.reserve(pr * 8));
+    CRM_CHECK(h->fit_beta.reserve(pr * (size_t)(h->c + 2) * 8)); CRM_CHECK(h->fit_x.reserve(pr * 8));
     CRM_CHECK(h->fit_nfev.reserve(pr * 4)); CRM_CHECK(h->fit_flags.reserve(pr * 4));
     CRM_CHECK(h->rho_idx.reserve((size_t)B * 4)); CRM_CHECK(h->best_lml.reserve((size_t)B * 8));
     CRM_CHECK(h->v0.reserve((size_t)B * 8)); CRM_CHECK(h->v1.reserve((size_t)B * 8));
@@ -718,6 +741,7 @@ static int do_scan_interaction(Handle* h, int donor_level, const double* G, long
                                const crm_scan_diag_t* dg, cudaStream_t st) {
     if (!h->ready) { set_error("crm_scan_interaction: handle is not set up"); return CRM_ERR_STATE; }
     CRM_CHECK(select_space(h, donor_level, "crm_scan_interaction"));
+    if (h->c > 7) { set_error("crm_scan_interaction supports at most 7 covariate columns (got %d)", h->c); return CRM_ERR_UNSUPPORTED; }
     if (donor_level && Gtest) { set_error("crm_scan_interaction: permuted tested genotypes are not supported with donor-level input"); return CRM_ERR_UNSUPPORTED; }
     if (!G || p < 0 || ldg < p || !out_pv || !out_rho1 || !out_e2 || !out_g2 || !out_eps2) { set_error("crm_scan_interaction: bad arguments"); return CRM_ERR_INVALID; }
     if (p == 0) return CRM_OK;
@@ -748,7 +772,14 @@ static int do_scan_association(Handle* h, int donor_level, const double* G, long
     fa.m = m; fa.mp = mp; fa.R = R; fa.c = c; fa.p = 1; fa.n = (double)h->n; fa.restricted = 0; fa.fixed_x = nullptr;
     fa.lml = h->fit_lml.as<double>(); fa.delta = h->fit_delta.as<double>(); fa.scale = h->fit_scale.as<double>();
     fa.beta = h->fit_beta.as<double>(); fa.xopt = h->fit_x.as<double>(); fa.nfev = h->fit_nfev.as<int>(); fa.flags = h->fit_flags.as<int>();
-    CRM_CHECK(launch_fit(fa, false, st));
+    // designs wider than the register-resident K2 kernel go through the shared-memory kernel K5
+    BetaArgs wa{};
+    wa.S = h->S.as<double>(); wa.S_stride = mp; wa.Zs = h->YW.as<double>(); wa.Zs_stride = (long long)(1 + c) * mp; wa.Zp = nullptr;
+    wa.Zp_snp_stride = 0; wa.Zp_rho_stride = 0; wa.shared_gram = h->ywgram.as<double>(); wa.rot = nullptr; wa.rot_ld = 0; wa.col_y = m; wa.col_W = m + 1;
+    wa.kexp = 1; wa.lin = nullptr; wa.lin_ld = 0; wa.sq = nullptr; wa.sq_ld = 0; wa.rho = nullptr; wa.m = m; wa.mp = mp; wa.c = c; wa.k0 = 0; wa.R = R; wa.p = 1;
+    wa.has_g = 0; wa.mix_rho = 0; wa.restricted = 0; wa.fixed_x = nullptr; wa.n = (double)h->n;
+    wa.lml = fa.lml; wa.delta = fa.delta; wa.scale = fa.scale; wa.beta = fa.beta; wa.ucoef = nullptr; wa.xopt = fa.xopt; wa.nfev = fa.nfev; wa.flags = fa.flags;
+    if (c > 7) CRM_CHECK(launch_beta_fit(wa, st)); else CRM_CHECK(launch_fit(fa, false, st));
     std::vector<double> lml(R), delta(R), scale(R), xopt(R);
     CRM_CUDA(cudaMemcpyAsync(lml.data(), fa.lml, R * 8, cudaMemcpyDeviceToHost, st));
     CRM_CUDA(cudaMemcpyAsync(delta.data(), fa.delta, R * 8, cudaMemcpyDeviceToHost, st));
@@ -789,7 +820,16 @@ static int do_scan_association(Handle* h, int donor_level, const double* G, long
         fb.gy = C + m; fb.gy_ld = ldH; fb.gW = C + m + 1; fb.gW_ld = ldH; fb.gg = sq; fb.gg_ld = 2;
         fb.R = 1; fb.p = (int)b; fb.restricted = 0; fb.fixed_x = fast ? xfix : nullptr;
         fb.lml = out_alt ? out_alt + s0 : h->best_lml.as<double>();
-        CRM_CHECK(launch_fit(fb, true, st));
+        if (c + 1 > 8) {
+            BetaArgs wb = wa;
+            wb.S = fb.S; wb.S_stride = 0; wb.Zs = h->YW.as<double>() + (long long)rb * (1 + c) * mp; wb.Zs_stride = 0;
+            wb.Zp = h->gr.as<double>(); wb.Zp_snp_stride = mp; wb.Zp_rho_stride = 0;
+            wb.rot = C; wb.rot_ld = ldH; wb.sq = sq; wb.sq_ld = 2; wb.R = 1; wb.p = (int)b; wb.has_g = 1; wb.fixed_x = fb.fixed_x;
+            wb.lml = fb.lml; wb.xopt = nullptr;
+            CRM_CHECK(launch_beta_fit(wb, st));
+        } else {
+            CRM_CHECK(launch_fit(fb, true, st));
+        }
         CRM_CHECK(launch_lrt(fb.lml, best, b, out_pv + s0, st));
         return (int)CRM_OK;
     });
@@ -869,6 +909,8 @@ static int do_predict(Handle* h, int donor_level, const double* G, long long ldg
         }
         BetaArgs ba{};
         ba.S = mB > 0 ? h->S.as<double>() + (long long)r0 * mp : nullptr; ba.Zs = h->Zs.as<double>(); ba.Zp = h->Zp.as<double>();
+        ba.S_stride = 0; ba.Zs_stride = 0; ba.Zp_snp_stride = (long long)kexp * mp; ba.Zp_rho_stride = 0;
+        ba.has_g = 1; ba.mix_rho = 1; ba.restricted = 1; ba.fixed_x = nullptr; ba.xopt = nullptr;
         ba.shared_gram = h->sgram.as<double>();
         ba.rot = C; ba.rot_ld = ldH; ba.col_y = h->m; ba.col_W = h->m + 1; ba.kexp = kexp;
         ba.lin = h->lin.as<double>(); ba.lin_ld = h->ld2; ba.sq = h->sq.as<double>(); ba.sq_ld = h->ld2;

@@ -68,20 +68,26 @@ struct PvalArgs {
 
 constexpr int PV_MAXLAM = 128;
 
-// K5 (betas.cuh): effect-size model of predict_interaction, one CTA per (SNP, rho index)
+// K5 (betas.cuh): general-design LMM fit in shared memory, one CTA per (SNP, rho index).  Two uses:
+//  * effect-size model of predict_interaction: design [W g E0], covariance (1-d)(rho U U' + (1-rho) B) + d I with
+//    U = g.E0 (k0 columns, Woodbury update), S / Zs shared by all rho (mix_rho = 1);
+//  * plain two-component fits with wide designs (more than 8 columns; K2 covers the narrow ones): k0 = 0, covariance
+//    (1-d) K_rho + d I with per-rho spectra and rotated columns (mix_rho = 0, strides select the rho block).
 struct BetaArgs {
-    const double* S;            // [mp] spectrum of the background B = sum_i L_i L_i' (zeros beyond its rank)
-    const double* Zs;           // [1 + c + k0][mp]  rotated shared columns  Q_B'[y | W | E0]
-    const double* Zp;           // [p][1 + k0][mp]   rotated per-SNP columns Q_B'[g | g.E0]
+    const double* S;            // [mp] spectrum (zeros beyond the kept rank); + rho_index * S_stride
+    const double* Zs;           // [1 + c + k0][mp]  rotated shared columns  Q'[y | W | E0]; + rho_index * Zs_stride
+    const double* Zp;           // [p][has_g + k0][mp] rotated per-SNP columns Q'[g | g.E0]; SNP stride Zp_snp_stride, + rho_index * Zp_rho_stride
+    long long S_stride, Zs_stride, Zp_snp_stride, Zp_rho_stride;
     const double* shared_gram;  // [(1 + c + k0)^2]  plain Gram of [y | W | E0]
     const double* rot; long long rot_ld; int col_y, col_W, kexp;   // K1 output rows (s*kexp + j): y'(.) and W'(.) columns
-    const double* lin; long long lin_ld;   // per SNP [sum g | g'E0 (k0) | g'(E0_j E0_l) pairs]
+    const double* lin; long long lin_ld;   // per SNP [sum g | g'E0 (k0) | g'(E0_j E0_l) pairs]   (k0 > 0 only)
     const double* sq; long long sq_ld;     // per SNP [g'g | (g^2)'E0 (k0) | (g^2)'(E0_j E0_l) pairs]
-    const double* rho;          // [R] grid (device)
-    int m, mp, c, k0, R, p;
+    const double* rho;          // [R] grid (device); used when mix_rho
+    int m, mp, c, k0, R, p, has_g, mix_rho, restricted;
+    const double* fixed_x;      // non-null: evaluate at logit(delta) = *fixed_x instead of searching
     double n;
-    // outputs [p][R]: lml, delta, scale; beta [p][R][c + 1 + k0]; ucoef [p][R][k0] = (g.E0)' K^-1 (y - M beta)
-    double* lml; double* delta; double* scale; double* beta; double* ucoef; int* nfev; int* flags;
+    // outputs [p][R]: lml, delta, scale; beta [p][R][c + has_g + k0]; ucoef [p][R][k0] = (g.E0)' K^-1 (y - M beta) (k0 > 0)
+    double* lml; double* delta; double* scale; double* beta; double* ucoef; double* xopt; int* nfev; int* flags;
 };
 constexpr int BETA_MAX_NZ = 67;
 

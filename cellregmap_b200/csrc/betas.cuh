@@ -98,7 +98,8 @@ __device__ inline void warp_jacobi_vec(double* A, double* V, int n, int lane) {
 
 struct BetaProblem {
     // sizes
-    int m, mp, c, k0, P, NZ, lane, tid;
+    int m, mp, c, k0, hg, P, NZ, lane, tid;
+    bool restricted, mix_rho;
     double n, rho;
     // rotated columns
     const double* S; const double* Zs; const double* Zp;
@@ -112,11 +113,11 @@ struct BetaProblem {
     double last_delta, last_scale;
 
     __device__ __forceinline__ const double* column(int col) const {
-        // Z = [y | W (c) | g | E0 (k0) | U (k0)]
+        // Z = [y | W (c) | g (hg = 0/1) | E0 (k0) | U (k0)]
         if (col <= c) return Zs + (long long)col * mp;
-        if (col == c + 1) return Zp;
-        if (col <= c + 1 + k0) return Zs + (long long)(col - 1) * mp;
-        return Zp + (long long)(col - c - 1 - k0) * mp;
+        if (hg && col == c + 1) return Zp;
+        if (col <= c + hg + k0) return Zs + (long long)(col - hg) * mp;
+        return Zp + (long long)(col - c - 1 - k0) * mp;      // U_j sits at Zp[hg + j]: col - (1 + P) + hg
     }
 
     // weighted Gram  sum_i w_i z_a z_b  over the rotated rows into acc[]; mode 0: w = 1, mode 1: w = 1 / d_i (+ sum log d_i)
@@ -162,7 +163,7 @@ struct BetaProblem {
     __device__ double eval(double x) {
         nfev++;
         const double delta = logistic_delta(x), omd = 1.0 - delta;
-        const double t = omd * (1.0 - rho), a = omd * rho;
+        const double t = mix_rho ? omd * (1.0 - rho) : omd, a = mix_rho ? omd * rho : 0.0;
         double acc[BETA_MAXE];
         double ld = stream_gram(acc, 1, t, delta);
         const double inv_delta = 1.0 / delta;
@@ -176,7 +177,7 @@ struct BetaProblem {
             double logdetK = ld + (n - m) * log(delta);
             // Gk = Gw[yM, yM]
             for (int e = lane; e < nzm * nzm; e += 32) { const int i = e / nzm, j = e - i * nzm; Gk[e] = Gw[i * NZ + j]; }
-            if (a > 0.0) {
+            if (a > 0.0 && k0 > 0) {
                 for (int e = lane; e < k0 * k0; e += 32) { const int i = e / k0, j = e - i * k0; inner[e] = Gw[(u0 + i) * NZ + (u0 + j)] + (i == j ? 1.0 / a : 0.0); }
                 for (int e = lane; e < k0 * nzm; e += 32) { const int i = e / nzm, j = e - i * nzm; X[e] = Gw[(u0 + i) * NZ + j]; }
                 __syncwarp();
@@ -228,7 +229,7 @@ struct BetaProblem {
             warp_backward_solve(Ar, P, P, tb, 1, 1, lane);     // tb = A'^-1 b'
             const double scale = fmax((Gk[0] - bt) / df, CRM_EPS_SMALL);
             double lml = -0.5 * (df * CRM_LOG2PI + df + n * log(scale) + logdetK);
-            lml += 0.5 * (logdetXX - (la - rank * log(scale)));
+            if (restricted) lml += 0.5 * (logdetXX - (la - rank * log(scale)));
             if (lane == 0) { red[0] = -lml; red[1] = scale; red[2] = delta; }
         }
         __syncthreads();
@@ -244,11 +245,13 @@ __global__ void __launch_bounds__(BETA_THREADS) crm_beta_fit_kernel(const BetaAr
     extern __shared__ __align__(16) double bsm[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int s = blockIdx.x, ri = blockIdx.y;
-    const int c = a.c, k0 = a.k0, P = c + 1 + k0, NZ = 2 + c + 2 * k0, nzm = 1 + P;
+    const int c = a.c, k0 = a.k0, hg = a.has_g ? 1 : 0, P = c + hg + k0, NZ = 1 + P + k0, nzm = 1 + P;
     BetaProblem pr;
-    pr.m = a.m; pr.mp = a.mp; pr.c = c; pr.k0 = k0; pr.P = P; pr.NZ = NZ; pr.lane = lane; pr.tid = tid;
-    pr.n = a.n; pr.rho = a.rho[ri];
-    pr.S = a.S; pr.Zs = a.Zs; pr.Zp = a.Zp + (long long)s * (1 + k0) * a.mp;
+    pr.m = a.m; pr.mp = a.mp; pr.c = c; pr.k0 = k0; pr.hg = hg; pr.P = P; pr.NZ = NZ; pr.lane = lane; pr.tid = tid;
+    pr.restricted = a.restricted != 0; pr.mix_rho = a.mix_rho != 0;
+    pr.n = a.n; pr.rho = a.mix_rho ? a.rho[ri] : 0.0;
+    pr.S = a.S + (long long)ri * a.S_stride; pr.Zs = a.Zs + (long long)ri * a.Zs_stride;
+    pr.Zp = a.Zp + (long long)s * a.Zp_snp_stride + (long long)ri * a.Zp_rho_stride;
     double* q = bsm;
     pr.ZZ = q; q += NZ * NZ;
     pr.ZZres = q; q += NZ * NZ;
@@ -272,17 +275,17 @@ __global__ void __launch_bounds__(BETA_THREADS) crm_beta_fit_kernel(const BetaAr
     }
     // ---- plain Gram Z'Z ----
     const int ns = 1 + c + k0;                       // shared columns [y | W | E0]
-    const double* row_g = a.rot + (long long)s * a.kexp * a.rot_ld;
-    const double* lin = a.lin + (long long)s * a.lin_ld;
-    const double* sq = a.sq + (long long)s * a.sq_ld;
+    const double* row_g = hg ? a.rot + (long long)s * a.kexp * a.rot_ld : nullptr;
+    const double* lin = a.lin ? a.lin + (long long)s * a.lin_ld : nullptr;
+    const double* sq = hg ? a.sq + (long long)s * a.sq_ld : nullptr;
 #pragma unroll
     for (int u = 0; u < BETA_MAXE; u++) {
         if (pr.ea[u] < 0) continue;
         const int ia = pr.ea[u], ib = pr.eb[u];      // ia >= ib
         // classify columns: kind 0 shared (index into [y|W|E0]), 1 g, 2 U_j
         int ka, ja, kb, jb;
-        if (ia <= c) { ka = 0; ja = ia; } else if (ia == c + 1) { ka = 1; ja = 0; } else if (ia <= c + 1 + k0) { ka = 0; ja = ia - 1; } else { ka = 2; ja = ia - c - 2 - k0; }
-        if (ib <= c) { kb = 0; jb = ib; } else if (ib == c + 1) { kb = 1; jb = 0; } else if (ib <= c + 1 + k0) { kb = 0; jb = ib - 1; } else { kb = 2; jb = ib - c - 2 - k0; }
+        if (ia <= c) { ka = 0; ja = ia; } else if (hg && ia == c + 1) { ka = 1; ja = 0; } else if (ia <= c + hg + k0) { ka = 0; ja = ia - hg; } else { ka = 2; ja = ia - 1 - P; }
+        if (ib <= c) { kb = 0; jb = ib; } else if (hg && ib == c + 1) { kb = 1; jb = 0; } else if (ib <= c + hg + k0) { kb = 0; jb = ib - hg; } else { kb = 2; jb = ib - 1 - P; }
         double zz;
         if (ka == 0 && kb == 0) zz = a.shared_gram[ja * ns + jb];
         else if (ka + kb == 1) {                     // g with a shared column
@@ -326,12 +329,12 @@ __global__ void __launch_bounds__(BETA_THREADS) crm_beta_fit_kernel(const BetaAr
     __syncthreads();
     pr.logdetXX = pr.red[0]; pr.rank = (int)pr.red[1];
     pr.mask = (unsigned long long)pr.red[2] | ((unsigned long long)pr.red[3] << 32);
-    pr.df = a.n - pr.rank;
+    pr.df = pr.restricted ? a.n - pr.rank : a.n;
     pr.nfev = 0; pr.flags = pr.mask ? 1 : 0;
     __syncthreads();
     // ---- fit ----
-    double fbest;
-    const double xbest = brent_minimize(pr, &fbest);
+    double fbest, xbest;
+    if (a.fixed_x) xbest = *a.fixed_x; else xbest = brent_minimize(pr, &fbest);
     const double f = pr.eval(xbest);
     pr.nfev--;
     // ---- outputs: lml, delta, scale, beta (design space), ucoef = U' K^-1 (y - M beta) ----
@@ -354,7 +357,8 @@ __global__ void __launch_bounds__(BETA_THREADS) crm_beta_fit_kernel(const BetaAr
             pr.X[j] = v; pr.X[k0 + j] = v;
         }
         __syncwarp();
-        if (av > 0.0) {
+        if (k0 == 0) {
+        } else if (av > 0.0) {
             // pr.inner still holds the Cholesky factor of the last evaluation (same x)
             warp_forward_solve(pr.inner, k0, k0, pr.X + k0, 1, 1, lane);
             warp_backward_solve(pr.inner, k0, k0, pr.X + k0, 1, 1, lane);
@@ -366,7 +370,10 @@ __global__ void __launch_bounds__(BETA_THREADS) crm_beta_fit_kernel(const BetaAr
         } else {
             for (int j = lane; j < k0; j += 32) a.ucoef[o * k0 + j] = pr.X[j] / pr.last_scale;
         }
-        if (lane == 0) { a.lml[o] = -f; a.delta[o] = pr.last_delta; a.scale[o] = pr.last_scale; a.nfev[o] = pr.nfev; a.flags[o] = pr.flags; }
+        if (lane == 0) {
+            a.lml[o] = -f; a.delta[o] = pr.last_delta; a.scale[o] = pr.last_scale; a.nfev[o] = pr.nfev; a.flags[o] = pr.flags;
+            if (a.xopt) a.xopt[o] = xbest;
+        }
     }
 }
 

@@ -6,8 +6,8 @@
 namespace crm {
 
 int launch_beta_fit(const BetaArgs& ba, cudaStream_t st) {
-    const int P = ba.c + 1 + ba.k0, NZ = 2 + ba.c + 2 * ba.k0, nzm = 1 + P;
-    if (NZ > BETA_MAX_NZ || P > 64) { set_error("2 + covariates + 2 * contexts = %d exceeds the compiled limit %d", NZ, BETA_MAX_NZ); return CRM_ERR_UNSUPPORTED; }
+    const int P = ba.c + (ba.has_g ? 1 : 0) + ba.k0, NZ = 1 + P + ba.k0, nzm = 1 + P;
+    if (NZ > BETA_MAX_NZ || P > 64 || P < 1) { set_error("design of %d columns (+ %d random-effect columns) exceeds the compiled limit of %d in total", P, ba.k0, BETA_MAX_NZ - 1); return CRM_ERR_UNSUPPORTED; }
     if (ba.p <= 0) return CRM_OK;
     size_t doubles = (size_t)3 * NZ * NZ + (size_t)NZ * (BETA_CHUNK + 1) + BETA_CHUNK + (size_t)P * P + (size_t)ba.k0 * ba.k0 +
                      (size_t)ba.k0 * nzm + (size_t)nzm * nzm + (size_t)P * P + P + (P + (size_t)P * P) + 8;

@@ -1,0 +1,108 @@
+"""Parity at the BASELINE.json sizes: oracle comparison on a sample of SNPs where the oracle finishes in seconds,
+and size-independent properties of the scan at full size (shard invariance, scale invariance of the score test,
+cell-order invariance, donor-level == expanded)."""
+import numpy as np
+import pytest
+
+from cellregmap_b200.synth import make_data
+
+pytestmark = pytest.mark.gpu
+DLOG10_P = 1e-4
+
+
+def _dlog10(a, b):
+    """max |log10 a - log10 b| where either is positive; entries that underflow to exactly 0 in both count as equal."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    both_zero = (a == 0) & (b == 0)
+    with np.errstate(divide="ignore"):
+        d = np.abs(np.log10(a[~both_zero]) - np.log10(b[~both_zero]))
+    return float(d.max()) if d.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    """BASELINE configs[1]: n = 10k cells, 200 donors, k = 20, low-rank hK (q = 10 -> m = 220), 2k SNPs."""
+    return make_data(n=10000, donors=200, k=20, p=2000, q=10, seed=42)
+
+
+def test_config2_oracle_sample(cuda_device, cfg2):
+    from cellregmap_b200 import run_interaction
+    from oracle import crm_port
+    d = cfg2
+    pv, info = run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    assert pv.shape == (2000,) and np.all((pv > 0) & (pv <= 1))
+    sample = np.r_[0:12, 5, 6, 10, 11, 1990:2000]
+    ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, d.G[:, sample], W=d.W, hK=d.hK, qs_method="gram")
+    np.testing.assert_array_equal(info["rho1"][sample], ref_info["rho1"])
+    assert np.max(np.abs(np.log10(pv[sample]) - np.log10(ref_pv))) <= DLOG10_P
+    for key in ("e2", "g2", "eps2"):
+        np.testing.assert_allclose(info[key][sample], ref_info[key], rtol=1e-6)
+    # the simulated GxC SNPs are the strongest hits
+    assert set(np.argsort(pv)[:2]) == {10, 11}
+
+
+def test_config2_properties(cuda_device, cfg2):
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    d = cfg2
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    Gt = torch.from_numpy(d.G).cuda()
+    pv, info = model.scan_interaction(Gt)
+    # 1. SNP shards (what each GPU of a multi-GPU run sees) reproduce the full scan bit for bit
+    parts = [model.scan_interaction(Gt[:, lo:hi].contiguous())[0] for lo, hi in ((0, 700), (700, 701), (701, 2000))]
+    np.testing.assert_array_equal(np.concatenate(parts), pv)
+    # 2. the score test is invariant to the scale of the genotype column (Q and all eigenvalues scale together)
+    pv2, info2 = model.scan_interaction(Gt * 2.0)
+    np.testing.assert_array_equal(info2["rho1"], info["rho1"])
+    assert np.max(np.abs(np.log10(pv2) - np.log10(pv))) <= 1e-6
+    # 3. p-values are ordered like the reference would order them: finite, in (0, 1], no NaN
+    assert np.isfinite(pv).all() and pv.min() > 0 and pv.max() <= 1
+
+
+def test_cell_order_invariance(cuda_device, cfg2):
+    """Permuting the cells (rows of every input) leaves every output unchanged up to summation order."""
+    from cellregmap_b200 import run_interaction
+    d = cfg2
+    sub = slice(0, 300)
+    pv, info = run_interaction(d.y, d.E, d.G[:, sub], W=d.W, hK=d.hK)
+    perm = np.random.default_rng(0).permutation(d.y.shape[0])
+    pv_p, info_p = run_interaction(d.y[perm], d.E[perm], np.ascontiguousarray(d.G[perm][:, sub]), W=d.W[perm], hK=d.hK[perm])
+    np.testing.assert_array_equal(info_p["rho1"], info["rho1"])
+    assert np.max(np.abs(np.log10(pv_p) - np.log10(pv))) <= 1e-6
+
+
+def test_config3_shapes_sample(cuda_device):
+    """BASELINE configs[2] shapes (n = 100k cells, 1,000 donors, k = 20, m = 1,020) on 256 SNPs: donor-level ingress equals
+    the expanded scan, shards are bit-exact, and a handful of SNPs are checked against the oracle."""
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    from oracle import crm_port
+    d = make_data(n=100000, donors=1000, k=20, p=256, q=50, seed=7, v_gxc=0.002, v_persistent=0.002)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    Gt = torch.from_numpy(d.G).cuda()
+    pv, info = model.scan_interaction(Gt)
+    pv_a, _ = model.scan_interaction(Gt[:, :100].contiguous())
+    np.testing.assert_array_equal(pv_a, pv[:100])
+    Gd = np.zeros((1000, 256))
+    Gd[d.donor] = d.G
+    pv_d, info_d = model.scan_interaction(Gd, donor_index=d.donor)
+    np.testing.assert_array_equal(info_d["rho1"], info["rho1"])
+    assert _dlog10(pv_d, pv) <= 1e-6
+    sample = [0, 10, 11]
+    ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, d.G[:, sample], W=d.W, hK=d.hK, qs_method="gram")
+    np.testing.assert_array_equal(info["rho1"][sample], ref_info["rho1"])
+    assert _dlog10(pv[sample], ref_pv) <= DLOG10_P
+    assert pv[10] < 1e-6 and pv[11] < 1e-6
+
+
+def test_config4_association_sample(cuda_device):
+    """BASELINE configs[3] family: run_association (LRT) at n = 50k on a sample of SNPs against the oracle."""
+    from cellregmap_b200 import run_association
+    from oracle import crm_port
+    d = make_data(n=50000, donors=500, k=20, p=64, q=10, seed=11)
+    pv, info = run_association(d.y, d.W, d.E, d.G, hK=d.hK)
+    sample = [0, 5, 6, 63]
+    # the reference's positional quirk makes W the context matrix: the background is rho W W' + (1-rho) hK hK'
+    ref_pv, ref_info = crm_port.run_association(d.y, d.W, d.E, d.G[:, sample], hK=d.hK)
+    np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+    assert np.max(np.abs(np.log10(pv[sample]) - np.log10(ref_pv))) <= DLOG10_P

@@ -176,6 +176,22 @@ def test_estimate_betas(cuda_device, onehot):
     np.testing.assert_array_equal(bgxe2, bgxe)
 
 
+def test_association_wide_design(cuda_device):
+    """run_association's positional quirk turns the k contexts into fixed-effect covariates (reference :498): with k = 12 the
+    design [E g] has 13 columns and goes through the shared-memory fit kernel (null model and per-SNP fits)."""
+    from cellregmap_b200 import run_association, run_association_fast
+    from oracle import crm_port
+    d = make_data(n=500, donors=40, k=12, p=30, q=6, seed=31)
+    ref_pv, ref_info = crm_port.run_association(d.y, d.W, d.E, d.G, hK=d.hK)
+    pv, info = run_association(d.y, d.W, d.E, d.G, hK=d.hK)
+    for key in ("rho1", "e2", "g2", "eps2"):
+        np.testing.assert_allclose(info[key], ref_info[key], rtol=RTOL_VC, atol=1e-12)
+    assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= DLOG10_P
+    ref_pf, _ = crm_port.run_association_fast(d.y, d.W, d.E, d.G, hK=d.hK)
+    pf, _ = run_association_fast(d.y, d.W, d.E, d.G, hK=d.hK)
+    assert np.max(np.abs(np.log10(pf) - np.log10(ref_pf))) <= DLOG10_P
+
+
 def test_input_validation(cuda_device):
     from cellregmap_b200 import CellRegMap
     d = make_data(n=100, donors=10, k=3, p=5, q=2, seed=1)
