@@ -210,6 +210,8 @@ def run_b200_arm(a):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     import cellregmap_b200 as crm
@@ -332,7 +334,7 @@ def run_b200_arm(a):
         h2d = G_h.numel() * 8 + sum(t.numel() * 8 for t in (y_h, W_h, E_h, hK_h))
         e2e = {"value": world * p / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(5 * p * 8),
                "ms_per_step": ms_e}
-        assert np.array_equal(pv_h, res[0].cpu().numpy()), "host and device paths disagree"
+        assert np.array_equal(pv_h, res[5 * rank if world > 1 else 0].cpu().numpy()), "host and device paths disagree"
         del G_h
 
     # ---- CPU baseline (rank 0, N = 1 only) ----

@@ -126,6 +126,10 @@ class CellRegMap:
                 assert n == L.shape[0]
             n_blocks = len(blocks)
             Lcat = torch.cat(blocks, dim=1).contiguous() if n_blocks else None
+        if not bool(torch.isfinite(self._y).all()):
+            raise ValueError("There are non-finite values in the outcome.")          # glimix_core.lmm.LMM
+        if not bool(torch.isfinite(self._W).all()):
+            raise ValueError("There are non-finite values in the covariates matrix.")
         assert self._W.ndim == 2
         assert self._E0.ndim == 2
         assert self._E1.ndim == 2

@@ -93,7 +93,7 @@ struct Handle {
     bool donors_set = false;
     DevBuf HxE_D, A2_D, dperm, doff;
     DevBuf HxE;           // optional n x (kexp * ldH) pre-expanded basis [Hx | Hx.E0_1 | ... | Hx.E0_k] (see launch_rotation)
-    bool use_hxe = false;
+    bool use_hxe = false, hxe_built = false;
     DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
     // null-model state for the association scans
     // scan workspaces
@@ -319,12 +319,8 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
     CRM_CUDA(cudaGetLastError()); count_launch();
     build_a2_kernel<<<blocks_for(h->n * h->ld2, 256), 256, 0, st>>>(E0, lde0, h->n, h->k0, h->A2.as<double>(), h->ld2);
     CRM_CUDA(cudaGetLastError()); count_launch();
-    if (h->use_hxe) {
-        build_hxe_kernel<<<blocks_for(h->n * h->kexp * h->ldH, 256), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, h->n,
-                                                                                   h->HxE.as<double>());
-        CRM_CUDA(cudaGetLastError()); count_launch();
-    }
-    h->cells.K = h->n; h->cells.HxE = h->use_hxe ? h->HxE.as<double>() : nullptr; h->cells.ldE = (long long)h->kexp * h->ldH;
+    h->hxe_built = false;    // the pre-expanded basis is (re)built by the first cell-level rotation that needs it
+    h->cells.K = h->n; h->cells.HxE = nullptr; h->cells.ldE = (long long)h->kexp * h->ldH;
     h->cells.Hx = h->Hx.as<double>(); h->cells.ldHx = h->ldH; h->cells.A2 = h->A2.as<double>(); h->cells.ld2 = h->ld2;
     if (h->donors_set) CRM_CHECK(aggregate_donors(h, st));
     return CRM_OK;
@@ -335,6 +331,14 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
 // loop is a plain DMMA contraction (99% of the FP64 tensor peak, costs n*kexp*ldH*8 bytes of HBM once per gene); without
 // it the factor is applied to the genotype fragments on the fly (EXPAND mode, ~90% of peak, no extra memory).
 static int launch_rotation(Handle* h, const double* G, long long ldg, long long gcols, long long B, double* C, cudaStream_t st) {
+    if (h->gs == &h->cells && h->use_hxe && !h->hxe_built) {
+        CRM_CHECK(h->HxE.reserve((size_t)h->n * h->kexp * h->ldH * 8));
+        build_hxe_kernel<<<blocks_for(h->n * h->kexp * h->ldH, 256), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, h->n,
+                                                                                   h->HxE.as<double>());
+        CRM_CUDA(cudaGetLastError()); count_launch();
+        h->cells.HxE = h->HxE.as<double>();
+        h->hxe_built = true;
+    }
     const Handle::GenoSpace& gs = *h->gs;
     GemmOperands op{};
     op.B = G; op.ldb = ldg; op.b_cols = gcols;
@@ -404,7 +408,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         }
         const char* env = getenv("CRM_NO_HXE");
         h->use_hxe = !(env && atoi(env) != 0) && (h->HxE.cap >= bytes || bytes < (size_t)(0.30 * (double)(free_b + h->HxE.cap))) && (long long)h->kexp * ldH < 2000000000LL;
-        if (h->use_hxe) CRM_CHECK(h->HxE.reserve(bytes)); else h->HxE.release();
+        if (!h->use_hxe) h->HxE.release();
     }
     CRM_CHECK(build_test_contexts(h, E0, lde0, st));
 

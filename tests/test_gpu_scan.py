@@ -247,3 +247,39 @@ def test_donor_level_genotypes_match_expanded(cuda_device):
     bg_d, bx_d = estimate_betas(d.y, d.W, d.E, Gd[:, :9], hK=d.hK, donor_index=d.donor)
     np.testing.assert_allclose(bg_d, bg_e, rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(bx_d, bx_e, rtol=0, atol=1e-6 * np.abs(bx_e).max())
+
+
+def test_edge_cases(cuda_device):
+    """Empty SNP set, single SNP, single context, tiny n, monomorphic (rank-deficient design) and all-zero SNPs."""
+    import torch
+    from cellregmap_b200 import CellRegMap, run_interaction
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    from oracle import crm_port
+    d = make_data(n=64, donors=8, k=1, p=5, q=2, seed=33)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    pv, info = model.scan_interaction(np.zeros((64, 0)))
+    assert pv.shape == (0,) and info["rho1"].shape == (0,)
+    ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    pv, info = model.scan_interaction(d.G)
+    np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+    assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= DLOG10_P
+    pv1, _ = model.scan_interaction(d.G[:, [3]])
+    np.testing.assert_array_equal(pv1, pv[[3]])
+    # monomorphic SNP: g is collinear with the intercept, the reference drops the direction (economic SVD of X) and goes on
+    d2 = make_data(n=300, donors=30, k=4, p=6, q=3, seed=34)
+    G = d2.G.copy()
+    G[:, 2] = 1.0
+    ref_pv, ref_info = crm_port.run_interaction(d2.y, d2.E, G, W=d2.W, hK=d2.hK)
+    pv, info = run_interaction(d2.y, d2.E, G, W=d2.W, hK=d2.hK)
+    np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+    assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= DLOG10_P
+    # all-zero SNP: no positive eigenvalue -> the reference (chiscore) raises RuntimeError
+    G[:, 4] = 0.0
+    with pytest.raises(RuntimeError):
+        crm_port.run_interaction(d2.y, d2.E, G, W=d2.W, hK=d2.hK)
+    with pytest.raises(RuntimeError):
+        run_interaction(d2.y, d2.E, G, W=d2.W, hK=d2.hK)
+    # non-finite phenotype: ValueError like glimix-core's LMM
+    ybad = d2.y.copy(); ybad[0] = np.nan
+    with pytest.raises(ValueError):
+        CellRegMap(ybad, d2.E)
