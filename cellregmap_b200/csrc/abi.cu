@@ -407,7 +407,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
                 free_b += (size_t)(reserved - used);
         }
         const char* env = getenv("CRM_NO_HXE");
-        h->use_hxe = !(env && atoi(env) != 0) && (h->HxE.cap >= bytes || bytes < (size_t)(0.30 * (double)(free_b + h->HxE.cap))) && (long long)h->kexp * ldH < 2000000000LL;
+        h->use_hxe = !(env && atoi(env) != 0) && (h->HxE.cap >= bytes || bytes < (size_t)(0.45 * (double)(free_b + h->HxE.cap))) && (long long)h->kexp * ldH < 2000000000LL;
         if (!h->use_hxe) h->HxE.release();
     }
     CRM_CHECK(build_test_contexts(h, E0, lde0, st));
@@ -670,7 +670,18 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     fa.m = m; fa.mp = mp; fa.R = R; fa.c = c; fa.p = (int)B; fa.n = (double)h->n; fa.restricted = 1; fa.fixed_x = nullptr;
     fa.lml = h->fit_lml.as<double>(); fa.delta = h->fit_delta.as<double>(); fa.scale = h->fit_scale.as<double>();
     fa.beta = h->fit_beta.as<double>(); fa.xopt = h->fit_x.as<double>(); fa.nfev = h->fit_nfev.as<int>(); fa.flags = h->fit_flags.as<int>();
-    CRM_CHECK(launch_fit(fa, true, st));
+    if (c + 1 > 8) {    // designs wider than the register-resident K2 kernel: shared-memory kernel K5, per-rho spectra
+        BetaArgs wa{};
+        wa.S = fa.S; wa.S_stride = mp; wa.Zs = h->YW.as<double>(); wa.Zs_stride = (long long)(1 + c) * mp;
+        wa.Zp = h->gr.as<double>(); wa.Zp_snp_stride = (long long)R * mp; wa.Zp_rho_stride = mp;
+        wa.shared_gram = h->ywgram.as<double>(); wa.rot = C; wa.rot_ld = ldH; wa.col_y = m; wa.col_W = m + 1; wa.kexp = kexp;
+        wa.lin = nullptr; wa.lin_ld = 0; wa.sq = sq; wa.sq_ld = h->ld2; wa.rho = nullptr;
+        wa.m = m; wa.mp = mp; wa.c = c; wa.k0 = 0; wa.R = R; wa.p = (int)B; wa.has_g = 1; wa.mix_rho = 0; wa.restricted = 1; wa.fixed_x = nullptr; wa.n = (double)h->n;
+        wa.lml = fa.lml; wa.delta = fa.delta; wa.scale = fa.scale; wa.beta = fa.beta; wa.ucoef = nullptr; wa.xopt = fa.xopt; wa.nfev = fa.nfev; wa.flags = fa.flags;
+        CRM_CHECK(launch_beta_fit(wa, st));
+    } else {
+        CRM_CHECK(launch_fit(fa, true, st));
+    }
     // 6. best rho per SNP, grouping by rho
     CRM_CHECK(launch_select(fa.lml, fa.delta, fa.scale, (int)B, R, h->rho_idx.as<int>(), h->best_lml.as<double>(), h->v0.as<double>(),
                             h->v1.as<double>(), st));
@@ -745,10 +756,9 @@ static int do_scan_interaction(Handle* h, int donor_level, const double* G, long
                                const crm_scan_diag_t* dg, cudaStream_t st) {
     if (!h->ready) { set_error("crm_scan_interaction: handle is not set up"); return CRM_ERR_STATE; }
     CRM_CHECK(select_space(h, donor_level, "crm_scan_interaction"));
-    if (h->c > 7) { set_error("crm_scan_interaction supports at most 7 covariate columns (got %d)", h->c); return CRM_ERR_UNSUPPORTED; }
     if (donor_level && Gtest) { set_error("crm_scan_interaction: permuted tested genotypes are not supported with donor-level input"); return CRM_ERR_UNSUPPORTED; }
-    if (!G || p < 0 || ldg < p || !out_pv || !out_rho1 || !out_e2 || !out_g2 || !out_eps2) { set_error("crm_scan_interaction: bad arguments"); return CRM_ERR_INVALID; }
     if (p == 0) return CRM_OK;
+    if (!G || p < 0 || ldg < p || !out_pv || !out_rho1 || !out_e2 || !out_g2 || !out_eps2) { set_error("crm_scan_interaction: bad arguments"); return CRM_ERR_INVALID; }
     long long B = pick_batch(h, p, true);
     if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->gs->K))));
     CRM_CHECK(reserve_scan(h, B, true));
@@ -764,7 +774,7 @@ static int do_scan_association(Handle* h, int donor_level, const double* G, long
                                double* out_alt, double* info4, double* out_null, cudaStream_t st) {
     if (!h->ready) { set_error("crm_scan_association: handle is not set up"); return CRM_ERR_STATE; }
     CRM_CHECK(select_space(h, donor_level, "crm_scan_association"));
-    if (!G || p < 0 || ldg < p || !out_pv || !info4) { set_error("crm_scan_association: bad arguments"); return CRM_ERR_INVALID; }
+    if ((p > 0 && (!G || ldg < p || !out_pv)) || p < 0 || !info4) { set_error("crm_scan_association: bad arguments"); return CRM_ERR_INVALID; }
     const int R = h->R, mp = h->mp, m = h->m, c = h->c, ldH = h->ldH, Mx = h->Mx;
     long long B = pick_batch(h, std::max<long long>(p, 1), false);
     if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->gs->K))));
@@ -846,8 +856,8 @@ static int do_predict(Handle* h, int donor_level, const double* G, long long ldg
                       double* out_beta_g, double* out_beta_gxe, long long ldo, double* out_rho1, cudaStream_t st) {
     if (!h->ready) { set_error("crm_predict_interaction: handle is not set up"); return CRM_ERR_STATE; }
     CRM_CHECK(select_space(h, donor_level, "crm_predict_interaction"));
-    if (!G || p < 0 || ldg < p || !maf || !out_beta_g || !out_beta_gxe || ldo < p) { set_error("crm_predict_interaction: bad arguments"); return CRM_ERR_INVALID; }
     if (p == 0) return CRM_OK;
+    if (!G || p < 0 || ldg < p || !maf || !out_beta_g || !out_beta_gxe || ldo < p) { set_error("crm_predict_interaction: bad arguments"); return CRM_ERR_INVALID; }
     const int R = h->R, mp = h->mp, c = h->c, k0 = h->k0, kexp = h->kexp, ldH = h->ldH, Mx = h->Mx;
     const int ns = 1 + c + k0, P = c + 1 + k0;
     int r0 = -1;

@@ -42,6 +42,10 @@ struct GemmArgs {
     int stages;
     int stage_bytes;
     int m_tiles, n_tiles;   // grid extent in tiles; the 1-D block index is rasterised in groups of GEMM_RASTER_N n-tiles
+    int k_splits;           // > 1: the K range is cut into k_splits chunks of k_chunk rows (small grids); chunk `z` writes
+    int k_chunk;            //      its partial tile to partial + z * partial_stride (packed, ld = m_count), summed afterwards
+    double* partial;
+    long long partial_stride;
 };
 constexpr int GEMM_RASTER_N = 8;
 
@@ -55,7 +59,10 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int stages = args.stages;
-    const int numK = (args.K + GEMM_BK - 1) / GEMM_BK;
+    const int split = blockIdx.y;
+    const int k_begin = split * args.k_chunk;
+    const int k_len = min(args.k_chunk, args.K - k_begin);
+    const int numK = (k_len + GEMM_BK - 1) / GEMM_BK;
     // TMA needs the innermost box coordinate on a 16-byte boundary: tile origins sit on even columns, the odd
     // leading column of a range (if any) is computed and discarded.
     // Rasterisation: consecutive block indices walk GEMM_RASTER_N n-tiles for one m-tile, then the next m-tile, so the
@@ -100,10 +107,10 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait_backoff(&empty[stage], phase ^ 1);
                 unsigned char* base = smem + (size_t)stage * args.stage_bytes;
                 mbar_expect_tx(&full[stage], (uint32_t)(A_BYTES + b_bytes + b2_bytes));
-                tma_load_2d(base, &tmA, &full[stage], m_tile0, kt * GEMM_BK);
-                tma_load_2d(base + A_BYTES, &tmB, &full[stage], s_first, kt * GEMM_BK);
-                if (MODE == GEMM_PRODUCT) tma_load_2d(base + A_BYTES + b_bytes, &tmB2, &full[stage], s_first, kt * GEMM_BK);
-                if (MODE == GEMM_EXPAND) tma_load_2d(base + A_BYTES + b_bytes, &tmB2, &full[stage], 0, kt * GEMM_BK);
+                tma_load_2d(base, &tmA, &full[stage], m_tile0, k_begin + kt * GEMM_BK);
+                tma_load_2d(base + A_BYTES, &tmB, &full[stage], s_first, k_begin + kt * GEMM_BK);
+                if (MODE == GEMM_PRODUCT) tma_load_2d(base + A_BYTES + b_bytes, &tmB2, &full[stage], s_first, k_begin + kt * GEMM_BK);
+                if (MODE == GEMM_EXPAND) tma_load_2d(base + A_BYTES + b_bytes, &tmB2, &full[stage], 0, k_begin + kt * GEMM_BK);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -175,7 +182,8 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int h = 0; h < 2; h++) {
             const int n = n_tile0 + wn * 32 + 8 * j + 2 * t + h;
             if (n >= n_end || n < args.n_begin) continue;
-            double* row = args.out + (long long)(n - args.n_begin) * args.ldc - args.m_begin;
+            double* row = (args.k_splits > 1 ? args.partial + (long long)split * args.partial_stride + (long long)(n - args.n_begin) * args.m_count
+                                             : args.out + (long long)(n - args.n_begin) * args.ldc) - args.m_begin;
 #pragma unroll
             for (int i = 0; i < MT; i++) {
                 const int m = m_tile0 + wm * (8 * MT) + 8 * i + g;
@@ -183,6 +191,16 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     }
+}
+
+// out[n][m] = sum over the K chunks of partial[z][n][m], in chunk order (deterministic)
+__global__ void crm_gemm_reduce_kernel(const double* partial, long long stride, int splits, int n_count, int m_count, double* out, long long ldc) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_count * m_count) return;
+    const long long n = idx / m_count; const int m = (int)(idx - n * m_count);
+    double s = 0.0;
+    for (int z = 0; z < splits; z++) s += partial[(long long)z * stride + idx];
+    out[n * ldc + m] = s;
 }
 
 }  // namespace crm

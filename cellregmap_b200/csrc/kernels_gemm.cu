@@ -1,5 +1,6 @@
 // Host-side launcher of K1 (tensor-map construction + launch).
 #include <stdlib.h>
+#include <algorithm>
 #include "gemm.cuh"
 #include "launch.cuh"
 
@@ -102,9 +103,34 @@ int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream)
     if (args.m_tiles == 0 || args.n_tiles == 0) return CRM_OK;
     const long long ctas = (long long)args.m_tiles * args.n_tiles;
     if (ctas > 2000000000LL) { set_error("GEMM of %d x %d tiles is too large for one launch", args.m_tiles, args.n_tiles); return CRM_ERR_UNSUPPORTED; }
-    dim3 grid((unsigned)ctas, 1, 1);
+    // small grids over a long contraction: cut K so that the launch fills the 148 SMs for a whole number of waves
+    args.k_splits = 1; args.k_chunk = args.K; args.partial = nullptr; args.partial_stride = 0;
+    if (ctas < 2 * 148 && args.K >= 64 * GEMM_BK) {
+        const int max_splits = std::min(16, std::max(1, args.K / (16 * GEMM_BK)));
+        int splits = 1; double best = 0.0;
+        for (int z = 1; z <= max_splits; z++) {     // wave efficiency of ctas * z blocks on 148 SMs
+            const long long blocks = ctas * z, waves = (blocks + 147) / 148;
+            const double eff = (double)blocks / (double)(waves * 148);
+            if (eff > best + 1e-9) { best = eff; splits = z; }
+        }
+        if (splits > 1) {
+            const int chunk = (((args.K + splits - 1) / splits) + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+            splits = (args.K + chunk - 1) / chunk;
+            args.k_splits = splits; args.k_chunk = chunk;
+            args.partial_stride = (long long)args.n_count * args.m_count;
+            CRM_CUDA(cudaMallocAsync((void**)&args.partial, (size_t)splits * args.partial_stride * sizeof(double), stream));
+        }
+    }
+    dim3 grid((unsigned)ctas, (unsigned)args.k_splits, 1);
     crm_gemm_kernel<MODE, MT><<<grid, gemm_threads(MT), smem, stream>>>(tmA, tmB, tmB2, args);
     CRM_CUDA(cudaGetLastError()); count_launch();
+    if (args.k_splits > 1) {
+        const long long total = (long long)args.n_count * args.m_count;
+        crm_gemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(args.partial, args.partial_stride, args.k_splits, args.n_count, args.m_count,
+                                                                                 args.out, args.ldc);
+        CRM_CUDA(cudaGetLastError()); count_launch();
+        CRM_CUDA(cudaFreeAsync(args.partial, stream));
+    }
     return CRM_OK;
 }
 

@@ -86,15 +86,14 @@ constexpr int SCORE_CHUNK = 32;
 constexpr int SCORE_MAXE = 8;
 
 
-template <int P>
 __global__ void __launch_bounds__(SCORE_THREADS) crm_score_kernel(const ScoreArgs a) {
     extern __shared__ __align__(16) double ssm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pos = blockIdx.x;
     const int s = a.perm[pos];
     const int rho = a.rho_idx[s];
+    const int P = a.c + 1, C = a.c;
     const int k = a.k, NZ = 1 + P + k, mp = a.mp, m = a.m;
-    constexpr int C = P - 1;
     const double v0 = a.v0[s], v1 = a.v1[s];
     // shared layout
     double* G = ssm;                       // NZ x NZ Gram (first rotated-weighted, then K0^-1 Gram)
@@ -102,7 +101,10 @@ __global__ void __launch_bounds__(SCORE_THREADS) crm_score_kernel(const ScoreArg
     double* wv = Zt + NZ * (SCORE_CHUNK + 1);   // CHUNK weights
     double* Mm = wv + SCORE_CHUNK;         // k x k
     double* sol = Mm + k * k;              // P x (1 + k): A^+ [X'Ky | X'K GE]
-    double* tv = sol + P * (1 + k);        // k
+    double* tv = sol + P * (1 + k);        // 2 k
+    double* Aw = tv + 2 * k;               // P x P
+    double* Vw = Aw + P * P;               // P x P
+    double* yw = Vw + P * P;               // P x (1 + k)
     const double* S = a.S + (long long)rho * mp;
     const double* yr = a.yr + (long long)rho * mp;
     const double* Wr = a.Wr + (long long)rho * C * mp;
@@ -168,32 +170,47 @@ __global__ void __launch_bounds__(SCORE_THREADS) crm_score_kernel(const ScoreArg
         G[ia * NZ + ib] = v; G[ib * NZ + ia] = v;
     }
     __syncthreads();
-    // ---- 3. A^+ [X'Ky | X'K GE] by thread-per-column (P x P pseudo-inverse, lstsq(rcond=None) semantics) ----
-    if (tid < 1 + k) {
-        double A[P][P], b[P], x[P], ld; bool pd;
-#pragma unroll
-        for (int i = 0; i < P; i++) {
-#pragma unroll
-            for (int j = 0; j < P; j++) A[i][j] = G[(1 + i) * NZ + (1 + j)];
-            const int col = (tid == 0) ? 0 : P + tid;
-            b[i] = G[(1 + i) * NZ + col];
+    // ---- 3. A^+ [X'Ky | X'K GE]: pseudo-inverse of the P x P block through its eigendecomposition (warp 0, Jacobi in
+    //         shared memory) with the relative cut-off eps * P of numpy's lstsq(rcond=None), reference _math.py:33-37 ----
+    if (warp == 0) {
+        for (int e = lane; e < P * P; e += 32) { const int i = e / P, j = e - i * P; Aw[e] = G[(1 + i) * NZ + (1 + j)]; }
+        __syncwarp();
+        warp_jacobi_vec(Aw, Vw, P, lane);
+    }
+    __syncthreads();
+    {
+        double lmax = 0.0;
+        for (int r = 0; r < P; r++) lmax = fmax(lmax, fabs(Aw[r * P + r]));
+        const double cut = CRM_EPS_TINY * P * lmax;
+        for (int e = tid; e < P * (1 + k); e += SCORE_THREADS) {      // yw[r][j] = (V' b_j)_r / lambda_r
+            const int r = e / (1 + k), j = e - r * (1 + k);
+            const int col = (j == 0) ? 0 : P + j;
+            const double l = Aw[r * P + r];
+            double v = 0.0;
+            if (fabs(l) > cut && fabs(l) > 0.0) {
+                for (int t = 0; t < P; t++) v += Vw[t * P + r] * G[(1 + t) * NZ + col];
+                v /= l;
+            }
+            yw[e] = v;
         }
-        sym_pinv_solve<P>(A, b, 0u, CRM_EPS_TINY * P, x, &ld, &pd);
-#pragma unroll
-        for (int i = 0; i < P; i++) sol[i * (1 + k) + tid] = x[i];
+        __syncthreads();
+        for (int e = tid; e < P * (1 + k); e += SCORE_THREADS) {      // sol[i][j] = sum_r V[i][r] yw[r][j]
+            const int i = e / (1 + k), j = e - i * (1 + k);
+            double v = 0.0;
+            for (int r = 0; r < P; r++) v += Vw[i * P + r] * yw[r * (1 + k) + j];
+            sol[e] = v;
+        }
     }
     __syncthreads();
     // t_j and M
     for (int j = tid; j < k; j += SCORE_THREADS) {
         double t = G[(P + 1 + j) * NZ + 0];
-#pragma unroll
         for (int i = 0; i < P; i++) t -= G[(P + 1 + j) * NZ + (1 + i)] * sol[i * (1 + k) + 0];
         tv[j] = t;
     }
     for (int e = tid; e < k * k; e += SCORE_THREADS) {
         const int j = e / k, l = e - j * k;
         double v = G[(P + 1 + j) * NZ + (P + 1 + l)];
-#pragma unroll
         for (int i = 0; i < P; i++) v -= G[(P + 1 + j) * NZ + (1 + i)] * sol[i * (1 + k) + 1 + l];
         Mm[e] = 0.5 * v;
     }

@@ -72,6 +72,17 @@ def test_run_interaction_tall_lowrank(cuda_device):
     _check_interaction(d, ref, stages, model, d.G)
 
 
+def test_run_interaction_many_covariates(cuda_device):
+    """Nine covariate columns: the design [W g] has 10 columns and takes the shared-memory fit kernel."""
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    from oracle import crm_port
+    d = make_data(n=700, donors=50, k=5, p=24, q=4, seed=4, n_covariates=9)
+    stages = {}
+    ref = crm_port.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK, stages=stages)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    _check_interaction(d, ref, stages, model, d.G)
+
+
 def test_interaction_without_background_and_default_W(cuda_device):
     """No hK / Ls: rho1 = [1.0] (reference :103-106); W defaults to an intercept (:70-71)."""
     from cellregmap_b200 import CellRegMap
