@@ -175,6 +175,19 @@ class CellRegMap:
     def n_samples(self):
         return int(self._y.shape[0])
 
+    def set_phenotype(self, y):
+        """Extension (not in the reference API): replace the phenotype of this model, keeping cells, contexts, covariates
+        and background.  Same results as constructing a new model with the new `y`, without redoing the decompositions
+        -- for scans of many genes over one data set."""
+        ynew = _to_dev(y, self._device).flatten()
+        assert ynew.shape[0] == self.n_samples
+        if not bool(torch.isfinite(ynew).all()):
+            raise ValueError("There are non-finite values in the outcome.")
+        torch.cuda.set_device(self._device)
+        _lib.call("crm_update_phenotype", self._handle, _ptr(ynew), _stream())
+        self._y = ynew
+        return self
+
     # ------------------------------------------------------------------------------------------
     def _genotypes(self, G, donor_index):
         """(genotype descriptor, flag bits for the C ABI).  With `donor_index` (n,) G is the d x p donor-level matrix

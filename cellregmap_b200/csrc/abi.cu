@@ -212,6 +212,26 @@ __global__ void rotate_null_kernel(const double* Tt, long long ldt, const double
         if (col == 0) yr[idx] = s; else Wr[((long long)rho * c + (col - 1)) * mp + i] = s;
     }
 }
+// refresh the phenotype-dependent column a = m of the (pre-expanded) bases after Hx[:, m] changed
+__global__ void refresh_y_hxe_kernel(const double* Hx, int ldH, int m, const double* Eext, int epitch, int kexp, long long n, double* HxE) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * kexp) return;
+    const long long i = idx / kexp; const int j = (int)(idx - i * kexp);
+    HxE[i * (long long)kexp * ldH + (long long)j * ldH + m] = Eext[i * epitch + j] * Hx[i * ldH + m];
+}
+__global__ void refresh_y_donor_kernel(const double* Hx, int ldH, int m, const double* Eext, int epitch, int kexp, const int* perm, const int* off, long long d,
+                                       double* HxE_D) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d * kexp) return;
+    const long long dn = idx / kexp; const int j = (int)(idx - dn * kexp);
+    double s = 0.0;
+    for (int t = off[dn]; t < off[dn + 1]; t++) { const long long i = perm[t]; s += Eext[i * epitch + j] * Hx[i * ldH + m]; }
+    HxE_D[dn * (long long)kexp * ldH + (long long)j * ldH + m] = s;
+}
+__global__ void symmetrise_row_kernel(double* gram, int ldg, int row, int count) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < count) gram[(long long)a * ldg + row] = gram[(long long)row * ldg + a];
+}
 // YW[rho][0][i] = yr[rho][i], YW[rho][1 + a][i] = Wr[rho][a][i];  ywgram = plain Gram of [y | W] from stats
 __global__ void build_yw_kernel(const double* yr, const double* Wr, const double* stats, int R, int c, int mp, double* YW, double* ywgram) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -417,7 +437,10 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     op.A = Hx; op.lda = ldH; op.a_cols = Mx;
     op.B = Hx; op.ldb = ldH; op.b_cols = Mx;
     op.B2 = Hx; op.ldb2 = ldH; op.b2_cols = Mx;
-    CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)n, 0, Mx, 0, Mx, h->gram.as<double>(), ldH, 1, st));
+    gemm_set_free_split(true);
+    const int gram_status = launch_gemm(GEMM_PLAIN, op, (int)n, 0, Mx, 0, Mx, h->gram.as<double>(), ldH, 1, st);
+    gemm_set_free_split(false);
+    CRM_CHECK(gram_status);
     extract_stats_kernel<<<1, 1024, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
 
@@ -492,6 +515,43 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         h->max_rank = std::max(h->max_rank, info[R + r]);
     }
     h->ready = true;
+    return CRM_OK;
+}
+
+// New phenotype for the same cells, contexts, covariates and background (scans of many genes over one data set): only the
+// y-dependent quantities are refreshed -- H'y, y'y, W'y, the rotated phenotype per rho, the y column of the expanded bases --
+// the Gram of H and the R eigendecompositions are kept.
+static int do_update_phenotype(Handle* h, const double* y, cudaStream_t st) {
+    if (!h->ready) { set_error("crm_update_phenotype: handle is not set up"); return CRM_ERR_STATE; }
+    if (!y) { set_error("crm_update_phenotype: null phenotype"); return CRM_ERR_INVALID; }
+    const int m = h->m, mp = h->mp, c = h->c, R = h->R, ldH = h->ldH, Mx = h->Mx;
+    double* Hx = h->Hx.as<double>();
+    CRM_CUDA(cudaMemcpy2DAsync(Hx + m, (size_t)ldH * 8, y, 8, 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+    GemmOperands op{};
+    op.A = Hx; op.lda = ldH; op.a_cols = Mx; op.B = Hx; op.ldb = ldH; op.b_cols = Mx; op.B2 = Hx; op.ldb2 = ldH; op.b2_cols = Mx;
+    gemm_set_free_split(true);
+    const int status = launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, Mx, m, 1, h->gram.as<double>() + (long long)m * ldH, ldH, 1, st);
+    gemm_set_free_split(false);
+    CRM_CHECK(status);
+    symmetrise_row_kernel<<<blocks_for(Mx, 128), 128, 0, st>>>(h->gram.as<double>(), ldH, m, Mx);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    extract_stats_kernel<<<1, 1024, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    rotate_null_kernel<<<blocks_for((long long)R * mp, 128), 128, 0, st>>>(h->Tt.as<double>(), (long long)R * mp, h->gram.as<double>(), ldH, m, mp, R, c,
+                                                                         h->yr.as<double>(), h->Wr.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    build_yw_kernel<<<blocks_for(std::max<long long>((long long)R * (1 + c) * mp, (long long)(1 + c) * (1 + c)), 256), 256, 0, st>>>(
+        h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    if (h->use_hxe && h->hxe_built) {
+        refresh_y_hxe_kernel<<<blocks_for(h->n * h->kexp, 256), 256, 0, st>>>(Hx, ldH, m, h->Eext.as<double>(), h->epitch, h->kexp, h->n, h->HxE.as<double>());
+        CRM_CUDA(cudaGetLastError()); count_launch();
+    }
+    if (h->donors_set) {
+        refresh_y_donor_kernel<<<blocks_for(h->donors.K * h->kexp, 128), 128, 0, st>>>(Hx, ldH, m, h->Eext.as<double>(), h->epitch, h->kexp, h->dperm.as<int>(),
+                                                                                   h->doff.as<int>(), h->donors.K, h->HxE_D.as<double>());
+        CRM_CUDA(cudaGetLastError()); count_launch();
+    }
     return CRM_OK;
 }
 
@@ -1022,6 +1082,12 @@ int crm_profile(crm_handle_t h, int enable, double* rot_ms, double* rot_flops, i
     H.prof_flops = 0.0;
     H.prof_on = enable != 0;
     return CRM_OK;
+}
+
+int crm_update_phenotype(crm_handle_t h, const double* y, void* stream) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    return do_update_phenotype(&h->impl, y, (cudaStream_t)stream);
 }
 
 int crm_set_donors(crm_handle_t h, const int32_t* perm, const int32_t* offsets, int64_t d, void* stream) {

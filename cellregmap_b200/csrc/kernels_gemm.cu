@@ -66,6 +66,9 @@ static int gemm_mt_choice() {
     return mt;
 }
 
+static thread_local bool g_free_split = false;
+void gemm_set_free_split(bool on) { g_free_split = on; }
+
 template <int MODE, int MT>
 int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream) {
     CUtensorMap tmA, tmB, tmB2;
@@ -103,22 +106,30 @@ int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream)
     if (args.m_tiles == 0 || args.n_tiles == 0) return CRM_OK;
     const long long ctas = (long long)args.m_tiles * args.n_tiles;
     if (ctas > 2000000000LL) { set_error("GEMM of %d x %d tiles is too large for one launch", args.m_tiles, args.n_tiles); return CRM_ERR_UNSUPPORTED; }
-    // small grids over a long contraction: cut K so that the launch fills the 148 SMs for a whole number of waves
+    // Narrow outputs over a long contraction leave most SMs idle: cut K into chunks (partials summed in chunk order).
+    // The chunking depends only on (m_tiles, K) -- never on the number of SNP columns -- so that a SNP's arithmetic is the
+    // same whatever shard it is scanned in (multi-GPU results stay bit-identical to 1-GPU results); the set-up Gram
+    // (free_split) has no SNP dimension and picks the split count by wave efficiency.
     args.k_splits = 1; args.k_chunk = args.K; args.partial = nullptr; args.partial_stride = 0;
-    if (ctas < 2 * 148 && args.K >= 64 * GEMM_BK) {
+    {
         const int max_splits = std::min(16, std::max(1, args.K / (16 * GEMM_BK)));
-        int splits = 1; double best = 0.0;
-        for (int z = 1; z <= max_splits; z++) {     // wave efficiency of ctas * z blocks on 148 SMs
-            const long long blocks = ctas * z, waves = (blocks + 147) / 148;
-            const double eff = (double)blocks / (double)(waves * 148);
-            if (eff > best + 1e-9) { best = eff; splits = z; }
+        int splits = 1;
+        if (g_free_split && ctas < 2 * 148) {
+            double best = 0.0;
+            for (int z = 1; z <= max_splits; z++) {     // wave efficiency of ctas * z blocks on 148 SMs
+                const long long blocks = ctas * z, waves = (blocks + 147) / 148;
+                const double eff = (double)blocks / (double)(waves * 148);
+                if (eff > best + 1e-9) { best = eff; splits = z; }
+            }
+        } else if (args.m_tiles <= 2 && MODE != GEMM_EXPAND) {
+            splits = max_splits;
         }
         if (splits > 1) {
             const int chunk = (((args.K + splits - 1) / splits) + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
             splits = (args.K + chunk - 1) / chunk;
             args.k_splits = splits; args.k_chunk = chunk;
             args.partial_stride = (long long)args.n_count * args.m_count;
-            CRM_CUDA(cudaMallocAsync((void**)&args.partial, (size_t)splits * args.partial_stride * sizeof(double), stream));
+            if (splits > 1) CRM_CUDA(cudaMallocAsync((void**)&args.partial, (size_t)splits * args.partial_stride * sizeof(double), stream));
         }
     }
     dim3 grid((unsigned)ctas, (unsigned)args.k_splits, 1);

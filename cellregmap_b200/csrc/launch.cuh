@@ -20,6 +20,9 @@ constexpr int GEMM_TILE_N = 128;
 int launch_gemm(int mode, const GemmOperands& op, int K, int m_begin, int m_count, int n_begin, int n_count,
                 double* out, long long ldc, int kexp, cudaStream_t stream);
 
+// next launch_gemm calls on this thread may choose the K split by grid size (operands without a SNP dimension)
+void gemm_set_free_split(bool on);
+
 int launch_fit_with_g(const FitArgs& fa, cudaStream_t st);   // design [W g], P = c + 1 in 1..8
 int launch_fit_null(const FitArgs& fa, cudaStream_t st);     // design W,     P = c     in 1..7
 inline int launch_fit(const FitArgs& fa, bool has_g, cudaStream_t st) { return has_g ? launch_fit_with_g(fa, st) : launch_fit_null(fa, st); }

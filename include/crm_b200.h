@@ -51,6 +51,13 @@ CRM_API int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t 
 CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream);
 
 /*
+ * New phenotype y (n doubles, device) for the same cells, contexts, covariates and background (extension): refreshes only
+ * the y-dependent state of the model; the Gram of the half-basis and the per-rho eigendecompositions are kept.  Equivalent
+ * to crm_setup with the new y.  Typical use: one model per data set, one crm_update_phenotype + scan per gene.
+ */
+CRM_API int crm_update_phenotype(crm_handle_t h, const double* y, void* stream);
+
+/*
  * Donor-level genotype ingress (extension).  The reference always receives genotypes expanded from donors to
  * cells, G_cells = G_donors[donor_of_cell].  After crm_set_donors the scan entry points also accept the d x p donor-level
  * matrix (flag bit 1 of `g_on_host`, see below): every contraction over cells is then done once per gene on the basis side

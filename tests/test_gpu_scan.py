@@ -294,3 +294,32 @@ def test_edge_cases(cuda_device):
     ybad = d2.y.copy(); ybad[0] = np.nan
     with pytest.raises(ValueError):
         CellRegMap(ybad, d2.E)
+
+
+def test_set_phenotype_equals_new_model(cuda_device):
+    """Extension: swapping the phenotype of a model gives the results of a freshly constructed model (all scans, both
+    genotype ingress forms)."""
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    d = make_data(n=500, donors=25, k=5, p=40, q=4, seed=41)
+    y2 = make_data(n=500, donors=25, k=5, p=40, q=4, seed=42).y
+    Gd = np.zeros((25, 40)); Gd[d.donor] = d.G
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    model.scan_interaction(d.G)                        # builds the expanded basis, so that its refresh is exercised
+    model.scan_interaction(Gd, donor_index=d.donor)    # and the donor-level operands
+    model.set_phenotype(y2)
+    fresh = _make_interaction_model(y2, d.E, d.W, None, None, d.hK)
+    for kw in ({}, {"donor_index": d.donor}):
+        G = Gd if kw else d.G
+        pv_a, info_a = model.scan_interaction(G, **kw)
+        pv_b, info_b = fresh.scan_interaction(G, **kw)
+        np.testing.assert_array_equal(info_a["rho1"], info_b["rho1"])
+        assert np.max(np.abs(np.log10(pv_a) - np.log10(pv_b))) <= 1e-7
+        for key in ("e2", "g2", "eps2"):
+            np.testing.assert_allclose(info_a[key], info_b[key], rtol=1e-7)
+    pa, _ = model.scan_association(d.G)
+    pb, _ = fresh.scan_association(d.G)
+    assert np.max(np.abs(np.log10(pa) - np.log10(pb))) <= 1e-7
+    ba, xa = model.predict_interaction(d.G[:, :5], np.full(5, 0.3))
+    bb, xb = fresh.predict_interaction(d.G[:, :5], np.full(5, 0.3))
+    np.testing.assert_allclose(ba, bb, rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(xa, xb, rtol=0, atol=1e-6 * np.abs(xb).max())
