@@ -2,6 +2,7 @@
 // Host orchestration only: set-up of the per-gene state, batching of SNPs, kernel launches.
 #include <cusolverDn.h>
 #include <stdarg.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -94,6 +95,7 @@ struct Handle {
     DevBuf HxE_D, A2_D, dperm, doff;
     DevBuf HxE;           // optional n x (kexp * ldH) pre-expanded basis [Hx | Hx.E0_1 | ... | Hx.E0_k] (see launch_rotation)
     bool use_hxe = false, hxe_built = false;
+    int hxe_blocks = 0;   // context blocks j held by HxE at a time: kexp = whole basis resident, fewer = streamed in groups
     DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
     // null-model state for the association scans
     // scan workspaces
@@ -125,14 +127,17 @@ __global__ void build_eext_kernel(const double* E0, long long lde0, long long n,
     const long long i = idx / epitch; const int j = (int)(idx - i * epitch);
     Eext[idx] = (j == 0) ? 1.0 : (j <= k0 ? E0[i * lde0 + (j - 1)] : 0.0);
 }
-// HxE[i][j * ldH + a] = Eext[i][j] * Hx[i][a]   (j = 0: Hx itself)
-__global__ void build_hxe_kernel(const double* Hx, int ldH, const double* Eext, int epitch, int kexp, long long n, double* out) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long ld = (long long)kexp * ldH;
-    if (idx >= n * ld) return;
-    const long long i = idx / ld; const long long r = idx - i * ld;
-    const int j = (int)(r / ldH), a = (int)(r - (long long)j * ldH);
-    out[idx] = Eext[i * epitch + j] * Hx[i * ldH + a];
+// out[i][(j - j0) * ldH + a] = Eext[i][j] * Hx[i][a]  for j in [j0, j0 + nj)   (j = 0: Hx itself)
+__global__ void build_hxe_kernel(const double* Hx, int ldH, const double* Eext, int epitch, int j0, int nj, long long n, double* out) {
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {          // one cell per block iteration, threads over basis columns
+        const double* hrow = Hx + i * ldH;
+        const double* erow = Eext + i * epitch + j0;
+        double* orow = out + i * (long long)nj * ldH;
+        for (int a = threadIdx.x; a < ldH; a += blockDim.x) {
+            const double hv = hrow[a];
+            for (int j = 0; j < nj; j++) orow[(long long)j * ldH + a] = erow[j] * hv;
+        }
+    }
 }
 // donor-level pre-expanded basis: out[dn][j * ldH + a] = sum over the cells t of donor dn of Eext[t][j] * Hx[t][a]
 __global__ void aggregate_hxe_kernel(const double* Hx, int ldH, const double* Eext, int epitch, int kexp, const int* perm, const int* off, double* out) {
@@ -169,33 +174,35 @@ __global__ void build_a2_kernel(const double* E0, long long lde0, long long n, i
     }
     A2[idx] = v;
 }
-// C_rho = D^(1/2) (H'H) D^(1/2), D = diag(rho I_k1, (1-rho) I)
-__global__ void scale_gram_kernel(const double* gram, int ldg, int m, int k1, double rho, double* out) {
+// C_rho = D^(1/2) (H'H) D^(1/2), D = diag(rho I_k1, (1-rho) I), restricted to the columns [a0, a0 + ms) that D keeps
+// (rho = 1 keeps only the E1 block, rho = 0 only the L block: the other block is exactly zero)
+__global__ void scale_gram_kernel(const double* gram, int ldg, int a0, int ms, int k1, double rho, double* out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= m * m) return;
-    const int a = idx / m, b = idx - a * m;
+    if (idx >= ms * ms) return;
+    const int a = a0 + idx / ms, b = a0 + idx % ms;
     const double da = a < k1 ? sqrt(rho) : sqrt(1.0 - rho), db = b < k1 ? sqrt(rho) : sqrt(1.0 - rho);
     out[idx] = da * db * gram[(long long)a * ldg + b];
 }
-// eigenpairs (ascending, eigenvector i in row i of V) -> S[i], Tt[a][rho*mp + i] = d_a V[i][a] / sqrt(S_i)
-__global__ void build_basis_kernel(const double* V, const double* ev, int m, int mp, int k1, double rho, int tall,
+// eigenpairs of the kept block [a0, a0 + ms) (ascending, eigenvector i in row i of V, length ms) ->
+// S[i], Tt[a][rho*mp + i] = d_a V[i][a - a0] / sqrt(S_i); entries i >= ms and rows outside the block are zero
+__global__ void build_basis_kernel(const double* V, const double* ev, int m, int mp, int a0, int ms, int k1, double rho, int tall,
                                    double* S, double* Tt, long long ldt, int rho_index, int* rank_out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const double evmax = ev[m - 1];
+    const double evmax = ev[ms - 1];
     const double thr_rel = 1e-12 * evmax;
     if (idx < mp) {
         double s = 0.0;
-        if (idx < m) { const double e = ev[idx]; const bool keep = (e > thr_rel) && (tall || e >= CRM_EPS_SMALL) && e > 0.0; s = keep ? e : 0.0; }
+        if (idx < ms) { const double e = ev[idx]; const bool keep = (e > thr_rel) && (tall || e >= CRM_EPS_SMALL) && e > 0.0; s = keep ? e : 0.0; }
         S[idx] = s;
     }
-    if (idx == 0) { int r = 0; for (int i = 0; i < m; i++) { const double e = ev[i]; if ((e > thr_rel) && (tall || e >= CRM_EPS_SMALL) && e > 0.0) r++; } rank_out[rho_index] = r; }
+    if (idx == 0) { int r = 0; for (int i = 0; i < ms; i++) { const double e = ev[i]; if ((e > thr_rel) && (tall || e >= CRM_EPS_SMALL) && e > 0.0) r++; } rank_out[rho_index] = r; }
     for (long long t = idx; t < (long long)m * mp; t += (long long)gridDim.x * blockDim.x) {
         const int a = (int)(t / mp), i = (int)(t - (long long)a * mp);
         double v = 0.0;
-        if (i < m) {
+        if (i < ms && a >= a0 && a < a0 + ms) {
             const double e = ev[i];
             const bool keep = (e > thr_rel) && (tall || e >= CRM_EPS_SMALL) && e > 0.0;
-            if (keep) { const double da = a < k1 ? sqrt(rho) : sqrt(1.0 - rho); v = da * V[(long long)i * m + a] / sqrt(e); }
+            if (keep) { const double da = a < k1 ? sqrt(rho) : sqrt(1.0 - rho); v = da * V[(long long)i * ms + (a - a0)] / sqrt(e); }
         }
         Tt[(long long)a * ldt + (long long)rho_index * mp + i] = v;
     }
@@ -340,31 +347,42 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
     build_a2_kernel<<<blocks_for(h->n * h->ld2, 256), 256, 0, st>>>(E0, lde0, h->n, h->k0, h->A2.as<double>(), h->ld2);
     CRM_CUDA(cudaGetLastError()); count_launch();
     h->hxe_built = false;    // the pre-expanded basis is (re)built by the first cell-level rotation that needs it
-    h->cells.K = h->n; h->cells.HxE = nullptr; h->cells.ldE = (long long)h->kexp * h->ldH;
+    h->cells.K = h->n; h->cells.HxE = nullptr; h->cells.ldE = (long long)h->kexp * h->ldH;   // cells.HxE unused: see launch_rotation
     h->cells.Hx = h->Hx.as<double>(); h->cells.ldHx = h->ldH; h->cells.A2 = h->A2.as<double>(); h->cells.ld2 = h->ld2;
     if (h->donors_set) CRM_CHECK(aggregate_donors(h, st));
     return CRM_OK;
 }
 
 // Rotation of [g, g.E0_1, ..., g.E0_k] onto [H | y | W] for B SNP columns: C[(s*kexp + j)][a].
-// Two equivalent routes through K1: with the pre-expanded basis HxE the Hadamard factor sits on the basis side and the
-// loop is a plain DMMA contraction (99% of the FP64 tensor peak, costs n*kexp*ldH*8 bytes of HBM once per gene); without
-// it the factor is applied to the genotype fragments on the fly (EXPAND mode, ~90% of peak, no extra memory).
+// Two equivalent routes through K1: with the pre-expanded basis HxE = [Hx | Hx.E0_1 | ...] the Hadamard factor sits on the
+// basis side and the loop is a plain DMMA contraction (98% of the FP64 tensor peak).  HxE stays resident when its
+// n*kexp*ldH*8 bytes fit comfortably; otherwise it is streamed through a smaller buffer in groups of context blocks, rebuilt
+// per rotation call (one elementwise pass per group, negligible against the contraction).  Without it (CRM_NO_HXE=1) the
+// factor is applied to the genotype fragments on the fly (EXPAND mode, ~90% of peak, no extra memory).
 static int launch_rotation(Handle* h, const double* G, long long ldg, long long gcols, long long B, double* C, cudaStream_t st) {
-    if (h->gs == &h->cells && h->use_hxe && !h->hxe_built) {
-        CRM_CHECK(h->HxE.reserve((size_t)h->n * h->kexp * h->ldH * 8));
-        build_hxe_kernel<<<blocks_for(h->n * h->kexp * h->ldH, 256), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, h->n,
-                                                                                   h->HxE.as<double>());
-        CRM_CUDA(cudaGetLastError()); count_launch();
-        h->cells.HxE = h->HxE.as<double>();
-        h->hxe_built = true;
-    }
     const Handle::GenoSpace& gs = *h->gs;
+    const long long ldE = (long long)h->kexp * h->ldH;
     GemmOperands op{};
-    op.B = G; op.ldb = ldg; op.b_cols = gcols;
-    if (gs.HxE) {
-        op.A = gs.HxE; op.lda = gs.ldE; op.a_cols = gs.ldE; op.B2 = G; op.ldb2 = ldg; op.b2_cols = gcols;
+    op.B = G; op.ldb = ldg; op.b_cols = gcols; op.B2 = G; op.ldb2 = ldg; op.b2_cols = gcols;
+    if (h->gs == &h->donors) {                       // donor-level operands are always fully expanded (d rows only)
+        op.A = gs.HxE; op.lda = gs.ldE; op.a_cols = gs.ldE;
         return launch_gemm(GEMM_PLAIN, op, (int)gs.K, 0, (int)gs.ldE, 0, (int)B, C, gs.ldE, 1, st);
+    }
+    if (h->use_hxe) {
+        const int nb = h->hxe_blocks;
+        CRM_CHECK(h->HxE.reserve((size_t)h->n * nb * h->ldH * 8));
+        for (int j0 = 0; j0 < h->kexp; j0 += nb) {
+            const int nj = std::min(nb, h->kexp - j0);
+            if (!(nb == h->kexp && h->hxe_built)) {
+                build_hxe_kernel<<<(unsigned)std::min<long long>(h->n, 148 * 16), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, j0, nj, h->n,
+                                                                                          h->HxE.as<double>());
+                CRM_CUDA(cudaGetLastError()); count_launch();
+            }
+            op.A = h->HxE.as<double>(); op.lda = (long long)nj * h->ldH; op.a_cols = op.lda;
+            CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, (int)op.lda, 0, (int)B, C + (long long)j0 * h->ldH, ldE, 1, st));
+        }
+        h->hxe_built = (nb == h->kexp);
+        return CRM_OK;
     }
     op.A = h->Hx.as<double>(); op.lda = h->ldH; op.a_cols = h->Mx;
     op.B2 = h->Eext.as<double>(); op.ldb2 = h->epitch; op.b2_cols = h->epitch;
@@ -427,7 +445,14 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
                 free_b += (size_t)(reserved - used);
         }
         const char* env = getenv("CRM_NO_HXE");
-        h->use_hxe = !(env && atoi(env) != 0) && (h->HxE.cap >= bytes || bytes < (size_t)(0.45 * (double)(free_b + h->HxE.cap))) && (long long)h->kexp * ldH < 2000000000LL;
+        const char* envb = getenv("CRM_HXE_BLOCKS");       // tests: force streaming in groups of this many context blocks
+        const double budget = 0.45 * (double)(free_b + h->HxE.cap);
+        const double block_bytes = (double)n * ldH * 8.0;
+        int blocks = (int)std::min<double>(h->kexp, std::floor(budget / block_bytes));
+        if (envb && atoi(envb) > 0) blocks = std::min(blocks, atoi(envb));
+        h->use_hxe = !(env && atoi(env) != 0) && blocks >= 1 && (double)blocks * ldH < 2.0e9;
+        h->hxe_blocks = h->use_hxe ? blocks : 0;
+        (void)bytes;
         if (!h->use_hxe) h->HxE.release();
     }
     CRM_CHECK(build_test_contexts(h, E0, lde0, st));
@@ -470,7 +495,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         CRM_CHECK(e.val.reserve((size_t)R * m * 8));
         if (!e.params) CRM_SOLVER(cusolverDnCreateParams(&e.params));
         for (int r = 0; r < R; r++) {
-            scale_gram_kernel<<<blocks_for((long long)m * m, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, m, k1, h->rho[r], e.mat.as<double>() + (size_t)r * m * m);
+            scale_gram_kernel<<<blocks_for((long long)m * m, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, 0, m, k1, h->rho[r], e.mat.as<double>() + (size_t)r * m * m);
             CRM_CUDA(cudaGetLastError()); count_launch();
         }
         size_t ws_dev = 0, ws_host = 0;
@@ -482,18 +507,25 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
                                           CUDA_R_64F, e.work.ptr, ws_dev, e.host_work.data(), ws_host, info_dev, R));
         for (int r = 0; r < R; r++) {
             build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
-                e.mat.as<double>() + (size_t)r * m * m, e.val.as<double>() + (size_t)r * m, m, mp, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
+                e.mat.as<double>() + (size_t)r * m * m, e.val.as<double>() + (size_t)r * m, m, mp, 0, m, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
                 h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
             CRM_CUDA(cudaGetLastError()); count_launch();
         }
     } else {
         for (int r = 0; r < R; r++) {
-            scale_gram_kernel<<<blocks_for((long long)m * m, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, m, k1, h->rho[r], e.mat.as<double>());
+            // rho = 1 / rho = 0 zero one diagonal block of D: only the surviving block is decomposed
+            int a0 = 0, ms = m;
+            if (mL > 0 && h->rho[r] == 1.0) { a0 = 0; ms = k1; }
+            else if (mL > 0 && h->rho[r] == 0.0) { a0 = k1; ms = (int)mL; }
+            scale_gram_kernel<<<blocks_for((long long)ms * ms, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, a0, ms, k1, h->rho[r], e.mat.as<double>());
             CRM_CUDA(cudaGetLastError()); count_launch();
-            CRM_SOLVER(cusolverDnDsyevd(e.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, e.mat.as<double>(), m, e.val.as<double>(),
+            int lw = 0;
+            CRM_SOLVER(cusolverDnDsyevd_bufferSize(e.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ms, e.mat.as<double>(), ms, e.val.as<double>(), &lw));
+            if (lw > lwork) { set_error("cuSOLVER workspace for the %d x %d block exceeds the one of the full problem", ms, ms); return CRM_ERR_SOLVER; }
+            CRM_SOLVER(cusolverDnDsyevd(e.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ms, e.mat.as<double>(), ms, e.val.as<double>(),
                                         e.work.as<double>(), lwork, info_dev + r));
             build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
-                e.mat.as<double>(), e.val.as<double>(), m, mp, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
+                e.mat.as<double>(), e.val.as<double>(), m, mp, a0, ms, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
                 h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
             CRM_CUDA(cudaGetLastError()); count_launch();
         }
@@ -543,7 +575,7 @@ static int do_update_phenotype(Handle* h, const double* y, cudaStream_t st) {
     build_yw_kernel<<<blocks_for(std::max<long long>((long long)R * (1 + c) * mp, (long long)(1 + c) * (1 + c)), 256), 256, 0, st>>>(
         h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
-    if (h->use_hxe && h->hxe_built) {
+    if (h->use_hxe && h->hxe_built && h->hxe_blocks == h->kexp) {
         refresh_y_hxe_kernel<<<blocks_for(h->n * h->kexp, 256), 256, 0, st>>>(Hx, ldH, m, h->Eext.as<double>(), h->epitch, h->kexp, h->n, h->HxE.as<double>());
         CRM_CUDA(cudaGetLastError()); count_launch();
     }

@@ -227,6 +227,14 @@ def test_rotation_routes_agree(cuda_device, monkeypatch):
     assert np.max(np.abs(np.log10(pv_a) - np.log10(pv_b))) <= 1e-8
     for key in ("e2", "g2", "eps2"):
         np.testing.assert_allclose(info_a[key], info_b[key], rtol=1e-9)
+    # streamed pre-expanded basis (groups of 3 context blocks) is bit-identical to the resident one
+    monkeypatch.delenv("CRM_NO_HXE")
+    monkeypatch.setenv("CRM_HXE_BLOCKS", "3")
+    model_c = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    pv_c, info_c = model_c.scan_interaction(d.G)
+    np.testing.assert_array_equal(pv_c, pv_a)
+    for key in ("rho1", "e2", "g2", "eps2"):
+        np.testing.assert_array_equal(info_c[key], info_a[key])
 
 
 def test_donor_level_genotypes_match_expanded(cuda_device):
