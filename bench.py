@@ -31,6 +31,11 @@ METRIC = "SNP-gene GxC tests/sec (run_interaction, n=100k cells, k=20)"
 UNIT = "tests/s"
 # measured on this pool's B200 (profiles/r01_dmma_probe.txt): DMMA.8x8x4 issue-rate peak; cuBLAS DGEMM reaches 35.4
 FP64_TENSOR_PEAK_TFLOPS = 37.1
+# dram__bytes_read.sum + dram__bytes_write.sum of the rotation launch at the default workload, from one ncu capture
+# (profiles/r01_ncu_rotation_traffic_benchsize.csv): 465.7 GB read + 1.8 GB written per 10k-SNP launch, against 27 GB of
+# algorithmic bytes (G 8 GB + pre-expanded basis 17.2 GB + output 1.7 GB) -- operand panels are re-read through L2 by the
+# 13 272 CTAs; 395 GB/s = 6 % of the HBM peak, the kernel is bound by the FP64 tensor pipe (99 % active).
+ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD = 465728855296 + 1766195200
 
 
 def parse_args():
@@ -376,7 +381,10 @@ def run_b200_arm(a):
                            "step": "constructor set-up + scan of the rank's SNP shard + all-gather of results"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                             "frac": (achieved / FP64_TENSOR_PEAK_TFLOPS) if achieved else None, "traffic": None,
+                             "frac": (achieved / FP64_TENSOR_PEAK_TFLOPS) if achieved else None,
+                             "traffic": (ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD if (a.cells, a.donors, a.contexts, a.hk_rank, a.snps) == (100000, 1000, 20, 50, 10000)
+                                         and api.PROFILE.get("pre_expanded_basis") else None),
+                             "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_rotation_traffic_benchsize.csv)",
                              "kernel": ("crm_gemm_kernel<PLAIN> on the pre-expanded basis [Hx|Hx.E_j] (rotation of [g, g.E] onto [H|y|W])"
                                         if api.PROFILE.get("pre_expanded_basis") else
                                         "crm_gemm_kernel<EXPAND> (rotation of [g, g.E] onto [H|y|W], Hadamard on the fly)"),

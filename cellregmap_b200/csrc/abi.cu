@@ -603,6 +603,16 @@ static long long pick_batch(const Handle* h, long long p, bool interaction) {
     return b;
 }
 
+// Column-block size for host-resident genotypes: two staging buffers of at most ~4 GB each, blocks of equal size (a
+// multiple of the 128-column GEMM tile) so that no launch ends in a nearly empty wave.
+static long long host_chunk(const Handle* h, long long B, long long p) {
+    const long long cap = std::max<long long>(128, (long long)(4.0e9 / (8.0 * (double)h->gs->K)) / 128 * 128);
+    B = std::min(B, cap);
+    if (p <= B) return B;
+    const long long nchunks = (p + B - 1) / B;
+    return std::min(B, round_up((p + nchunks - 1) / nchunks, 128));
+}
+
 static int reserve_scan(Handle* h, long long B, bool interaction) {
     const int R = h->R, mp = h->mp, m = h->m, k = h->k0;
     if (interaction) {
@@ -852,7 +862,7 @@ static int do_scan_interaction(Handle* h, int donor_level, const double* G, long
     if (p == 0) return CRM_OK;
     if (!G || p < 0 || ldg < p || !out_pv || !out_rho1 || !out_e2 || !out_g2 || !out_eps2) { set_error("crm_scan_interaction: bad arguments"); return CRM_ERR_INVALID; }
     long long B = pick_batch(h, p, true);
-    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->gs->K))));
+    if (g_on_host) B = host_chunk(h, B, p);
     CRM_CHECK(reserve_scan(h, B, true));
     return for_each_block(h, G, ldg, Gtest, ldgt, p, g_on_host, B, st, [&](const GBlock& k) -> int {
         return interaction_batch(h, k.G, k.ld, k.cols, k.G2, k.ld2, k.b, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, k.s0, st);
@@ -869,7 +879,7 @@ static int do_scan_association(Handle* h, int donor_level, const double* G, long
     if ((p > 0 && (!G || ldg < p || !out_pv)) || p < 0 || !info4) { set_error("crm_scan_association: bad arguments"); return CRM_ERR_INVALID; }
     const int R = h->R, mp = h->mp, m = h->m, c = h->c, ldH = h->ldH, Mx = h->Mx;
     long long B = pick_batch(h, std::max<long long>(p, 1), false);
-    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->gs->K))));
+    if (g_on_host) B = host_chunk(h, B, p);
     CRM_CHECK(reserve_scan(h, std::max<long long>(B, 1), false));
     // ---- null model: ML fit of y ~ W for every rho, best by strict '>' ----
     FitArgs fa{};
@@ -982,7 +992,7 @@ static int do_predict(Handle* h, int donor_level, const double* G, long long ldg
     const double per_snp = 8.0 * ((double)kexp * ldH + 2.0 * h->ld2 + 2.0 * (double)kexp * mp + (double)R * (P + k0 + 8));
     long long B = std::max<long long>(16, std::min<long long>(p, (long long)(4.0e9 / per_snp)));
     B = std::min<long long>(B, 65535LL * GEMM_TILE_N / kexp);
-    if (g_on_host) B = std::min<long long>(B, std::max<long long>(64, (long long)(1.5e9 / (8.0 * h->gs->K))));
+    if (g_on_host) B = host_chunk(h, B, p);
     CRM_CHECK(h->C.reserve((size_t)B * kexp * ldH * 8));
     CRM_CHECK(h->sq.reserve((size_t)B * h->ld2 * 8));
     CRM_CHECK(h->lin.reserve((size_t)B * h->ld2 * 8));
