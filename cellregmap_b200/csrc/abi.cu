@@ -282,12 +282,6 @@ __global__ void or_flags_kernel(const int* fit_flags, const int* rho_idx, const 
     const int f = fit_flags[s * R + rho_idx[s]];
     out[s] = (sflags[s] & 1) | ((f & 1) << 1) | ((f & 2) << 1);
 }
-__global__ void copy_strided_kernel(const double* src, long long src_ld, long long rows, int cols, double* dst, long long dst_ld) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * cols) return;
-    const long long r = idx / cols; const int cidx = (int)(idx - r * cols);
-    dst[r * dst_ld + cidx] = src[r * src_ld + cidx];
-}
 
 // Ys = [y | W | E0] (n x ld) from Hx (columns m.. ) and Eext (columns 1..k0)
 __global__ void build_ys_kernel(const double* Hx, int ldH, int m, int c, const double* Eext, int epitch, int k0, long long n, double* Ys, int ld) {
@@ -697,14 +691,23 @@ static int for_each_block(Handle* h, const double* G, long long ldg, const doubl
         return CRM_OK;
     }
     CRM_CHECK(ensure_streams(h));
-    const long long nb = (p + B - 1) / B, Bp = round_up(B, 2);
+    // block boundaries: a short first block (its copy is the only one that is not hidden behind compute), then blocks of B
+    const long long Bp = round_up(B, 2);
+    std::vector<long long> starts;
+    {
+        const long long first = (p > B) ? std::min<long long>(B, 512) : std::min(B, p);
+        starts.push_back(0);
+        for (long long s0 = first; s0 < p; s0 += B) starts.push_back(s0);
+        starts.push_back(p);
+    }
+    const long long nb = (long long)starts.size() - 1;
     CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
     CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
-    CRM_CHECK(stage_host_block(h, G, ldg, G2, ldg2, 0, std::min(B, p), Bp, 0));
+    CRM_CHECK(stage_host_block(h, G, ldg, G2, ldg2, starts[0], starts[1] - starts[0], Bp, 0));
     for (long long ib = 0; ib < nb; ib++) {
         const int slot = (int)(ib & 1);
-        const long long s0 = ib * B, b = std::min(B, p - s0);
-        if (ib + 1 < nb) CRM_CHECK(stage_host_block(h, G, ldg, G2, ldg2, s0 + B, std::min(B, p - s0 - B), Bp, slot ^ 1));
+        const long long s0 = starts[ib], b = starts[ib + 1] - s0;
+        if (ib + 1 < nb) CRM_CHECK(stage_host_block(h, G, ldg, G2, ldg2, starts[ib + 1], starts[ib + 2] - starts[ib + 1], Bp, slot ^ 1));
         CRM_CUDA(cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
         GBlock blk{h->gchunk[slot].as<double>(), Bp, b, G2 ? h->gtchunk[slot].as<double>() : nullptr, Bp, b, s0};
         CRM_CHECK(fn(blk));

@@ -106,3 +106,17 @@ def test_config4_association_sample(cuda_device):
     ref_pv, ref_info = crm_port.run_association(d.y, d.W, d.E, d.G[:, sample], hK=d.hK)
     np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
     assert np.max(np.abs(np.log10(pv[sample]) - np.log10(ref_pv))) <= DLOG10_P
+
+
+def test_wide_background_basis(cuda_device):
+    """m = k + k q = 2 404 columns in the half-covariance: the per-rho vectors no longer fit the fit kernel's shared memory
+    (global-memory path) and the spectrum is long; checked against the oracle on a few SNPs."""
+    from cellregmap_b200 import run_interaction
+    from oracle import crm_port
+    d = make_data(n=3000, donors=700, k=4, p=12, q=600, seed=15)
+    ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK, qs_method="gram")
+    pv, info = run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+    assert _dlog10(pv, ref_pv) <= DLOG10_P
+    for key in ("e2", "g2", "eps2"):
+        np.testing.assert_allclose(info[key], ref_info[key], rtol=1e-5, atol=1e-10)

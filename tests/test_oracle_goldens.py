@@ -1,11 +1,17 @@
-"""Oracle vs the reference's own known answers (cellregmap/test/test_math.py:17-91)."""
+"""Oracle vs the reference's own known answers (cellregmap/test/test_math.py:17-91), stored in
+tests/golden/reference_test_math.json."""
 import itertools
+import json
+import os
 
 import numpy as np
 from numpy.testing import assert_allclose
 
 from oracle import math_port as mp
 from oracle.sugar_port import economic_qs
+
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_test_math.json")))
 
 
 def _data():
@@ -38,20 +44,20 @@ def test_QSCov():
 
 def test_P_matrix():
     d = _data()
-    P = np.array([[0.50355613, -0.24203676, -0.34880245], [-0.24203676, 0.11633617, 0.16765363], [-0.34880245, 0.16765363, 0.24160792]])
+    P = np.array(GOLD["P_matrix"]["value"])
     assert_allclose(mp.P_matrix(d["W"], d["K"]), P, rtol=2e-7)
 
 
 def _golden_y(d):
     qs = [mp.score_statistic(y, d["W"], d["K"], d["dK"]) for y in d["ys"]]
-    best = int(np.argmin([abs(q - 0.49961017073389324) for q in qs]))
+    best = int(np.argmin([abs(q - GOLD["score_statistic"]["value"]) for q in qs]))
     return d["ys"][best], qs[best]
 
 
 def test_score_statistic():
     d = _data()
     _, q = _golden_y(d)
-    assert_allclose(q, 0.49961017073389324, rtol=1e-12)
+    assert_allclose(q, GOLD["score_statistic"]["value"], rtol=1e-12)
 
 
 def test_score_statistic_structured_matches_dense():
@@ -66,7 +72,7 @@ def test_score_statistic_structured_matches_dense():
 def test_score_statistic_distr_weights():
     d = _data()
     w = mp.score_statistic_distr_weights(d["W"], d["K"], d["dK"])
-    assert_allclose(w, np.array([4.55266277e-09, 3.46249449e-01]), atol=1e-7)
+    assert_allclose(w, np.array(GOLD["distr_weights"]["value"]), atol=GOLD["distr_weights"]["atol"])
 
 
 def test_score_statistic_liu_params():
@@ -74,13 +80,9 @@ def test_score_statistic_liu_params():
     _, q = _golden_y(d)
     w = mp.score_statistic_distr_weights(d["W"], d["K"], d["dK"])
     params = mp.score_statistic_liu_params(q, w)
-    assert_allclose(params["pv"], 0.22966744652848403)
-    assert_allclose(params["mu_q"], 0.34624945394475326)
-    assert_allclose(params["sigma_q"], 0.48967066729451103)
-    assert_allclose(params["dof_x"], 1.0)
+    for key in ("pv", "mu_q", "sigma_q", "dof_x"):
+        assert_allclose(params[key], GOLD["liu_params"][key])
 
 
 def test_qmin():
-    params = [{"pv": 0.22966742, "mu_q": 0.34945, "sigma_q": 0.48670, "dof_x": 1.5},
-              {"pv": 0.65, "mu_q": 0.695, "sigma_q": 0.1, "dof_x": 0.7}]
-    assert_allclose(mp.qmin(params), [0.5506645025120773, 0.7157125486956082])
+    assert_allclose(mp.qmin(GOLD["qmin"]["params"]), GOLD["qmin"]["value"])
