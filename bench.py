@@ -165,17 +165,20 @@ def cpu_reference_sample(a, gene, Gd, n_snps, repeats=1):
     once, outside the timed region, via the Gram route (qs_method="gram") so that the run stays bounded; per-SNP
     cost in the reference does not depend on the number of SNPs, so tests/s = SNPs / scan seconds."""
     from oracle import crm_port
+    from threadpoolctl import threadpool_limits
     threads = os.cpu_count() or 1
-    t0 = time.time()
-    Ls = crm_port.get_L_values(gene["hK"], gene["E"])
-    model = crm_port.CellRegMapOracle(y=gene["y"], E=gene["E"], W=gene["W"], E1=gene["E"], Ls=Ls, qs_method="gram")
-    setup_s = time.time() - t0
-    G = np.ascontiguousarray(Gd[:, :n_snps][gene["donor"]])
-    times = []
-    for _ in range(repeats):
+    # torchrun exports OMP_NUM_THREADS=1; the reference's only parallelism is the BLAS under numpy, so give it every core
+    with threadpool_limits(limits=threads):
         t0 = time.time()
-        model.scan_interaction(G)
-        times.append(time.time() - t0)
+        Ls = crm_port.get_L_values(gene["hK"], gene["E"])
+        model = crm_port.CellRegMapOracle(y=gene["y"], E=gene["E"], W=gene["W"], E1=gene["E"], Ls=Ls, qs_method="gram")
+        setup_s = time.time() - t0
+        G = np.ascontiguousarray(Gd[:, :n_snps][gene["donor"]])
+        times = []
+        for _ in range(repeats):
+            t0 = time.time()
+            model.scan_interaction(G)
+            times.append(time.time() - t0)
     return {"scan_s": times, "setup_s": setup_s, "cores": threads, "snps": n_snps}
 
 
@@ -215,8 +218,8 @@ def run_b200_arm(a):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout (one JSON line only)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "NONE"       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     import cellregmap_b200 as crm

@@ -331,3 +331,30 @@ def test_set_phenotype_equals_new_model(cuda_device):
     bb, xb = fresh.predict_interaction(d.G[:, :5], np.full(5, 0.3))
     np.testing.assert_allclose(ba, bb, rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(xa, xb, rtol=0, atol=1e-6 * np.abs(xb).max())
+
+
+@pytest.mark.parametrize("variant", ["standardised_G", "imputed_dosages", "offset_and_scale", "badly_scaled_covariate", "weak_background"])
+def test_interaction_robustness_variants(cuda_device, variant):
+    """Inputs away from the comfortable case: standardised / non-integer genotypes, a phenotype with a large offset and
+    scale, a covariate on a 1e4 scale, almost no background variance."""
+    from cellregmap_b200 import run_interaction
+    from oracle import crm_port
+    rng = np.random.default_rng(abs(hash(variant)) % 1000)
+    d = make_data(n=450, donors=45, k=5, p=18, q=4, seed=50, n_covariates=2, normalize_G=(variant == "standardised_G"))
+    y, W, G = d.y.copy(), d.W.copy(), d.G.copy()
+    if variant == "imputed_dosages":
+        G = np.clip(G + 0.15 * rng.standard_normal(G.shape), 0.0, 2.0)
+    if variant == "offset_and_scale":
+        y = 250.0 + 40.0 * y
+    if variant == "badly_scaled_covariate":
+        W[:, 1] = 1.0e4 * W[:, 1] + 3.0e4
+    if variant == "weak_background":
+        y = 0.3 + rng.standard_normal(y.shape[0])
+    ref_pv, ref_info = crm_port.run_interaction(y, d.E, G, W=W, hK=d.hK)
+    pv, info = run_interaction(y, d.E, G, W=W, hK=d.hK)
+    if variant != "weak_background":      # with no background signal the lml grid is flat and the pick is noise (SURVEY 7)
+        np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+        np.testing.assert_allclose(info["eps2"], ref_info["eps2"], rtol=RTOL_VC)
+    same = info["rho1"] == ref_info["rho1"]
+    assert same.mean() >= 0.8
+    assert np.max(np.abs(np.log10(pv[same]) - np.log10(ref_pv[same]))) <= DLOG10_P
