@@ -350,11 +350,21 @@ def test_interaction_robustness_variants(cuda_device, variant):
         W[:, 1] = 1.0e4 * W[:, 1] + 3.0e4
     if variant == "weak_background":
         y = 0.3 + rng.standard_normal(y.shape[0])
-    ref_pv, ref_info = crm_port.run_interaction(y, d.E, G, W=W, hK=d.hK)
+    stages = {}
+    ref_pv, ref_info = crm_port.run_interaction(y, d.E, G, W=W, hK=d.hK, stages=stages)
     pv, info = run_interaction(y, d.E, G, W=W, hK=d.hK)
-    if variant != "weak_background":      # with no background signal the lml grid is flat and the pick is noise
-        np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
-        np.testing.assert_allclose(info["eps2"], ref_info["eps2"], rtol=RTOL_VC)
     same = info["rho1"] == ref_info["rho1"]
-    assert same.mean() >= 0.8
+    if variant != "weak_background":
+        assert same.all()
+        np.testing.assert_allclose(info["eps2"], ref_info["eps2"], rtol=RTOL_VC)
+    else:
+        # no background signal: the fitted background variance collapses, the lml grid is flat to round-off and the strict
+        # '>' pick of rho1 is noise (SURVEY 7 "degenerate rho1 ties") -- wherever the pick differs the oracle's own lml values
+        # must be tied, and the test itself (K0 ~ eps2 I whatever rho1) must still agree
+        lml = np.array([[f[1] for f in fits] for fits in stages["fits"]])
+        grid = np.linspace(0, 1, 11)
+        for i in np.where(~same)[0]:
+            a = int(np.argmin(np.abs(grid - info["rho1"][i]))); b = int(np.argmin(np.abs(grid - ref_info["rho1"][i])))
+            assert abs(lml[i, a] - lml[i, b]) <= 1e-7 * abs(lml[i, b])
+        assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= 1e-3
     assert np.max(np.abs(np.log10(pv[same]) - np.log10(ref_pv[same]))) <= DLOG10_P
