@@ -19,7 +19,7 @@ from . import _lib
 EPS_SMALL = float(np.sqrt(np.finfo(float).eps))
 
 # bench.py switches this on to time the rotation kernel with CUDA events inside the library
-PROFILE = {"on": False, "rot_ms": 0.0, "rot_flops": 0.0, "rot_launches": 0}
+PROFILE = {"on": False, "rot_ms": 0.0, "rot_flops": 0.0, "rot_launches": 0, "int8_ms": 0.0, "int8_ops": 0.0, "int8_launches": 0}
 
 
 def _device(device=None):
@@ -275,6 +275,10 @@ class CellRegMap:
             PROFILE["rot_ms"] += ms.value
             PROFILE["rot_flops"] += fl.value
             PROFILE["rot_launches"] += nl.value
+            _lib.call("crm_profile_int8", self._handle, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(nl))
+            PROFILE["int8_ms"] += ms.value
+            PROFILE["int8_ops"] += fl.value
+            PROFILE["int8_launches"] += nl.value
         out.update(extra)
         return out
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "crm_launch_count": (ctypes.c_longlong, []),
     "crm_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_int64)]),
+    "crm_profile_int8": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "crm_gemm": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64,
                                 ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                 ctypes.c_int, ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int,

@@ -39,6 +39,27 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+// CRM_TRACE=1: per-phase device times (CUDA events on the launching stream) printed to stderr at the end of a call
+struct PhaseTrace {
+    bool on;
+    cudaStream_t st;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    explicit PhaseTrace(cudaStream_t s) : st(s) { static const bool env = [] { const char* v = getenv("CRM_TRACE"); return v && atoi(v) != 0; }(); on = env; mark("begin"); }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.emplace_back(name, e);
+    }
+    void report(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[crm trace] %s:", what);
+        for (size_t i = 1; i < marks.size(); i++) { float ms = 0.f; cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second); fprintf(stderr, " %s %.2f ms |", marks[i].first, ms); }
+        fprintf(stderr, "\n");
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
+};
+
 // Grow-only device buffer.  Allocation goes through the device's default CUDA memory pool (cudaMallocAsync on the
 // legacy default stream) with an unlimited release threshold, so that creating and destroying model objects in a loop
 // (one per gene) reuses the same physical memory instead of paying cudaMalloc/cudaFree of tens of GB every time.
@@ -95,6 +116,13 @@ struct Handle {
     DevBuf HxE_D, A2_D, dperm, doff;
     DevBuf HxE;           // optional n x (kexp * ldH) pre-expanded basis [Hx | Hx.E0_1 | ... | Hx.E0_k] (see launch_rotation)
     bool use_hxe = false, hxe_built = false;
+    // exact int8 split of the rotation for integer dosages (ozaki.cuh): digit planes of HxE, built by the first rotation that uses them
+    int rotation_mode = 0;        // 0 auto (int8 split when the genotype block is integer), 1 fp64 DMMA only, 2 int8 split required
+    bool oz_built = false, oz_built_a2 = false;
+    DevBuf A8, a8expo, Gt8, G2t8, D32, ozflags, A28, a28expo;   // A28: digit planes of A2 = [1 | E0 | pairs] for the g^2 Grams
+    bool oz_block_valid = false;   // Gt8 / G2t8 hold the int8 image of the genotype block of the rotation just done
+    int oz_block_gmax = 0;
+    double prof_oz_gemm_ops = 0.0; std::vector<cudaEvent_t> prof_oz_events;
     int hxe_blocks = 0;   // context blocks j held by HxE at a time: kexp = whole basis resident, fewer = streamed in groups
     DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
     // null-model state for the association scans
@@ -110,7 +138,7 @@ struct Handle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     void free_all() {
-        DevBuf* all[] = {&HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
+        DevBuf* all[] = {&A8, &a8expo, &Gt8, &G2t8, &D32, &ozflags, &A28, &a28expo, &HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
                          &gtchunk[0], &gtchunk[1], &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
@@ -341,6 +369,8 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
     build_a2_kernel<<<blocks_for(h->n * h->ld2, 256), 256, 0, st>>>(E0, lde0, h->n, h->k0, h->A2.as<double>(), h->ld2);
     CRM_CUDA(cudaGetLastError()); count_launch();
     h->hxe_built = false;    // the pre-expanded basis is (re)built by the first cell-level rotation that needs it
+    h->oz_built = false;
+    h->oz_built_a2 = false;
     h->cells.K = h->n; h->cells.HxE = nullptr; h->cells.ldE = (long long)h->kexp * h->ldH;   // cells.HxE unused: see launch_rotation
     h->cells.Hx = h->Hx.as<double>(); h->cells.ldHx = h->ldH; h->cells.A2 = h->A2.as<double>(); h->cells.ld2 = h->ld2;
     if (h->donors_set) CRM_CHECK(aggregate_donors(h, st));
@@ -353,6 +383,59 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
 // n*kexp*ldH*8 bytes fit comfortably; otherwise it is streamed through a smaller buffer in groups of context blocks, rebuilt
 // per rotation call (one elementwise pass per group, negligible against the contraction).  Without it (CRM_NO_HXE=1) the
 // factor is applied to the genotype fragments on the fly (EXPAND mode, ~90% of peak, no extra memory).
+// Rotation through the exact int8 split (ozaki.cuh): *used = 1 when the block was integer-valued and the route was taken.
+static int rotation_int8_split(Handle* h, const double* G, long long ldg, long long B, double* C, cudaStream_t st, int* used) {
+    *used = 0;
+    const long long n = h->n, Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
+    const size_t a8_bytes = (size_t)OZAKI_SLICES * Mp * Kp;
+    if (!h->oz_built) {      // room for the digit planes?
+        size_t free_b = 0, total_b = 0;
+        CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        cudaMemPool_t mp_; unsigned long long reserved = 0, usedb = 0;
+        if (cudaDeviceGetDefaultMemPool(&mp_, h->device) == cudaSuccess && cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrUsedMemCurrent, &usedb) == cudaSuccess && reserved > usedb) free_b += (size_t)(reserved - usedb);
+        if (h->A8.cap < a8_bytes && (double)a8_bytes + (double)OZAKI_SLICES * Mp * Bp * 4.0 > 0.5 * (double)free_b) return CRM_OK;
+    }
+    PhaseTrace tr(st);
+    h->oz_block_valid = false;
+    CRM_CHECK(h->Gt8.reserve((size_t)Bp * Kp));
+    CRM_CHECK(h->G2t8.reserve((size_t)Bp * Kp));
+    CRM_CHECK(h->ozflags.reserve(64));
+    CRM_CHECK(oz_launch_genotypes(G, ldg, n, B, h->Gt8.as<int8_t>(), h->G2t8.as<int8_t>(), Bp, Kp, h->ozflags.as<int>(), st));
+    int flags[2] = {0, 0};
+    CRM_CUDA(cudaMemcpyAsync(flags, h->ozflags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaStreamSynchronize(st));
+    tr.mark("genotypes->int8");
+    if (flags[0] != 0) return CRM_OK;                                              // not integer dosages
+    if ((double)Kp * 64.0 * (double)std::max(flags[1], 1) >= 2147483648.0) return CRM_OK;   // int32 accumulation could overflow
+    if (!h->oz_built) {
+        CRM_CHECK(h->A8.reserve(a8_bytes));
+        CRM_CHECK(h->a8expo.reserve((size_t)Mtot * sizeof(int)));
+        CRM_CHECK(oz_launch_exponents(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, n, h->a8expo.as<int>(), st));
+        CRM_CHECK(oz_launch_slices(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, 0, h->kexp, n, h->a8expo.as<int>(), h->A8.as<int8_t>(), Mp, Kp, st));
+        h->oz_built = true;
+        tr.mark("digit planes");
+    }
+    CRM_CHECK(h->D32.reserve((size_t)OZAKI_SLICES * Mp * Bp * sizeof(int)));
+    if (h->prof_on) {
+        cudaEvent_t e0, e1;
+        CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
+        CRM_CUDA(cudaEventRecord(e0, st));
+        h->prof_oz_events.push_back(e0); h->prof_oz_events.push_back(e1);
+        h->prof_oz_gemm_ops += 2.0 * (double)OZAKI_SLICES * (double)Mp * (double)Kp * (double)Bp;
+    }
+    CRM_CHECK(oz_int8_gemm(h->A8.as<int8_t>(), (long long)OZAKI_SLICES * Mp, h->Gt8.as<int8_t>(), Bp, Kp, h->D32.as<int>(), Bp, st));
+    if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_oz_events.back(), st));
+    tr.mark("int8 gemm");
+    CRM_CHECK(oz_launch_combine(h->D32.as<int>(), Mp, Bp, h->a8expo.as<int>(), Mtot, B, C, Mtot, st));
+    tr.mark("combine");
+    tr.report("int8 rotation");
+    h->oz_block_valid = true;
+    h->oz_block_gmax = flags[1];
+    *used = 1;
+    return CRM_OK;
+}
+
 static int launch_rotation(Handle* h, const double* G, long long ldg, long long gcols, long long B, double* C, cudaStream_t st) {
     const Handle::GenoSpace& gs = *h->gs;
     const long long ldE = (long long)h->kexp * h->ldH;
@@ -361,6 +444,12 @@ static int launch_rotation(Handle* h, const double* G, long long ldg, long long 
     if (h->gs == &h->donors) {                       // donor-level operands are always fully expanded (d rows only)
         op.A = gs.HxE; op.lda = gs.ldE; op.a_cols = gs.ldE;
         return launch_gemm(GEMM_PLAIN, op, (int)gs.K, 0, (int)gs.ldE, 0, (int)B, C, gs.ldE, 1, st);
+    }
+    if (h->rotation_mode != 1) {
+        int used = 0;
+        CRM_CHECK(rotation_int8_split(h, G, ldg, B, C, st, &used));
+        if (used) return CRM_OK;
+        if (h->rotation_mode == 2) { set_error("CRM_ROTATION=int8 but the genotype block is not integer-valued in [-127, 127] (or memory is short)"); return CRM_ERR_UNSUPPORTED; }
     }
     if (h->use_hxe) {
         const int nb = h->hxe_blocks;
@@ -420,6 +509,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     CRM_CHECK(h->stats.reserve((size_t)(1 + c + c * c + R + 4) * 8));
     CRM_CHECK(h->devinfo.reserve((size_t)(2 * R + 8) * sizeof(int)));
 
+    PhaseTrace tr(st);
     // Hx = [E1 | L | y | W]
     double* Hx = h->Hx.as<double>();
     CRM_CUDA(cudaMemsetAsync(Hx, 0, (size_t)n * ldH * 8, st));
@@ -449,6 +539,10 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         (void)bytes;
         if (!h->use_hxe) h->HxE.release();
     }
+    {
+        const char* rm = getenv("CRM_ROTATION");      // "dmma": fp64 tensor cores only; "int8": exact int8 split required; default auto
+        h->rotation_mode = (rm && !strcmp(rm, "dmma")) ? 1 : (rm && !strcmp(rm, "int8")) ? 2 : 0;
+    }
     CRM_CHECK(build_test_contexts(h, E0, lde0, st));
 
     // Gram of [H | y | W] by the K1 kernel (plain mode): H'H, H'y, H'W, y'y, W'y, W'W
@@ -462,6 +556,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     CRM_CHECK(gram_status);
     extract_stats_kernel<<<1, 1024, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
+    tr.mark("operands+gram");
 
     // per-rho eigendecomposition (cuSOLVER, one-off per gene) with one pooled cuSOLVER context per device.  Measured on
     // B200: Dsyevd takes 12 ms per 1020 x 1020 problem and R of them on R streams (with or without one host thread each)
@@ -524,6 +619,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
             CRM_CUDA(cudaGetLastError()); count_launch();
         }
     }
+    tr.mark("eigendecompositions");
     rotate_null_kernel<<<blocks_for((long long)R * mp, 128), 128, 0, st>>>(h->Tt.as<double>(), (long long)R * mp, h->gram.as<double>(), ldH, m,
                                                                          mp, R, c, h->yr.as<double>(), h->Wr.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
@@ -541,6 +637,8 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         h->max_rank = std::max(h->max_rank, info[R + r]);
     }
     h->ready = true;
+    tr.mark("rotate null");
+    tr.report("set-up");
     return CRM_OK;
 }
 
@@ -569,6 +667,7 @@ static int do_update_phenotype(Handle* h, const double* y, cudaStream_t st) {
     build_yw_kernel<<<blocks_for(std::max<long long>((long long)R * (1 + c) * mp, (long long)(1 + c) * (1 + c)), 256), 256, 0, st>>>(
         h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
+    h->oz_built = false;     // the digit planes of the y column (and its exponent) change with the phenotype: rebuilt on demand
     if (h->use_hxe && h->hxe_built && h->hxe_blocks == h->kexp) {
         refresh_y_hxe_kernel<<<blocks_for(h->n * h->kexp, 256), 256, 0, st>>>(Hx, ldH, m, h->Eext.as<double>(), h->epitch, h->kexp, h->n, h->HxE.as<double>());
         CRM_CUDA(cudaGetLastError()); count_launch();
@@ -722,6 +821,7 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     const int R = h->R, mp = h->mp, m = h->m, k = h->k0, kexp = h->kexp, c = h->c, ldH = h->ldH, Mx = h->Mx;
     double* C = h->C.as<double>();
     double* sq = h->sq.as<double>();
+    PhaseTrace tr(st);
     // 1. rotation of [g, g.E0] onto [H | y | W]
     if (h->prof_on) {
         cudaEvent_t e0, e1;
@@ -732,8 +832,21 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     }
     CRM_CHECK(launch_rotation(h, Gt ? Gt : Gd, Gt ? ldgt : ldg, gcols, B, C, st));
     if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_events.back(), st));
+    tr.mark("rotation");
     // 2. squared-genotype Grams against [1 | E0 | pairs]:  g'g, (g.E0)'g, (g.E0)'(g.E0)
-    {
+    if (!Gt && h->gs == &h->cells && h->oz_block_valid && h->oz_block_gmax <= 11) {
+        // integer dosages: g^2 is an exact int8 operand as well -> same int8 split with the digit planes of A2
+        const long long n = h->n, M2p = round_up(h->M2, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
+        if (h->A28.cap == 0 || !h->oz_built_a2) {
+            CRM_CHECK(h->A28.reserve((size_t)OZAKI_SLICES * M2p * Kp));
+            CRM_CHECK(h->a28expo.reserve((size_t)h->M2 * sizeof(int)));
+            CRM_CHECK(oz_launch_matrix_planes(h->A2.as<double>(), h->ld2, h->M2, n, h->a28expo.as<int>(), h->A28.as<int8_t>(), M2p, Kp, st));
+            h->oz_built_a2 = true;
+        }
+        CRM_CHECK(h->D32.reserve((size_t)OZAKI_SLICES * M2p * Bp * sizeof(int)));
+        CRM_CHECK(oz_int8_gemm(h->A28.as<int8_t>(), (long long)OZAKI_SLICES * M2p, h->G2t8.as<int8_t>(), Bp, Kp, h->D32.as<int>(), Bp, st));
+        CRM_CHECK(oz_launch_combine(h->D32.as<int>(), M2p, Bp, h->a28expo.as<int>(), h->M2, B, sq, h->ld2, st));
+    } else {
         GemmOperands op{};
         op.A = h->gs->A2; op.lda = h->gs->ld2; op.a_cols = h->M2;
         op.B = Gt ? Gt : Gd; op.ldb = Gt ? ldgt : ldg; op.b_cols = gcols;
@@ -754,6 +867,7 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
         o2.B2 = Gt; o2.ldb2 = ldgt;
         CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->gs->K, 1, k, 0, (int)B, sq + 1, h->ld2, 1, st));
     }
+    tr.mark("g2 grams");
     // 3. H'g as a K-outer operand, 4. rotated genotype for every rho
     const long long ldhg = round_up(B, 2);
     CRM_CHECK(launch_gather_transpose(C, ldH, nullptr, kexp, 0, 1, B, m, h->Hg.as<double>(), ldhg, st));
@@ -764,6 +878,7 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
         op.B2 = op.B; op.ldb2 = ldhg; op.b2_cols = B;
         CRM_CHECK(launch_gemm(GEMM_PLAIN, op, m, 0, R * mp, 0, (int)B, h->gr.as<double>(), (long long)R * mp, 1, st));
     }
+    tr.mark("transform g");
     // 5. REML fits for every (SNP, rho)
     FitArgs fa{};
     fa.S = h->S.as<double>(); fa.yr = h->yr.as<double>(); fa.Wr = h->Wr.as<double>();
@@ -787,6 +902,7 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     } else {
         CRM_CHECK(launch_fit(fa, true, st));
     }
+    tr.mark("fits");
     // 6. best rho per SNP, grouping by rho
     CRM_CHECK(launch_select(fa.lml, fa.delta, fa.scale, (int)B, R, h->rho_idx.as<int>(), h->best_lml.as<double>(), h->v0.as<double>(),
                             h->v1.as<double>(), st));
@@ -799,6 +915,7 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     std::vector<int> off(R + 1);
     CRM_CUDA(cudaMemcpyAsync(off.data(), h->offsets.as<int>(), (size_t)(R + 1) * 4, cudaMemcpyDeviceToHost, st));
     CRM_CUDA(cudaStreamSynchronize(st));
+    tr.mark("select+group");
     // 7. H'(g.E0) in rho-sorted order as a K-outer operand, 8. rotation into the selected eigenbasis, group by group
     const long long ldvg = round_up(B * k, 2);
     CRM_CHECK(launch_gather_transpose(C, ldH, h->perm.as<int>(), kexp, 1, k, B * k, m, h->Vg.as<double>(), ldvg, st));
@@ -811,6 +928,7 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
         op.B2 = op.B; op.ldb2 = ldvg; op.b2_cols = B * k;
         CRM_CHECK(launch_gemm(GEMM_PLAIN, op, m, r * mp, mp, (int)(off[r] * k), (int)(cnt * k), h->GEr.as<double>() + (long long)off[r] * k * mp, mp, 1, st));
     }
+    tr.mark("transform gE");
     // 9. score statistic + eigenvalues
     ScoreArgs sa{};
     sa.S = fa.S; sa.yr = fa.yr; sa.Wr = fa.Wr; sa.m = m; sa.mp = mp; sa.R = R; sa.c = c; sa.k = k; sa.kexp = kexp; sa.p = (int)B;
@@ -821,12 +939,14 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     sa.Q = h->Q.as<double>(); sa.lam = h->lam.as<double>(); sa.lam_ld = k; sa.nlam = h->nlam.as<int>(); sa.flags = h->sflags.as<int>();
     sa.Mout = (dg && dg->M) ? dg->M + s0 * k * k : nullptr;
     CRM_CHECK(launch_score(sa, B, st));
+    tr.mark("score");
     // 10. p-values
     PvalArgs pa{};
     pa.Q = sa.Q; pa.lam = sa.lam; pa.nlam = sa.nlam; pa.lam_ld = k; pa.count = (int)B; pa.lim = 10000; pa.acc = 1e-6;
     pa.pv = out_pv + s0; pa.liu = (dg && dg->liu) ? dg->liu + s0 : h->liu.as<double>();
     pa.ifault = (dg && dg->ifault) ? dg->ifault + s0 : h->ifault.as<int>(); pa.converged = h->conv.as<int>(); pa.trace = nullptr;
     CRM_CHECK(launch_pvalues(pa, st));
+    tr.mark("p-values");
     // 11. outputs
     double* grid_dev = h->scratch.as<double>();
     CRM_CUDA(cudaMemcpyAsync(grid_dev, h->rho.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
@@ -847,6 +967,8 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
             CRM_CUDA(cudaGetLastError()); count_launch();
         }
     }
+    tr.mark("outputs");
+    tr.report("interaction batch");
     return CRM_OK;
 }
 
@@ -1148,6 +1270,25 @@ int crm_set_donors(crm_handle_t h, const int32_t* perm, const int32_t* offsets, 
     H.donors.K = d;
     H.donors_set = true;
     return aggregate_donors(&H, st);
+}
+
+int crm_profile_int8(crm_handle_t h, double* gemm_ms, double* gemm_ops, int64_t* launches) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    Handle& H = h->impl;
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < H.prof_oz_events.size(); i += 2) {
+        float t = 0.f;
+        CRM_CUDA(cudaEventSynchronize(H.prof_oz_events[i + 1]));
+        CRM_CUDA(cudaEventElapsedTime(&t, H.prof_oz_events[i], H.prof_oz_events[i + 1]));
+        ms += t;
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_ops) *gemm_ops = H.prof_oz_gemm_ops;
+    if (launches) *launches = (int64_t)(H.prof_oz_events.size() / 2);
+    for (cudaEvent_t e : H.prof_oz_events) cudaEventDestroy(e);
+    H.prof_oz_events.clear();
+    H.prof_oz_gemm_ops = 0.0;
+    return CRM_OK;
 }
 
 int crm_get_dims(crm_handle_t h, int64_t* d) {

@@ -1,0 +1,168 @@
+// Exact integer split of the fp64 rotation (Ozaki scheme) for integer dosages.
+//
+// The rotation C[s][col] = sum_n HxE[n][col] * G[n][s] (see launch_rotation in abi.cu) has one operand that is exactly
+// representable in int8 whenever the genotypes are integer dosages (0/1/2, or any integer in [-127, 127]).  The other
+// operand is split once per gene into SLICES int8 digit planes per column,
+//     HxE[n][col] = 2^(e_col + 1) * sum_t q_t[n][col] 2^(-7 (t + 1))   (+ a remainder below 2^(e_col - 56)),
+// so that every slice product q_t' g is an exact int8 x int8 -> int32 tensor-core contraction (tcgen05 on sm_100) and
+//     C[s][col] = 2^(e_col + 1) * sum_t 2^(-7 (t + 1)) D_t[col][s]
+// is assembled in fp64.  Eight 7-bit digits cover 56 bits below the column maximum: the result carries the rounding of
+// one fp64 sum of eight terms, like the DMMA route carries the rounding of its fp64 accumulation.
+#pragma once
+#include "common.cuh"
+
+namespace crm {
+
+constexpr int OZ_SLICES = 8;
+constexpr int OZ_TILE = 32;
+
+constexpr int OZ_EXP_EMPTY = -100000;      // exponent marker of an all-zero column
+
+// exponent e with |x| < 2^e for the largest |x| of each column of HxE = Eext[:, j] * Hx[:, a]  (col = j * ldH + a);
+// expo must be pre-filled with OZ_EXP_EMPTY; rows are split over blockIdx.z and merged with atomicMax
+__global__ void oz_column_exponent_kernel(const double* Hx, int ldH, const double* Eext, int epitch, long long n, int* expo) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (a >= ldH) return;
+    const long long chunk = (n + gridDim.z - 1) / gridDim.z, i0 = (long long)blockIdx.z * chunk, i1 = min(n, i0 + chunk);
+    double mx = 0.0;
+    for (long long i = i0; i < i1; i++) mx = fmax(mx, fabs(Eext[i * epitch + j] * Hx[i * ldH + a]));
+    if (mx > 0.0) {
+        int e = 0;
+        frexp(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)  ->  mx < 2^e
+        atomicMax(&expo[(long long)j * ldH + a], e);
+    }
+}
+
+constexpr int OZ_ROWS = 128;               // cells per block of the slicing kernel (4 per thread -> char4 stores)
+
+// digit planes, K-major: A8[t][col][i] (plane stride = Mp * Kp, row stride = Kp, Kp a multiple of 4)
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* Hx, int ldH, const double* Eext, int epitch, int j0, int nj, long long n, const int* expo,
+                                                       int8_t* A8, long long Mp, long long Kp) {
+    __shared__ double tile[OZ_ROWS][OZ_TILE + 1];
+    const long long i0 = (long long)blockIdx.x * OZ_ROWS;
+    const int a0 = blockIdx.y * OZ_TILE;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int jj = 0; jj < nj; jj++) {
+        const int j = j0 + jj;
+        for (int r = ty; r < OZ_ROWS; r += 8) {                   // read: rows i, columns a (coalesced along a)
+            const long long i = i0 + r; const int a = a0 + tx;
+            tile[r][tx] = (i < n && a < ldH) ? Eext[i * epitch + j] * Hx[i * ldH + a] : 0.0;
+        }
+        __syncthreads();
+        for (int r = ty; r < OZ_TILE; r += 8) {                   // write: rows a, 4 consecutive cells per thread
+            const int a = a0 + r; const long long i = i0 + 4 * tx;
+            if (a < ldH && i < Kp) {
+                const long long col = (long long)j * ldH + a;
+                const int e = expo[col];
+                double x[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) x[u] = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(tile[4 * tx + u][r], -(e + 1));   // |x| < 1/2
+#pragma unroll
+                for (int t = 0; t < OZ_SLICES; t++) {
+                    char4 q;
+                    signed char* qq = reinterpret_cast<signed char*>(&q);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { x[u] *= 128.0; const double d = rint(x[u]); x[u] -= d; qq[u] = (signed char)(int)d; }
+                    *reinterpret_cast<char4*>(A8 + (long long)t * Mp * Kp + col * Kp + i) = q;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// the same two steps for an explicit n x cols matrix X (row stride ldx): exponents, then digit planes P8[t][col][i]
+__global__ void oz_matrix_exponent_kernel(const double* X, long long ldx, int cols, long long n, int* expo) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cols) return;
+    const long long chunk = (n + gridDim.y - 1) / gridDim.y, i0 = (long long)blockIdx.y * chunk, i1 = min(n, i0 + chunk);
+    double mx = 0.0;
+    for (long long i = i0; i < i1; i++) mx = fmax(mx, fabs(X[i * ldx + a]));
+    if (mx > 0.0) { int e = 0; frexp(mx, &e); atomicMax(&expo[a], e); }
+}
+__global__ void __launch_bounds__(256) oz_matrix_slice_kernel(const double* X, long long ldx, int cols, long long n, const int* expo, int8_t* P8, long long Mp,
+                                                              long long Kp) {
+    __shared__ double tile[OZ_ROWS][OZ_TILE + 1];
+    const long long i0 = (long long)blockIdx.x * OZ_ROWS;
+    const int a0 = blockIdx.y * OZ_TILE;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < OZ_ROWS; r += 8) {
+        const long long i = i0 + r; const int a = a0 + tx;
+        tile[r][tx] = (i < n && a < cols) ? X[i * ldx + a] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < OZ_TILE; r += 8) {
+        const int a = a0 + r; const long long i = i0 + 4 * tx;
+        if (a < cols && i < Kp) {
+            const int e = expo[a];
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(tile[4 * tx + u][r], -(e + 1));
+#pragma unroll
+            for (int t = 0; t < OZ_SLICES; t++) {
+                char4 q;
+                signed char* qq = reinterpret_cast<signed char*>(&q);
+#pragma unroll
+                for (int u = 0; u < 4; u++) { x[u] *= 128.0; const double d = rint(x[u]); x[u] -= d; qq[u] = (signed char)(int)d; }
+                *reinterpret_cast<char4*>(P8 + (long long)t * Mp * Kp + (long long)a * Kp + i) = q;
+            }
+        }
+    }
+}
+
+// Gt8[s][i] = (int8) G[i][s] for a block of SNP columns (K-major), zero padded to Bp x Kp; flags[0] |= 1 when some entry is
+// not an integer in [-127, 127]; flags[1] = max |g|
+// G2t8 (may be null) receives the squares g^2 (valid when max |g| <= 11).
+__global__ void oz_genotype_kernel(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags) {
+    __shared__ double tile[OZ_TILE][OZ_TILE + 1];
+    const long long i0 = (long long)blockIdx.x * OZ_TILE;
+    const long long s0 = (long long)blockIdx.y * OZ_TILE;
+    int bad = 0, gmax = 0;
+    for (int r = threadIdx.y; r < OZ_TILE; r += blockDim.y) {
+        const long long i = i0 + r, s = s0 + threadIdx.x;
+        double v = 0.0;
+        if (i < n && s < B) {
+            v = G[i * ldg + s];
+            if (!(v == rint(v)) || fabs(v) > 127.0) bad = 1; else gmax = max(gmax, (int)fabs(v));
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < OZ_TILE; r += blockDim.y) {
+        const long long s = s0 + r, i = i0 + threadIdx.x;
+        if (s < Bp && i < Kp) {
+            const int gv = (int)tile[threadIdx.x][r];
+            Gt8[s * Kp + i] = (int8_t)gv;
+            if (G2t8) G2t8[s * Kp + i] = (int8_t)(gv * gv);
+        }
+    }
+    if (bad) atomicOr(&flags[0], 1);
+    if (gmax) atomicMax(&flags[1], gmax);
+}
+
+// C[s][col] = 2^(e_col + 1) sum_t 2^(-7 (t + 1)) D[t * Mp + col][s]   (D int32, row stride ldd; C fp64, row stride ldc)
+__global__ void oz_combine_kernel(const int* D, long long Mp, long long ldd, const int* expo, long long Mtot, long long B, double* C, long long ldc) {
+    __shared__ double tile[OZ_TILE][OZ_TILE + 1];
+    const long long s0 = (long long)blockIdx.x * OZ_TILE;
+    const long long c0 = (long long)blockIdx.y * OZ_TILE;
+    for (int r = threadIdx.y; r < OZ_TILE; r += blockDim.y) {           // read: rows col, columns s (coalesced along s)
+        const long long col = c0 + r, s = s0 + threadIdx.x;
+        double acc = 0.0;
+        if (col < Mtot && s < B) {
+#pragma unroll
+            for (int t = OZ_SLICES - 1; t >= 0; t--)                   // smallest terms first; Horner in base 2^-7 (exact scalings)
+                acc = (acc + (double)D[((long long)t * Mp + col) * ldd + s]) * 0.0078125;
+            const int e = expo[col];
+            acc = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(acc, e + 1);
+        }
+        tile[r][threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < OZ_TILE; r += blockDim.y) {           // write: rows s, columns col (coalesced along col)
+        const long long s = s0 + r, col = c0 + threadIdx.x;
+        if (s < B && col < Mtot) C[s * ldc + col] = tile[threadIdx.x][r];
+    }
+}
+
+}  // namespace crm

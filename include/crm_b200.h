@@ -124,6 +124,10 @@ CRM_API long long crm_launch_count(void);
  * call (ms, algorithmic flop = 2 n m (1+k0) per SNP, launches), resets them, and switches the timing on/off. */
 CRM_API int crm_profile(crm_handle_t h, int enable, double* rot_ms, double* rot_flops, int64_t* rot_launches);
 
+/* Same for the int8 tensor-core contraction of the exact int8 split of the rotation (taken for integer dosages unless
+ * CRM_ROTATION=dmma): totals since the last call (ms, int8 multiply-add operations x 2, launches). */
+CRM_API int crm_profile_int8(crm_handle_t h, double* gemm_ms, double* gemm_ops, int64_t* launches);
+
 /* ---- stage-level entry points (used by the parity tests and by the Python mirror) ---- */
 
 /* K1: out[n_count][m_count] (ldc) = B[:, n_begin:+n_count]' A[:, m_begin:+m_count] over K rows.

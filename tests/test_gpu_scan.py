@@ -216,6 +216,7 @@ def test_rotation_routes_agree(cuda_device, monkeypatch):
     """The pre-expanded-basis route (plain contraction) and the on-the-fly Hadamard route give the same scan."""
     from cellregmap_b200._cellregmap import _make_interaction_model
     d = make_data(n=900, donors=60, k=7, p=130, q=5, seed=17)
+    monkeypatch.setenv("CRM_ROTATION", "dmma")      # integer dosages would otherwise take the int8 split
     model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
     assert model._dims["pre_expanded_basis"]
     pv_a, info_a = model.scan_interaction(d.G)
@@ -368,3 +369,39 @@ def test_interaction_robustness_variants(cuda_device, variant):
             assert abs(lml[i, a] - lml[i, b]) <= 1e-7 * abs(lml[i, b])
         assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= 1e-3
     assert np.max(np.abs(np.log10(pv[same]) - np.log10(ref_pv[same]))) <= DLOG10_P
+
+
+def test_int8_split_rotation_matches_fp64_rotation(cuda_device, monkeypatch):
+    """Integer dosages take the exact int8 split of the rotation; CRM_ROTATION=dmma forces the fp64 tensor-core route.
+    Same selected rho1, variance components to 1e-8, p-values to 1e-7 in log10; non-integer genotypes fall back by
+    themselves."""
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    from oracle import crm_port
+    d = make_data(n=1100, donors=60, k=7, p=150, q=5, seed=61)
+    monkeypatch.setenv("CRM_ROTATION", "int8")
+    m_i = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    out_i = m_i._scan_interaction_device(d.G, diagnostics=True)
+    monkeypatch.setenv("CRM_ROTATION", "dmma")
+    m_d = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    out_d = m_d._scan_interaction_device(d.G, diagnostics=True)
+    assert torch.equal(out_i["rho1"], out_d["rho1"])
+    np.testing.assert_allclose(out_i["Q"].cpu().numpy(), out_d["Q"].cpu().numpy(), rtol=1e-7)
+    for key in ("e2", "g2", "eps2"):
+        np.testing.assert_allclose(out_i[key].cpu().numpy(), out_d[key].cpu().numpy(), rtol=2e-6, atol=1e-12)
+    assert float((torch.log10(out_i["pv"]) - torch.log10(out_d["pv"])).abs().max()) <= 1e-6
+    # against the oracle
+    ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, d.G[:, :40], W=d.W, hK=d.hK)
+    np.testing.assert_array_equal(out_i["rho1"][:40].cpu().numpy(), ref_info["rho1"])
+    assert np.max(np.abs(np.log10(out_i["pv"][:40].cpu().numpy()) - np.log10(ref_pv))) <= DLOG10_P
+    # auto mode: non-integer genotypes silently use the fp64 route and agree with it
+    monkeypatch.delenv("CRM_ROTATION")
+    Gf = d.G + 0.25
+    m_a = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    pv_a, _ = m_a.scan_interaction(Gf)
+    pv_f, _ = m_d.scan_interaction(Gf)
+    np.testing.assert_array_equal(pv_a, pv_f)
+    monkeypatch.setenv("CRM_ROTATION", "int8")
+    m_bad = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    with pytest.raises(RuntimeError):
+        m_bad.scan_interaction(Gf)
