@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-donor-level", action="store_true")
+    ap.add_argument("--no-fp64-route", action="store_true")
     return ap.parse_args()
 
 
@@ -286,7 +287,7 @@ def run_b200_arm(a):
         step_device()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    api.PROFILE.update(on=True, rot_ms=0.0, rot_flops=0.0, rot_launches=0)
+    api.PROFILE.update(on=True, rot_ms=0.0, rot_flops=0.0, rot_launches=0, int8_ms=0.0, int8_ops=0.0, int8_launches=0)
     launches0 = lib.crm_launch_count()
     ms_total, wall, res = timed(step_device, a.steps)
     launches = lib.crm_launch_count() - launches0
@@ -296,8 +297,67 @@ def run_b200_arm(a):
     value = world * p / (ms_per_step / 1e3)
     rot_ms, rot_flops, rot_launches = api.PROFILE["rot_ms"], api.PROFILE["rot_flops"], api.PROFILE["rot_launches"]
     achieved = rot_flops / (rot_ms * 1e-3) / 1e12 if rot_ms > 0 else None
+    int8_ms, int8_ops, int8_launches = api.PROFILE["int8_ms"], api.PROFILE["int8_ops"], api.PROFILE["int8_launches"]
     pv = res[0]
     top = torch.argsort(pv)[:4].tolist()
+    alg_flop = 2.0 * a.cells * a.contexts * (1 + a.hk_rank) * (1 + a.contexts)
+    default_workload = (a.cells, a.donors, a.contexts, a.hk_rank, a.snps) == (100000, 1000, 20, 50, 10000)
+    if int8_launches > 0:
+        # Integer dosages: the rotation ran as the exact int8 split (hand-written slicing / conversion / recombination
+        # kernels around one plain int8 tensor-core GEMM served by cuBLASLt's tcgen05 kernels).  The dominant kernel of the
+        # step is that library GEMM; its roofline is int8 TOP/s against 2 x the measured dense bf16 peak.
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        int8_tops = int8_ops / (int8_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": int8_tops / int8_peak, "traffic": None,
+                    "kernel": "int8 x int8 -> int32 GEMM of the exact int8 split of the rotation (cuBLASLt, tcgen05): 8 digit planes of "
+                              "[Hx|Hx.E_j] against int8 dosages",
+                    "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json" if peaks else "2 x 1.59 PFLOP/s fallback of B200_PROFILING.md") +
+                                   " (int8 dense = 2 x bf16 dense on B200)",
+                    "launches": int(int8_launches), "ms_per_launch": int8_ms / max(1, int8_launches), "share_of_step": int8_ms / ms_total if ms_total else None,
+                    "rotation_fp64_equivalent": {"achieved": achieved, "unit": "TFLOP/s", "algorithmic_flop_per_test": alg_flop,
+                                                 "ms_per_launch": rot_ms / max(1, rot_launches), "share_of_step": rot_ms / ms_total if ms_total else None,
+                                                 "vs_fp64_tensor_peak": (achieved / FP64_TENSOR_PEAK_TFLOPS) if achieved else None,
+                                                 "note": "whole rotation (int8 conversion + digit planes + GEMM + fp64 recombination) in algorithmic fp64 flop; "
+                                                         "above the 37.1 TFLOP/s FP64 tensor peak because the work runs on the int8 tensor pipe"}}
+    else:
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": (achieved / FP64_TENSOR_PEAK_TFLOPS) if achieved else None,
+                    "traffic": ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD if default_workload and api.PROFILE.get("pre_expanded_basis") else None,
+                    "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_rotation_traffic_benchsize.csv)",
+                    "kernel": ("crm_gemm_kernel<PLAIN> on the pre-expanded basis [Hx|Hx.E_j] (rotation of [g, g.E] onto [H|y|W])"
+                               if api.PROFILE.get("pre_expanded_basis") else "crm_gemm_kernel<EXPAND> (rotation, Hadamard on the fly)"),
+                    "algorithmic_flop_per_test": alg_flop, "launches": int(rot_launches), "ms_per_launch": rot_ms / max(1, rot_launches),
+                    "share_of_step": rot_ms / ms_total if ms_total else None,
+                    "peak_source": "FP64 DMMA issue-rate peak measured on this pool (profiles/r01_dmma_probe.txt); cuBLAS DGEMM 35.4"}
+
+    # ---- the same job on the fp64 tensor-core route (hand-written DMMA kernel; what non-integer genotypes get) ----
+    fp64_route = None
+    if int8_launches > 0 and not a.no_fp64_route:
+        os.environ["CRM_ROTATION"] = "dmma"
+        try:
+            step_device()
+            api.PROFILE.update(on=True, rot_ms=0.0, rot_flops=0.0, rot_launches=0, int8_ms=0.0, int8_ops=0.0, int8_launches=0)
+            ms_f, wall_f, res_f = timed(step_device, a.steps)
+            api.PROFILE["on"] = False
+        finally:
+            del os.environ["CRM_ROTATION"]
+        ms_f = max(ms_f, wall_f * 1e3) / a.steps
+        ach_f = api.PROFILE["rot_flops"] / (api.PROFILE["rot_ms"] * 1e-3) / 1e12 if api.PROFILE["rot_ms"] > 0 else None
+        pos = (res[0] > 0) & (res_f[0] > 0)
+        fp64_route = {"value": world * p / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f,
+                      "max_abs_dlog10p_vs_int8_split": float((torch.log10(res_f[0][pos]) - torch.log10(res[0][pos])).abs().max()),
+                      "roofline": {"bound": "tensor", "achieved": ach_f, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                   "frac": (ach_f / FP64_TENSOR_PEAK_TFLOPS) if ach_f else None,
+                                   "traffic": ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD if default_workload else None,
+                                   "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_rotation_traffic_benchsize.csv)",
+                                   "kernel": "crm_gemm_kernel<PLAIN> (hand-written DMMA + TMA) on the pre-expanded basis [Hx|Hx.E_j]",
+                                   "launches": int(api.PROFILE["rot_launches"]), "ms_per_launch": api.PROFILE["rot_ms"] / max(1, api.PROFILE["rot_launches"]),
+                                   "peak_source": "FP64 DMMA issue-rate peak measured on this pool (profiles/r01_dmma_probe.txt); cuBLAS DGEMM 35.4"}}
 
     # ---- extension: donor-level genotype ingress (same job, G given as donors x SNPs + donor index) ----
     donor_level = None
@@ -383,18 +443,7 @@ def run_b200_arm(a):
                 "config": {"workload": workload_name(a), "snps_per_gpu": p, "l2": "inputs (8 GB genotypes, 0.8 GB basis) far larger than L2",
                            "step": "constructor set-up + scan of the rank's SNP shard + all-gather of results"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                             "frac": (achieved / FP64_TENSOR_PEAK_TFLOPS) if achieved else None,
-                             "traffic": (ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD if (a.cells, a.donors, a.contexts, a.hk_rank, a.snps) == (100000, 1000, 20, 50, 10000)
-                                         and api.PROFILE.get("pre_expanded_basis") else None),
-                             "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_rotation_traffic_benchsize.csv)",
-                             "kernel": ("crm_gemm_kernel<PLAIN> on the pre-expanded basis [Hx|Hx.E_j] (rotation of [g, g.E] onto [H|y|W])"
-                                        if api.PROFILE.get("pre_expanded_basis") else
-                                        "crm_gemm_kernel<EXPAND> (rotation of [g, g.E] onto [H|y|W], Hadamard on the fly)"),
-                             "algorithmic_flop_per_test": 2.0 * a.cells * a.contexts * (1 + a.hk_rank) * (1 + a.contexts),
-                             "launches": int(rot_launches), "ms_per_launch": rot_ms / max(1, rot_launches),
-                             "share_of_step": rot_ms / ms_total if ms_total else None,
-                             "peak_source": "FP64 DMMA issue-rate peak measured on this pool (profiles/r01_dmma_probe.txt); cuBLAS DGEMM 35.4"},
+                "roofline": roofline, "fp64_route": fp64_route,
                 "cpu_baseline": cpu, "donor_level_ingress": donor_level, "shared_setup": shared_setup,
                 "top_hits": top}
         print(json.dumps(line), flush=True)

@@ -94,10 +94,14 @@ struct FitProblem {
         for (int a = 0; a < P; a++) { sXy[a] = 0.0;
 #pragma unroll
             for (int b = 0; b < P; b++) sXX[a][b] = 0.0; }
+        // sum of log D_i as the log of products of four (D_i in [eps, max S]: no over/underflow), one log per four elements
+        double prod = 1.0;
+        int cnt = 0;
         for (int i = lane; i < m; i += 32) {
             const double D = fma(S[i], omd, delta);
             const double w = 1.0 / D;
-            ld += log(D);
+            prod *= D;
+            if (++cnt == 4) { ld += log(prod); prod = 1.0; cnt = 0; }
             double xv[P]; load_x(i, xv);
             const double yv = yr[i], wy = w * yv;
             syy += wy * yv;
@@ -106,6 +110,7 @@ struct FitProblem {
 #pragma unroll
                 for (int b = 0; b <= a; b++) sXX[a][b] += wx * xv[b]; }
         }
+        ld += log(prod);
         const double inv_delta = 1.0 / delta;
         const double yKy = warp_sum(syy) + yy_res * inv_delta;
         ld = warp_sum(ld) + (n - m) * log(delta);

@@ -113,32 +113,47 @@ __global__ void __launch_bounds__(256) oz_matrix_slice_kernel(const double* X, l
 
 // Gt8[s][i] = (int8) G[i][s] for a block of SNP columns (K-major), zero padded to Bp x Kp; flags[0] |= 1 when some entry is
 // not an integer in [-127, 127]; flags[1] = max |g|
-// G2t8 (may be null) receives the squares g^2 (valid when max |g| <= 11).
-__global__ void oz_genotype_kernel(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags) {
-    __shared__ double tile[OZ_TILE][OZ_TILE + 1];
-    const long long i0 = (long long)blockIdx.x * OZ_TILE;
+// G2t8 (may be null) receives the squares g^2 (valid when max |g| <= 11).  128 cells x 32 SNPs per block, char4 stores.
+__global__ void __launch_bounds__(256) oz_genotype_kernel(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp,
+                                                          long long Kp, int* flags) {
+    __shared__ double tile[OZ_ROWS][OZ_TILE + 1];
+    __shared__ int s_bad, s_max;
+    const long long i0 = (long long)blockIdx.x * OZ_ROWS;
     const long long s0 = (long long)blockIdx.y * OZ_TILE;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_bad = 0; s_max = 0; }
+    __syncthreads();
     int bad = 0, gmax = 0;
-    for (int r = threadIdx.y; r < OZ_TILE; r += blockDim.y) {
-        const long long i = i0 + r, s = s0 + threadIdx.x;
+    for (int r = ty; r < OZ_ROWS; r += 8) {
+        const long long i = i0 + r, s = s0 + tx;
         double v = 0.0;
         if (i < n && s < B) {
             v = G[i * ldg + s];
             if (!(v == rint(v)) || fabs(v) > 127.0) bad = 1; else gmax = max(gmax, (int)fabs(v));
         }
-        tile[r][threadIdx.x] = v;
+        tile[r][tx] = v;
     }
+    bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if (tx == 0) { if (bad) atomicOr(&s_bad, 1); atomicMax(&s_max, gmax); }
     __syncthreads();
-    for (int r = threadIdx.y; r < OZ_TILE; r += blockDim.y) {
-        const long long s = s0 + r, i = i0 + threadIdx.x;
+    for (int r = ty; r < OZ_TILE; r += 8) {
+        const long long s = s0 + r, i = i0 + 4 * tx;
         if (s < Bp && i < Kp) {
-            const int gv = (int)tile[threadIdx.x][r];
-            Gt8[s * Kp + i] = (int8_t)gv;
-            if (G2t8) G2t8[s * Kp + i] = (int8_t)(gv * gv);
+            char4 q, q2;
+            signed char* a = reinterpret_cast<signed char*>(&q);
+            signed char* b = reinterpret_cast<signed char*>(&q2);
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int gv = (int)tile[4 * tx + u][r]; a[u] = (signed char)gv; b[u] = (signed char)(gv * gv); }
+            *reinterpret_cast<char4*>(Gt8 + s * Kp + i) = q;
+            if (G2t8) *reinterpret_cast<char4*>(G2t8 + s * Kp + i) = q2;
         }
     }
-    if (bad) atomicOr(&flags[0], 1);
-    if (gmax) atomicMax(&flags[1], gmax);
+    if (threadIdx.x == 0) {      // one (conditional) atomic per block
+        if (s_bad) atomicOr(&flags[0], 1);
+        if (s_max > *reinterpret_cast<volatile int*>(&flags[1])) atomicMax(&flags[1], s_max);
+    }
 }
 
 // C[s][col] = 2^(e_col + 1) sum_t 2^(-7 (t + 1)) D[t * Mp + col][s]   (D int32, row stride ldd; C fp64, row stride ldc)

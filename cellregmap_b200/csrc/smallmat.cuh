@@ -22,13 +22,14 @@ __device__ __forceinline__ void jacobi_eig(double (&A)[P][P], double (&V)[P][P])
 #pragma unroll
             for (int j = i + 1; j < P; j++) off += A[i][j] * A[i][j];
         }
-        if (off <= 1e-34 * diag || off == 0.0) break;
+        if (off <= 1e-30 * diag || off == 0.0) break;      // |off| <= 1e-15 |diag|: below the round-off of the rotations
 #pragma unroll
         for (int p = 0; p < P - 1; p++) {
 #pragma unroll
             for (int q = p + 1; q < P; q++) {
                 const double apq = A[p][q];
                 if (apq == 0.0) continue;
+                if (fabs(apq) <= 1e-17 * sqrt(fabs(A[p][p] * A[q][q]))) { A[p][q] = 0.0; A[q][p] = 0.0; continue; }   // negligible coupling
                 const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
@@ -141,12 +142,13 @@ __device__ inline void warp_jacobi_vec(double* A, double* V, int n, int lane) {
         double off = 0.0, dg = 0.0;
         for (int e = lane; e < n * n; e += 32) { const double v = A[e]; if (e / n == e % n) dg += v * v; else off += v * v; }
         off = warp_sum(off); dg = warp_sum(dg);
-        if (off <= 1e-34 * dg || off == 0.0) break;
+        if (off <= 1e-30 * dg || off == 0.0) break;
         for (int p = 0; p < n - 1; p++)
             for (int q = p + 1; q < n; q++) {
                 const double apq = A[p * n + q];
                 if (apq == 0.0) continue;
                 const double app = A[p * n + p], aqq = A[q * n + q];
+                if (fabs(apq) <= 1e-17 * sqrt(fabs(app * aqq))) { __syncwarp(); if (lane == 0) { A[p * n + q] = 0.0; A[q * n + p] = 0.0; } __syncwarp(); continue; }
                 const double theta = (aqq - app) / (2.0 * apq);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;

@@ -1,14 +1,16 @@
 #!/bin/bash
-# Does the one-time initialisation of cusolverDnXsyevBatched persist across processes on one box (JIT cache)?
+# First-call cost of cusolverDnXsyevBatched (CRM_EIG_BATCHED=1) at the bench shapes, in two consecutive processes.
 for i in 1 2; do
   echo "process $i"; CRM_EIG_BATCHED=1 python - <<'PY'
 import time, sys, numpy as np, torch
 sys.path.insert(0, ".")
-from cellregmap_b200.synth import make_data
+import bench
 from cellregmap_b200._cellregmap import _make_interaction_model
-d = make_data(n=3000, donors=100, k=20, p=8, q=50, seed=1)
+a = bench.parse_args()
+gene = bench.make_gene(a)
+dev = torch.device("cuda", 0)
+y, W, E, hK = (torch.from_numpy(gene[k]).to(dev) for k in ("y", "W", "E", "hK"))
 for it in range(3):
-    t0 = time.time(); m = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK); torch.cuda.synchronize(); print("setup %d: %.1f ms" % (it, 1e3 * (time.time() - t0)))
+    torch.cuda.synchronize(); t0 = time.time(); m = _make_interaction_model(y, E, W, None, None, hK, device=dev); torch.cuda.synchronize(); print("setup %d: %.1f ms" % (it, 1e3 * (time.time() - t0)), flush=True)
 PY
 done
-ls -la ~/.nv/ComputeCache 2>/dev/null | head -3
