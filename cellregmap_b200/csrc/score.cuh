@@ -226,38 +226,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) crm_score_kernel(const ScoreArg
     double qs = 0.0;
     for (int j = lane; j < k; j += 32) qs += tv[j] * tv[j];
     qs = 0.5 * warp_sum(qs);
-    for (int sweep = 0; sweep < 40; sweep++) {
-        double off = 0.0, dg = 0.0;
-        for (int e = lane; e < k * k; e += 32) { const int j = e / k, l = e - j * k; const double v = Mm[e]; if (j == l) dg += v * v; else off += v * v; }
-        off = warp_sum(off); dg = warp_sum(dg);
-        if (off <= 1e-30 * dg || off == 0.0) break;      // |off| <= 1e-15 |diag|: below the round-off of the rotations
-        for (int pp = 0; pp < k - 1; pp++) {
-            for (int qq = pp + 1; qq < k; qq++) {
-                const double apq = Mm[pp * k + qq];
-                if (apq == 0.0) continue;
-                const double app = Mm[pp * k + pp], aqq = Mm[qq * k + qq];
-                if (fabs(apq) <= 1e-17 * sqrt(fabs(app * aqq))) { __syncwarp(); if (lane == 0) { Mm[pp * k + qq] = 0.0; Mm[qq * k + pp] = 0.0; } __syncwarp(); continue; }
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double cc = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cc;
-                __syncwarp();
-                for (int r = lane; r < k; r += 32) {
-                    if (r != pp && r != qq) {
-                        const double arp = Mm[r * k + pp], arq = Mm[r * k + qq];
-                        const double nrp = cc * arp - sn * arq, nrq = sn * arp + cc * arq;
-                        Mm[r * k + pp] = nrp; Mm[pp * k + r] = nrp;
-                        Mm[r * k + qq] = nrq; Mm[qq * k + r] = nrq;
-                    }
-                }
-                if (lane == 0) {
-                    Mm[pp * k + pp] = app - tt * apq; Mm[qq * k + qq] = aqq + tt * apq;
-                    Mm[pp * k + qq] = 0.0; Mm[qq * k + pp] = 0.0;
-                }
-                __syncwarp();
-            }
-        }
-    }
-    __syncwarp();
+    warp_jacobi_vec(Mm, nullptr, k, lane);      // eigenvalues of M on its diagonal
     // descending rank sort of the diagonal into tv[], then the chiscore filter: lambda > mean(lambda >= 0) / 1e5
     for (int j = lane; j < k; j += 32) {
         const double lj = Mm[j * k + j];

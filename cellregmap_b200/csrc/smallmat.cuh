@@ -134,37 +134,66 @@ __device__ inline void warp_backward_solve(const double* L, int n, int ld, doubl
         }
     __syncwarp();
 }
-// cyclic Jacobi with eigenvectors on a symmetric n x n shared matrix (eigenvalues end on the diagonal, V columns)
+// Jacobi eigendecomposition of a symmetric n x n matrix in shared memory by one warp (n <= 64), parallel (round-robin
+// tournament) ordering: each round rotates n/2 disjoint index pairs at once -- lane i computes the rotation of pair i, then all
+// lanes apply the n/2 rotations to the columns (one row per lane) and to the rows (one column per lane).  Eigenvalues end on
+// the diagonal; V (may be null) receives the eigenvectors in its columns.
 __device__ inline void warp_jacobi_vec(double* A, double* V, int n, int lane) {
-    for (int e = lane; e < n * n; e += 32) V[e] = (e / n == e % n) ? 1.0 : 0.0;
+    if (V) for (int e = lane; e < n * n; e += 32) V[e] = (e / n == e % n) ? 1.0 : 0.0;
     __syncwarp();
+    if (n < 2) return;
+    const int ne = n + (n & 1);            // even number of players; index n (if present) is a bye
+    const int npairs = ne / 2;             // <= 32
     for (int sweep = 0; sweep < 40; sweep++) {
         double off = 0.0, dg = 0.0;
         for (int e = lane; e < n * n; e += 32) { const double v = A[e]; if (e / n == e % n) dg += v * v; else off += v * v; }
         off = warp_sum(off); dg = warp_sum(dg);
-        if (off <= 1e-30 * dg || off == 0.0) break;
-        for (int p = 0; p < n - 1; p++)
-            for (int q = p + 1; q < n; q++) {
-                const double apq = A[p * n + q];
-                if (apq == 0.0) continue;
-                const double app = A[p * n + p], aqq = A[q * n + q];
-                if (fabs(apq) <= 1e-17 * sqrt(fabs(app * aqq))) { __syncwarp(); if (lane == 0) { A[p * n + q] = 0.0; A[q * n + p] = 0.0; } __syncwarp(); continue; }
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-                __syncwarp();
-                for (int r = lane; r < n; r += 32) {
-                    if (r != p && r != q) {
-                        const double arp = A[r * n + p], arq = A[r * n + q];
-                        const double nrp = c * arp - s * arq, nrq = s * arp + c * arq;
-                        A[r * n + p] = nrp; A[p * n + r] = nrp; A[r * n + q] = nrq; A[q * n + r] = nrq;
+        if (off <= 1e-30 * dg || off == 0.0) break;      // |off| <= 1e-15 |diag|: below the round-off of the rotations
+        for (int rd = 0; rd < ne - 1; rd++) {
+            // pair of this lane in round rd (circle method: player ne-1 fixed, the others rotate)
+            int p = -1, q = -1;
+            double c = 1.0, sn = 0.0;
+            if (lane < npairs) {
+                int a0 = (lane == 0) ? ne - 1 : (rd + lane) % (ne - 1);
+                int b0 = (lane == 0) ? rd % (ne - 1) : (rd - lane + ne - 1) % (ne - 1);
+                if (a0 > b0) { const int t = a0; a0 = b0; b0 = t; }
+                if (b0 < n) {
+                    const double apq = A[a0 * n + b0], app = A[a0 * n + a0], aqq = A[b0 * n + b0];
+                    if (apq != 0.0 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(tt * tt + 1.0); sn = tt * c;
+                        p = a0; q = b0;
                     }
-                    const double vrp = V[r * n + p], vrq = V[r * n + q];
-                    V[r * n + p] = c * vrp - s * vrq; V[r * n + q] = s * vrp + c * vrq;
                 }
-                if (lane == 0) { A[p * n + p] = app - tt * apq; A[q * n + q] = aqq + tt * apq; A[p * n + q] = 0.0; A[q * n + p] = 0.0; }
-                __syncwarp();
             }
+            __syncwarp();
+            // columns: A <- A J (and V <- V J), one row per lane
+            for (int i = 0; i < npairs; i++) {
+                const int pp = __shfl_sync(0xffffffffu, p, i), qq = __shfl_sync(0xffffffffu, q, i);
+                const double cc = __shfl_sync(0xffffffffu, c, i), ss = __shfl_sync(0xffffffffu, sn, i);
+                if (pp < 0) continue;
+                for (int r = lane; r < n; r += 32) {
+                    const double arp = A[r * n + pp], arq = A[r * n + qq];
+                    A[r * n + pp] = cc * arp - ss * arq; A[r * n + qq] = ss * arp + cc * arq;
+                    if (V) { const double vrp = V[r * n + pp], vrq = V[r * n + qq]; V[r * n + pp] = cc * vrp - ss * vrq; V[r * n + qq] = ss * vrp + cc * vrq; }
+                }
+            }
+            __syncwarp();
+            // rows: A <- J' A, one column per lane
+            for (int i = 0; i < npairs; i++) {
+                const int pp = __shfl_sync(0xffffffffu, p, i), qq = __shfl_sync(0xffffffffu, q, i);
+                const double cc = __shfl_sync(0xffffffffu, c, i), ss = __shfl_sync(0xffffffffu, sn, i);
+                if (pp < 0) continue;
+                for (int col = lane; col < n; col += 32) {
+                    const double apc = A[pp * n + col], aqc = A[qq * n + col];
+                    A[pp * n + col] = cc * apc - ss * aqc; A[qq * n + col] = ss * apc + cc * aqc;
+                }
+            }
+            __syncwarp();
+            if (lane < npairs && p >= 0) { A[p * n + q] = 0.0; A[q * n + p] = 0.0; }     // annihilated exactly
+            __syncwarp();
+        }
     }
     __syncwarp();
 }
