@@ -1,4 +1,4 @@
-"""Per-iteration wall times of the two phases of a bench step (model construction = set-up, scan)."""
+"""Per-iteration wall times of a bench step: model construction (set-up), scan, release; then the un-synchronised loop."""
 import json, sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
@@ -13,10 +13,17 @@ rows = []
 for it in range(5):
     torch.cuda.synchronize(); t0 = time.time()
     model = api._make_interaction_model(y, E, W, None, None, hK, device=dev)
-    torch.cuda.synchronize(); t1 = time.time()
+    t1h = time.time(); torch.cuda.synchronize(); t1 = time.time()
     out = model._scan_interaction_device(G)
-    torch.cuda.synchronize(); t2 = time.time()
+    t2h = time.time(); torch.cuda.synchronize(); t2 = time.time()
     del model, out
     torch.cuda.synchronize(); t3 = time.time()
-    rows.append({"setup_ms": (t1 - t0) * 1e3, "scan_ms": (t2 - t1) * 1e3, "free_ms": (t3 - t2) * 1e3})
+    rows.append({"setup_ms": (t1 - t0) * 1e3, "setup_host_ms": (t1h - t0) * 1e3, "scan_ms": (t2 - t1) * 1e3, "scan_host_ms": (t2h - t1) * 1e3, "free_ms": (t3 - t2) * 1e3})
 print(json.dumps(rows))
+def step():
+    model = api._make_interaction_model(y, E, W, None, None, hK, device=dev)
+    out = model._scan_interaction_device(G)
+    return torch.stack([out["pv"], out["rho1"]])
+step(); torch.cuda.synchronize(); t0 = time.time()
+for _ in range(5): r = step()
+torch.cuda.synchronize(); print("loop ms/step", (time.time() - t0) * 1e3 / 5)
