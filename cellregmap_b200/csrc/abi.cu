@@ -384,6 +384,20 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
 // per rotation call (one elementwise pass per group, negligible against the contraction).  Without it (CRM_NO_HXE=1) the
 // factor is applied to the genotype fragments on the fly (EXPAND mode, ~90% of peak, no extra memory).
 // Rotation through the exact int8 split (ozaki.cuh): *used = 1 when the block was integer-valued and the route was taken.
+// CRM_INT8_GEMM=lt routes the int8 contraction through cuBLASLt + oz_combine_kernel instead of the fused tcgen05 kernel
+static bool int8_route_library() {
+    static const bool lt = [] { const char* v = getenv("CRM_INT8_GEMM"); return v && !strcmp(v, "lt"); }();
+    return lt;
+}
+// C[s][col] (ldc) = recombined int8 contraction of the digit planes P8 [8][Mp][Kp] against Gt8 [Bp][Kp]
+static int int8_split_contract(Handle* h, const int8_t* P8, long long Mp, long long Mtot, const int* expo, const int8_t* Gt8, long long Bp, long long B,
+                               long long Kp, double* C, long long ldc, cudaStream_t st) {
+    if (!int8_route_library()) return oz_launch_mma(P8, Mp, Mtot, expo, Gt8, Bp, B, Kp, C, ldc, st);
+    CRM_CHECK(h->D32.reserve((size_t)OZAKI_SLICES * Mp * Bp * sizeof(int)));
+    CRM_CHECK(oz_int8_gemm(P8, (long long)OZAKI_SLICES * Mp, Gt8, Bp, Kp, h->D32.as<int>(), Bp, st));
+    return oz_launch_combine(h->D32.as<int>(), Mp, Bp, expo, Mtot, B, C, ldc, st);
+}
+
 static int rotation_int8_split(Handle* h, const double* G, long long ldg, long long B, double* C, cudaStream_t st, int* used) {
     *used = 0;
     const long long n = h->n, Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
@@ -394,7 +408,7 @@ static int rotation_int8_split(Handle* h, const double* G, long long ldg, long l
         cudaMemPool_t mp_; unsigned long long reserved = 0, usedb = 0;
         if (cudaDeviceGetDefaultMemPool(&mp_, h->device) == cudaSuccess && cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
             cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrUsedMemCurrent, &usedb) == cudaSuccess && reserved > usedb) free_b += (size_t)(reserved - usedb);
-        if (h->A8.cap < a8_bytes && (double)a8_bytes + (double)OZAKI_SLICES * Mp * Bp * 4.0 > 0.5 * (double)free_b) return CRM_OK;
+        if (h->A8.cap < a8_bytes && (double)a8_bytes + (int8_route_library() ? (double)OZAKI_SLICES * Mp * Bp * 4.0 : 0.0) > 0.5 * (double)free_b) return CRM_OK;
     }
     PhaseTrace tr(st);
     h->oz_block_valid = false;
@@ -416,7 +430,6 @@ static int rotation_int8_split(Handle* h, const double* G, long long ldg, long l
         h->oz_built = true;
         tr.mark("digit planes");
     }
-    CRM_CHECK(h->D32.reserve((size_t)OZAKI_SLICES * Mp * Bp * sizeof(int)));
     if (h->prof_on) {
         cudaEvent_t e0, e1;
         CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
@@ -424,11 +437,9 @@ static int rotation_int8_split(Handle* h, const double* G, long long ldg, long l
         h->prof_oz_events.push_back(e0); h->prof_oz_events.push_back(e1);
         h->prof_oz_gemm_ops += 2.0 * (double)OZAKI_SLICES * (double)Mp * (double)Kp * (double)Bp;
     }
-    CRM_CHECK(oz_int8_gemm(h->A8.as<int8_t>(), (long long)OZAKI_SLICES * Mp, h->Gt8.as<int8_t>(), Bp, Kp, h->D32.as<int>(), Bp, st));
+    CRM_CHECK(int8_split_contract(h, h->A8.as<int8_t>(), Mp, Mtot, h->a8expo.as<int>(), h->Gt8.as<int8_t>(), Bp, B, Kp, C, Mtot, st));
     if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_oz_events.back(), st));
-    tr.mark("int8 gemm");
-    CRM_CHECK(oz_launch_combine(h->D32.as<int>(), Mp, Bp, h->a8expo.as<int>(), Mtot, B, C, Mtot, st));
-    tr.mark("combine");
+    tr.mark("int8 contraction");
     tr.report("int8 rotation");
     h->oz_block_valid = true;
     h->oz_block_gmax = flags[1];
@@ -843,9 +854,7 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
             CRM_CHECK(oz_launch_matrix_planes(h->A2.as<double>(), h->ld2, h->M2, n, h->a28expo.as<int>(), h->A28.as<int8_t>(), M2p, Kp, st));
             h->oz_built_a2 = true;
         }
-        CRM_CHECK(h->D32.reserve((size_t)OZAKI_SLICES * M2p * Bp * sizeof(int)));
-        CRM_CHECK(oz_int8_gemm(h->A28.as<int8_t>(), (long long)OZAKI_SLICES * M2p, h->G2t8.as<int8_t>(), Bp, Kp, h->D32.as<int>(), Bp, st));
-        CRM_CHECK(oz_launch_combine(h->D32.as<int>(), M2p, Bp, h->a28expo.as<int>(), h->M2, B, sq, h->ld2, st));
+        CRM_CHECK(int8_split_contract(h, h->A28.as<int8_t>(), M2p, h->M2, h->a28expo.as<int>(), h->G2t8.as<int8_t>(), Bp, B, Kp, sq, h->ld2, st));
     } else {
         GemmOperands op{};
         op.A = h->gs->A2; op.lda = h->gs->ld2; op.a_cols = h->M2;
@@ -1333,6 +1342,45 @@ int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const doubl
     op.A = A; op.lda = lda; op.a_cols = a_cols; op.B = B; op.ldb = ldb; op.b_cols = b_cols;
     op.B2 = B2 ? B2 : B; op.ldb2 = B2 ? ldb2 : ldb; op.b2_cols = B2 ? b2_cols : b_cols;
     return launch_gemm(mode, op, (int)K, m_begin, m_count, (int)n_begin, (int)n_count, out, ldc, kexp, (cudaStream_t)stream);
+}
+
+int crm_int8_split_gemm(const double* X, int64_t ldx, int64_t cols, const double* G, int64_t ldg, int64_t B, int64_t n, int route, double* C, int64_t ldc,
+                        int32_t* flags2, float* contraction_ms, void* stream) {
+    if (!X || !G || !C || !flags2 || cols <= 0 || B <= 0 || n <= 0 || ldx < cols || ldg < B || ldc < cols || route < 0 || route > 1) { set_error("crm_int8_split_gemm: bad arguments"); return CRM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long Mp = round_up(cols, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
+    DevBuf P8, expo, Gt8, flags, D32;
+    CRM_CHECK(P8.reserve((size_t)OZAKI_SLICES * Mp * Kp)); CRM_CHECK(expo.reserve((size_t)cols * 4)); CRM_CHECK(Gt8.reserve((size_t)Bp * Kp)); CRM_CHECK(flags.reserve(64));
+    CRM_CUDA(cudaMemsetAsync(P8.ptr, 0, (size_t)OZAKI_SLICES * Mp * Kp, st));
+    CRM_CHECK(oz_launch_matrix_planes(X, ldx, (int)cols, n, expo.as<int>(), P8.as<int8_t>(), Mp, Kp, st));
+    CRM_CHECK(oz_launch_genotypes(G, ldg, n, B, Gt8.as<int8_t>(), nullptr, Bp, Kp, flags.as<int>(), st));
+    CRM_CUDA(cudaMemcpyAsync(flags2, flags.ptr, 8, cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaStreamSynchronize(st));
+    int status = CRM_OK;
+    if (flags2[0] == 0 && (double)Kp * 64.0 * (double)std::max(flags2[1], 1) < 2147483648.0) {
+        cudaEvent_t e0, e1;
+        CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
+        CRM_CUDA(cudaEventRecord(e0, st));
+        if (route == 0) status = oz_launch_mma(P8.as<int8_t>(), Mp, cols, expo.as<int>(), Gt8.as<int8_t>(), Bp, B, Kp, C, ldc, st);
+        else {
+            status = D32.reserve((size_t)OZAKI_SLICES * Mp * Bp * sizeof(int));
+            if (status == CRM_OK) status = oz_int8_gemm(P8.as<int8_t>(), (long long)OZAKI_SLICES * Mp, Gt8.as<int8_t>(), Bp, Kp, D32.as<int>(), Bp, st);
+            if (status == CRM_OK) status = oz_launch_combine(D32.as<int>(), Mp, Bp, expo.as<int>(), cols, B, C, ldc, st);
+        }
+        cudaEventRecord(e1, st);
+        cudaError_t ce = cudaStreamSynchronize(st);
+        float ms = 0.f;
+        if (ce == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+        if (contraction_ms) *contraction_ms = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (status == CRM_OK && ce != cudaSuccess) { set_error("crm_int8_split_gemm: %s", cudaGetErrorString(ce)); status = CRM_ERR_CUDA; }
+    } else {
+        set_error("crm_int8_split_gemm: G is not integer-valued in [-127, 127] or the int32 accumulation could overflow");
+        status = CRM_ERR_UNSUPPORTED;
+    }
+    cudaStreamSynchronize(st);
+    P8.release(); expo.release(); Gt8.release(); flags.release(); D32.release();
+    return status;
 }
 
 int crm_lmm_fit_rotated(const double* S, const double* yr, const double* Wr, const double* gr, const double* gy, const double* gW,

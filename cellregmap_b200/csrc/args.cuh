@@ -91,4 +91,8 @@ struct BetaArgs {
 };
 constexpr int BETA_MAX_NZ = 67;
 
+// exact int8 split (ozaki.cuh, oz_mma.cuh)
+constexpr int OZ_SLICES = 8;               // signed 7-bit digit planes per column
+constexpr int OZ_EXP_EMPTY = -100000;      // exponent marker of an all-zero column
+
 }  // namespace crm

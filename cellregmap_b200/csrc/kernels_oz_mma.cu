@@ -1,0 +1,60 @@
+// Translation unit: tcgen05 int8 contraction with fused fp64 recombination (oz_mma.cuh) -- tensor maps + launch.
+#include <algorithm>
+
+#include "launch.cuh"
+#include "oz_mma.cuh"
+
+namespace crm {
+
+typedef CUresult (*PFN_encodeTiledU8)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// K-major int8 matrix (rows x Kp bytes, row stride Kp) -> tensor map with boxes of 128 bytes of K x box_rows rows, 128-byte
+// swizzle, out-of-range rows / K bytes read as zero
+static int make_map_k_major(CUtensorMap* map, const int8_t* ptr, long long rows, long long Kp, int box_rows) {
+    static PFN_encodeTiledU8 enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) { set_error("cuTensorMapEncodeTiled entry point not available"); return CRM_ERR_CUDA; }
+        enc = reinterpret_cast<PFN_encodeTiledU8>(p);
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (Kp & 15) || box_rows > 256) { set_error("int8 TMA operand must be 16-byte aligned with a row stride that is a multiple of 16 (ptr=%p Kp=%lld)", (const void*)ptr, Kp); return CRM_ERR_INVALID; }
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp};
+    cuuint32_t box[2] = {(cuuint32_t)OZM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (int8, rows=%lld Kp=%lld box=%d) failed with CUresult %d", rows, Kp, box_rows, (int)r); return CRM_ERR_CUDA; }
+    return CRM_OK;
+}
+
+int oz_launch_mma(const int8_t* A8, long long Mp, long long Mtot, const int* expo, const int8_t* Gt8, long long Bp, long long B, long long Kp, double* C,
+                  long long ldc, cudaStream_t st) {
+    if (B <= 0 || Mtot <= 0) return CRM_OK;
+    if ((long long)OZ_SLICES * Mp > 2000000000LL || Kp > 2000000000LL) { set_error("int8 contraction: operand too large for 32-bit TMA coordinates"); return CRM_ERR_UNSUPPORTED; }
+    CUtensorMap tmA, tmB;
+    CRM_CHECK(make_map_k_major(&tmA, A8, (long long)OZ_SLICES * Mp, Kp, OZM_BM));
+    CRM_CHECK(make_map_k_major(&tmB, Gt8, Bp, Kp, OZM_BN));
+    OzMmaArgs a{};
+    a.Mp = Mp; a.Mtot = Mtot; a.B = B; a.ldc = ldc;
+    a.kblocks = (int)((Kp + OZM_BK - 1) / OZM_BK);
+    a.m_tiles = (int)((Mtot + OZM_BM - 1) / OZM_BM);
+    a.n_tiles = (int)((B + OZM_BN - 1) / OZM_BN);
+    a.expo = expo; a.C = C;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        CRM_CUDA(cudaGetDevice(&dev));
+        CRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CRM_CUDA(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZM_SMEM_BYTES));
+    }
+    const long long units = (long long)a.m_tiles * a.n_tiles;
+    const unsigned grid = (unsigned)std::min<long long>(units, sms);
+    oz_mma_kernel<<<grid, OZM_THREADS, OZM_SMEM_BYTES, st>>>(tmA, tmB, a);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
+}  // namespace crm

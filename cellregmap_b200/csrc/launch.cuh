@@ -49,6 +49,9 @@ int oz_launch_slices(const double* Hx, int ldH, const double* Eext, int epitch, 
 int oz_launch_genotypes(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st);
 int oz_launch_matrix_planes(const double* X, long long ldx, int cols, long long n, int* expo, int8_t* P8, long long Mp, long long Kp, cudaStream_t st);
 int oz_launch_combine(const int* D, long long Mp, long long ldd, const int* expo, long long Mtot, long long B, double* C, long long ldc, cudaStream_t st);
+// the same contraction + recombination in one hand-written tcgen05 kernel (oz_mma.cuh): C[s][col], bit-identical
+int oz_launch_mma(const int8_t* A8, long long Mp, long long Mtot, const int* expo, const int8_t* Gt8, long long Bp, long long B, long long Kp, double* C,
+                  long long ldc, cudaStream_t st);
 int oz_int8_gemm(const int8_t* A8, long long Mrows, const int8_t* Gt8, long long Bp, long long Kp, int* D, long long ldd, cudaStream_t st);
 
 }  // namespace crm

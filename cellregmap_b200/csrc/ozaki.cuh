@@ -10,13 +10,12 @@
 // one fp64 sum of eight terms, like the DMMA route carries the rounding of its fp64 accumulation.
 #pragma once
 #include "common.cuh"
+#include "args.cuh"
 
 namespace crm {
 
-constexpr int OZ_SLICES = 8;
 constexpr int OZ_TILE = 32;
 
-constexpr int OZ_EXP_EMPTY = -100000;      // exponent marker of an all-zero column
 
 // exponent e with |x| < 2^e for the largest |x| of each column of HxE = Eext[:, j] * Hx[:, a]  (col = j * ldH + a);
 // expo must be pre-filled with OZ_EXP_EMPTY; rows are split over blockIdx.z and merged with atomicMax

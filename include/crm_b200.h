@@ -136,6 +136,14 @@ CRM_API int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, con
              const double* B2, int64_t ldb2, int64_t b2_cols, int64_t K, int m_begin, int m_count, int64_t n_begin,
              int64_t n_count, double* out, int64_t ldc, int kexp, void* stream);
 
+/* K0 on caller-supplied operands: C[B][cols] (ldc) = G' X by the exact int8 split -- 8 digit planes of the real matrix X [n][cols]
+ * (ldx) against the integer-valued matrix G [n][B] (ldg); replaces the same `Q0.T @` products as crm_gemm (cellregmap/_math.py:72-73)
+ * when the genotypes are integer dosages.  route 0: hand-written tcgen05 kernel with fused fp64 recombination; 1: cuBLASLt int8 GEMM +
+ * recombination kernel (bit-identical).  flags2 (host) = {G not integer in [-127,127], max |g|}; contraction_ms (host, optional) =
+ * CUDA-event time of the contraction alone.  Synchronises the stream. */
+CRM_API int crm_int8_split_gemm(const double* X, int64_t ldx, int64_t cols, const double* G, int64_t ldg, int64_t B, int64_t n, int route,
+                        double* C, int64_t ldc, int32_t* flags2, float* contraction_ms, void* stream);
+
 /* K2 on caller-supplied rotated statistics: replaces glimix_core LMM(y, X, QS, restricted).fit() for p x R problems.
  * S, yr [R][mp]; Wr [R][c][mp]; gr [p][R*mp] (NULL: design is W only, p must be 1); gy [p], gW [p][c], gg [p];
  * stats = [y'y, W'y (c), W'W (c*c)].  Outputs [p][R] (beta [p][R][c + has_g]). */

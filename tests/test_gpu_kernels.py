@@ -31,6 +31,40 @@ def _gemm(mode, A, B, B2, m_begin, m_count, n_begin, n_count, kexp, dev):
     return o[:, :m_count]
 
 
+def _int8_split(X, G, route, dev):
+    import torch
+    from cellregmap_b200 import _lib
+    Xt, Gt = _t(X, dev), _t(G, dev)
+    cols, B = X.shape[1], G.shape[1]
+    out = torch.full((B, cols + 3), -7.0, dtype=torch.float64, device=dev)
+    flags = (ctypes.c_int32 * 2)()
+    ms = ctypes.c_float(0.0)
+    _lib.call("crm_int8_split_gemm", _p(Xt), cols, cols, _p(Gt), B, B, X.shape[0], route, _p(out), cols + 3, flags, ctypes.byref(ms), ctypes.c_void_p(0))
+    o = out.cpu().numpy()
+    assert np.all(o[:, cols:] == -7.0)
+    return o[:, :cols], (flags[0], flags[1]), ms.value
+
+
+@pytest.mark.parametrize("n,cols,B", [(16, 8, 5), (1000, 130, 37), (4099, 300, 260), (20000, 129, 515), (700, 1200, 3)])
+def test_int8_split_contraction(cuda_device, n, cols, B):
+    """K0: the fused tcgen05 kernel equals the cuBLASLt + recombination route bit for bit, and both equal the exact
+    contraction (integer-valued X: every product and sum is exactly representable)."""
+    rng = np.random.default_rng(n + cols)
+    G = rng.integers(0, 3, size=(n, B)).astype(np.float64)
+    X = rng.standard_normal((n, cols)) * np.exp(rng.uniform(-8, 8, size=cols))
+    X[:, min(3, cols - 1)] = 0.0                              # an all-zero column (empty exponent)
+    c_mma, f0, _ = _int8_split(X, G, 0, cuda_device)
+    c_lt, f1, _ = _int8_split(X, G, 1, cuda_device)
+    assert f0 == f1 == (0, 2)
+    assert np.array_equal(c_mma, c_lt)
+    ref = G.T @ X
+    scale = np.abs(G).T @ np.abs(X) + 1e-300
+    assert np.max(np.abs(c_mma - ref) / scale) < 1e-14
+    Xi = np.round(rng.standard_normal((n, cols)) * 1000.0)   # integers: exact result
+    c_i, _, _ = _int8_split(Xi, G, 0, cuda_device)
+    assert np.array_equal(c_i, G.T @ Xi)
+
+
 @pytest.mark.parametrize("K,M,N", [(1, 2, 2), (37, 130, 6), (1000, 222, 300), (4099, 64, 129)])
 def test_gemm_plain(cuda_device, K, M, N):
     rng = np.random.default_rng(K + M + N)
