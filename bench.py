@@ -303,9 +303,9 @@ def run_b200_arm(a):
     alg_flop = 2.0 * a.cells * a.contexts * (1 + a.hk_rank) * (1 + a.contexts)
     default_workload = (a.cells, a.donors, a.contexts, a.hk_rank, a.snps) == (100000, 1000, 20, 50, 10000)
     if int8_launches > 0:
-        # Integer dosages: the rotation ran as the exact int8 split (hand-written slicing / conversion / recombination
-        # kernels around one plain int8 tensor-core GEMM served by cuBLASLt's tcgen05 kernels).  The dominant kernel of the
-        # step is that library GEMM; its roofline is int8 TOP/s against 2 x the measured dense bf16 peak.
+        # Integer dosages: the rotation ran as the exact int8 split.  Its dominant kernel is oz_mma_kernel (hand-written
+        # tcgen05.mma kind::i8 + TMA + TMEM, fp64 recombination of the digit planes fused into the epilogue); its roofline is
+        # int8 TOP/s against 2 x the measured dense bf16 peak.  CRM_INT8_GEMM=lt swaps in cuBLASLt + a recombination kernel.
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -314,8 +314,9 @@ def run_b200_arm(a):
         int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
         int8_tops = int8_ops / (int8_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": int8_tops / int8_peak, "traffic": None,
-                    "kernel": "int8 x int8 -> int32 GEMM of the exact int8 split of the rotation (cuBLASLt, tcgen05): 8 digit planes of "
-                              "[Hx|Hx.E_j] against int8 dosages",
+                    "kernel": ("cuBLASLt int8 GEMM + oz_combine_kernel" if os.environ.get("CRM_INT8_GEMM") == "lt" else
+                               "oz_mma_kernel (hand-written tcgen05.mma kind::i8 + TMA, TMEM accumulators, fused fp64 recombination)") +
+                              ": 8 digit planes of [Hx|Hx.E_j] against int8 dosages, the exact int8 split of the rotation",
                     "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json" if peaks else "2 x 1.59 PFLOP/s fallback of B200_PROFILING.md") +
                                    " (int8 dense = 2 x bf16 dense on B200)",
                     "launches": int(int8_launches), "ms_per_launch": int8_ms / max(1, int8_launches), "share_of_step": int8_ms / ms_total if ms_total else None,

@@ -402,13 +402,18 @@ static int rotation_int8_split(Handle* h, const double* G, long long ldg, long l
     *used = 0;
     const long long n = h->n, Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
     const size_t a8_bytes = (size_t)OZAKI_SLICES * Mp * Kp;
-    if (!h->oz_built) {      // room for the digit planes?
-        size_t free_b = 0, total_b = 0;
-        CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        cudaMemPool_t mp_; unsigned long long reserved = 0, usedb = 0;
-        if (cudaDeviceGetDefaultMemPool(&mp_, h->device) == cudaSuccess && cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-            cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrUsedMemCurrent, &usedb) == cudaSuccess && reserved > usedb) free_b += (size_t)(reserved - usedb);
-        if (h->A8.cap < a8_bytes && (double)a8_bytes + (int8_route_library() ? (double)OZAKI_SLICES * Mp * Bp * 4.0 : 0.0) > 0.5 * (double)free_b) return CRM_OK;
+    if (!h->oz_built && h->A8.cap < a8_bytes) {      // room for the digit planes?  (cudaMemGetInfo costs milliseconds: only asked for large requests)
+        static size_t total_mem[16] = {0};
+        if (!total_mem[h->device]) { size_t f = 0; CRM_CUDA(cudaMemGetInfo(&f, &total_mem[h->device])); }
+        const double need = (double)a8_bytes + (int8_route_library() ? (double)OZAKI_SLICES * Mp * Bp * 4.0 : 0.0);
+        if (need > 0.2 * (double)total_mem[h->device]) {
+            size_t free_b = 0, total_b = 0;
+            CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            cudaMemPool_t mp_; unsigned long long reserved = 0, usedb = 0;
+            if (cudaDeviceGetDefaultMemPool(&mp_, h->device) == cudaSuccess && cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrUsedMemCurrent, &usedb) == cudaSuccess && reserved > usedb) free_b += (size_t)(reserved - usedb);
+            if (need > 0.5 * (double)free_b) return CRM_OK;
+        }
     }
     PhaseTrace tr(st);
     h->oz_block_valid = false;
@@ -423,7 +428,7 @@ static int rotation_int8_split(Handle* h, const double* G, long long ldg, long l
     if (flags[0] != 0) return CRM_OK;                                              // not integer dosages
     if ((double)Kp * 64.0 * (double)std::max(flags[1], 1) >= 2147483648.0) return CRM_OK;   // int32 accumulation could overflow
     if (!h->oz_built) {
-        CRM_CHECK(h->A8.reserve(a8_bytes));
+        if (h->A8.reserve(a8_bytes) != CRM_OK) return CRM_OK;      // no room after all: the fp64 route takes over
         CRM_CHECK(h->a8expo.reserve((size_t)Mtot * sizeof(int)));
         CRM_CHECK(oz_launch_exponents(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, n, h->a8expo.as<int>(), st));
         CRM_CHECK(oz_launch_slices(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, 0, h->kexp, n, h->a8expo.as<int>(), h->A8.as<int8_t>(), Mp, Kp, st));
@@ -1346,7 +1351,7 @@ int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const doubl
 
 int crm_int8_split_gemm(const double* X, int64_t ldx, int64_t cols, const double* G, int64_t ldg, int64_t B, int64_t n, int route, double* C, int64_t ldc,
                         int32_t* flags2, float* contraction_ms, void* stream) {
-    if (!X || !G || !C || !flags2 || cols <= 0 || B <= 0 || n <= 0 || ldx < cols || ldg < B || ldc < cols || route < 0 || route > 1) { set_error("crm_int8_split_gemm: bad arguments"); return CRM_ERR_INVALID; }
+    if (!X || !G || !C || !flags2 || cols <= 0 || B <= 0 || n <= 0 || ldx < cols || ldg < B || ldc < cols || route < 0 || route > 2) { set_error("crm_int8_split_gemm: bad arguments"); return CRM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const long long Mp = round_up(cols, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
     DevBuf P8, expo, Gt8, flags, D32;
@@ -1361,7 +1366,7 @@ int crm_int8_split_gemm(const double* X, int64_t ldx, int64_t cols, const double
         cudaEvent_t e0, e1;
         CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
         CRM_CUDA(cudaEventRecord(e0, st));
-        if (route == 0) status = oz_launch_mma(P8.as<int8_t>(), Mp, cols, expo.as<int>(), Gt8.as<int8_t>(), Bp, B, Kp, C, ldc, st);
+        if (route != 1) status = oz_launch_mma(P8.as<int8_t>(), Mp, cols, expo.as<int>(), Gt8.as<int8_t>(), Bp, B, Kp, C, ldc, st, route == 0 ? 1 : 2);
         else {
             status = D32.reserve((size_t)OZAKI_SLICES * Mp * Bp * sizeof(int));
             if (status == CRM_OK) status = oz_int8_gemm(P8.as<int8_t>(), (long long)OZAKI_SLICES * Mp, Gt8.as<int8_t>(), Bp, Kp, D32.as<int>(), Bp, st);

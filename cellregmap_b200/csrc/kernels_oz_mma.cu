@@ -1,4 +1,6 @@
 // Translation unit: tcgen05 int8 contraction with fused fp64 recombination (oz_mma.cuh) -- tensor maps + launch.
+#include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 
 #include "launch.cuh"
@@ -30,25 +32,57 @@ static int make_map_k_major(CUtensorMap* map, const int8_t* ptr, long long rows,
     return CRM_OK;
 }
 
+// variant < 0: process default -- the single-CTA kernel; CRM_INT8_MMA=2cta selects the CTA-pair kernel, which keeps the tensor
+// pipe busier (92 % vs 86 %) but runs into the power cap earlier: 118-143 ms against 101-110 ms at bench size
+// (profiles/r01_int8_split_sweep.txt)
+static bool oz_use_pairs(int variant) {
+    static const bool env_pairs = [] { const char* v = getenv("CRM_INT8_MMA"); return v && !strcmp(v, "2cta"); }();
+    return variant < 0 ? env_pairs : variant == 2;
+}
+
 int oz_launch_mma(const int8_t* A8, long long Mp, long long Mtot, const int* expo, const int8_t* Gt8, long long Bp, long long B, long long Kp, double* C,
-                  long long ldc, cudaStream_t st) {
+                  long long ldc, cudaStream_t st, int variant) {
     if (B <= 0 || Mtot <= 0) return CRM_OK;
     if ((long long)OZ_SLICES * Mp > 2000000000LL || Kp > 2000000000LL) { set_error("int8 contraction: operand too large for 32-bit TMA coordinates"); return CRM_ERR_UNSUPPORTED; }
     CUtensorMap tmA, tmB;
-    CRM_CHECK(make_map_k_major(&tmA, A8, (long long)OZ_SLICES * Mp, Kp, OZM_BM));
-    CRM_CHECK(make_map_k_major(&tmB, Gt8, Bp, Kp, OZM_BN));
+    CRM_CHECK(make_map_k_major(&tmA, A8, (long long)OZ_SLICES * Mp, Kp, 128));
+    const bool pairs = oz_use_pairs(variant);
+    CRM_CHECK(make_map_k_major(&tmB, Gt8, Bp, Kp, pairs ? 128 : OZM_BN));
     OzMmaArgs a{};
     a.Mp = Mp; a.Mtot = Mtot; a.B = B; a.ldc = ldc;
     a.kblocks = (int)((Kp + OZM_BK - 1) / OZM_BK);
     a.m_tiles = (int)((Mtot + OZM_BM - 1) / OZM_BM);
     a.n_tiles = (int)((B + OZM_BN - 1) / OZM_BN);
     a.expo = expo; a.C = C;
+    { static const int ng = [] { const char* v = getenv("CRM_OZ_NGROUP"); return v && atoi(v) > 0 ? atoi(v) : OZM_NGROUP; }(); a.ngroup = ng; }
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         CRM_CUDA(cudaGetDevice(&dev));
         CRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         CRM_CUDA(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZM_SMEM_BYTES));
+    }
+    if (pairs) {
+        static bool attr2 = false;
+        static int max_pairs = 0;
+        if (!attr2) {
+            CRM_CUDA(cudaFuncSetAttribute(oz_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES));
+            // CTA pairs that can be resident at once (an SM whose TPC partner is fused off cannot host half a pair)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)sms, 1, 1); cfg.blockDim = dim3(OZM_THREADS, 1, 1); cfg.dynamicSmemBytes = OZ2_SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_pairs, oz_mma2_kernel, &cfg) != cudaSuccess || max_pairs <= 0) { cudaGetLastError(); max_pairs = sms / 2; }
+            if (getenv("CRM_TRACE")) fprintf(stderr, "[crm trace] oz_mma2_kernel: %d SMs, %d resident CTA pairs\n", sms, max_pairs);
+            attr2 = true;
+        }
+        a.m_tiles = (int)((Mtot + OZ2_BM - 1) / OZ2_BM);
+        const long long units2 = (long long)a.m_tiles * a.n_tiles;
+        const unsigned grid2 = 2u * (unsigned)std::min<long long>(units2, max_pairs);
+        oz_mma2_kernel<<<grid2, OZM_THREADS, OZ2_SMEM_BYTES, st>>>(tmA, tmB, a);
+        CRM_CUDA(cudaGetLastError()); count_launch();
+        return CRM_OK;
     }
     const long long units = (long long)a.m_tiles * a.n_tiles;
     const unsigned grid = (unsigned)std::min<long long>(units, sms);

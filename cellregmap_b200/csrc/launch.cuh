@@ -51,7 +51,7 @@ int oz_launch_matrix_planes(const double* X, long long ldx, int cols, long long 
 int oz_launch_combine(const int* D, long long Mp, long long ldd, const int* expo, long long Mtot, long long B, double* C, long long ldc, cudaStream_t st);
 // the same contraction + recombination in one hand-written tcgen05 kernel (oz_mma.cuh): C[s][col], bit-identical
 int oz_launch_mma(const int8_t* A8, long long Mp, long long Mtot, const int* expo, const int8_t* Gt8, long long Bp, long long B, long long Kp, double* C,
-                  long long ldc, cudaStream_t st);
+                  long long ldc, cudaStream_t st, int variant = -1);   // variant: -1 process default, 1 single CTA, 2 CTA pairs
 int oz_int8_gemm(const int8_t* A8, long long Mrows, const int8_t* Gt8, long long Bp, long long Kp, int* D, long long ldd, cudaStream_t st);
 
 }  // namespace crm

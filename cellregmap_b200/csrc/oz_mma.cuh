@@ -29,12 +29,12 @@ constexpr int OZM_A_BYTES = OZM_BM * OZM_BK;                  // 16 KB
 constexpr int OZM_B_BYTES = OZM_BN * OZM_BK;                  // 32 KB
 constexpr int OZM_STAGE_BYTES = 2 * OZM_A_BYTES + OZM_B_BYTES;
 constexpr int OZM_SMEM_BYTES = OZM_STAGES * OZM_STAGE_BYTES + 1024 + 256;
-constexpr int OZM_NGROUP = 4;                                 // SNP tiles per rasterisation group
+constexpr int OZM_NGROUP = 8;                                 // default number of SNP tiles per rasterisation group
 static_assert(OZ_SLICES == 8, "the pass structure below assumes 8 digit planes");
 
 struct OzMmaArgs {
     long long Mp, Mtot, B, ldc;
-    int kblocks, m_tiles, n_tiles;
+    int kblocks, m_tiles, n_tiles, ngroup;
     const int* expo;
     double* C;
 };
@@ -100,10 +100,10 @@ struct OzTile { int m0, n0, ncols; };
 // unit -> tile: groups of OZM_NGROUP SNP tiles x all column tiles, SNP tile fastest, so that the CTAs in flight (consecutive
 // units) share a few dosage panels and a contiguous run of digit-plane panels through L2
 __device__ __forceinline__ OzTile oz_unit_tile(const OzMmaArgs& a, int u) {
-    const int per_group = OZM_NGROUP * a.m_tiles;
+    const int per_group = a.ngroup * a.m_tiles;
     const int g = u / per_group, r = u - g * per_group;
-    const int ng = min(OZM_NGROUP, a.n_tiles - g * OZM_NGROUP);
-    const int mt = r / ng, nt = g * OZM_NGROUP + (r - mt * ng);
+    const int ng = min(a.ngroup, a.n_tiles - g * a.ngroup);
+    const int mt = r / ng, nt = g * a.ngroup + (r - mt * ng);
     OzTile t;
     t.m0 = mt * OZM_BM; t.n0 = nt * OZM_BN;
     const long long left = a.B - (long long)t.n0;
@@ -224,6 +224,195 @@ __global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tc_dealloc(tmem_base, 512);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// CTA-pair version (cta_group::2): two CTAs of a cluster share one tile of 256 columns x 256 SNPs.  Each CTA stages its own
+// 128 columns of both digit planes and its own half of the SNP tile (48 KB per stage instead of 64 KB: the single-CTA kernel
+// sits on the L2 -> SM bandwidth cap, profiles/r01_ncu_oz_mma_kernel.txt), the leader CTA issues tcgen05.mma.cta_group::2
+// (M = 256, N = 256) which reads both halves of the SNP tile and writes 128 accumulator lanes into the TMEM of each CTA.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int OZ2_BM = 256;
+constexpr int OZ2_STAGES = 4;
+constexpr int OZ2_A_BYTES = 128 * OZM_BK;                     // one digit plane, this CTA's 128 columns
+constexpr int OZ2_B_BYTES = 128 * OZM_BK;                     // this CTA's half of the SNP tile
+constexpr int OZ2_STAGE_BYTES = 2 * OZ2_A_BYTES + OZ2_B_BYTES;
+constexpr int OZ2_SMEM_BYTES = OZ2_STAGES * OZ2_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_map(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tc2_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc2_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in both CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void tc2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// TMA load into this CTA's shared memory, completion counted on an mbarrier that may live in the peer CTA
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ OzTile oz2_unit_tile(const OzMmaArgs& a, int u) {
+    const int per_group = a.ngroup * a.m_tiles;
+    const int g = u / per_group, r = u - g * per_group;
+    const int ng = min(a.ngroup, a.n_tiles - g * a.ngroup);
+    const int mt = r / ng, nt = g * a.ngroup + (r - mt * ng);
+    OzTile t;
+    t.m0 = mt * OZ2_BM; t.n0 = nt * OZM_BN;
+    const long long left = a.B - (long long)t.n0;
+    t.ncols = (int)min((long long)OZM_BN, (left + 31) / 32 * 32);
+    return t;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZM_THREADS, 1)
+oz_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzMmaArgs a) {
+    extern __shared__ uint8_t oz_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OZ2_STAGES * OZ2_STAGE_BYTES);
+    uint64_t* full = bars;                         // [STAGES]  TMA (both CTAs) -> MMA; the leader's copy is the one in use
+    uint64_t* empty = bars + OZ2_STAGES;           // [STAGES]  MMA -> TMA, one per CTA (multicast commit)
+    uint64_t* tmem_full = bars + 2 * OZ2_STAGES;   // MMA -> epilogue, one per CTA (multicast commit)
+    uint64_t* tmem_empty = tmem_full + 1;          // epilogues of both CTAs -> MMA (leader's copy)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int units = a.m_tiles * a.n_tiles;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < OZ2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 256);
+        mbar_fence_init();
+    }
+    if (warp == 1) tc2_alloc(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                            // ===== TMA producer (both CTAs) =====
+            uint32_t it = 0;
+            for (int u = pair; u < units; u += npairs) {
+                const OzTile t = oz2_unit_tile(a, u);
+                const int brow = t.n0 + (int)rank * (t.ncols >> 1);
+                for (int pass = 0; pass < 4; pass++) {
+                    const int row1 = (int)((long long)(7 - 2 * pass) * a.Mp) + t.m0 + (int)rank * 128;
+                    const int row2 = (int)((long long)(6 - 2 * pass) * a.Mp) + t.m0 + (int)rank * 128;
+                    for (int kb = 0; kb < a.kblocks; kb++, it++) {
+                        const uint32_t s = it % OZ2_STAGES, ph = (it / OZ2_STAGES) & 1u;
+                        mbar_wait_backoff(&empty[s], ph ^ 1u);
+                        uint8_t* st = smem + s * OZ2_STAGE_BYTES;
+                        if (rank == 0) mbar_expect_tx(&full[s], 2 * OZ2_STAGE_BYTES);
+                        const uint32_t fb = cluster_map(smem_u32(&full[s]), 0);
+                        tma2_load_2d(st, &tmA, fb, kb * OZM_BK, row1);
+                        tma2_load_2d(st + OZ2_A_BYTES, &tmA, fb, kb * OZM_BK, row2);
+                        tma2_load_2d(st + 2 * OZ2_A_BYTES, &tmB, fb, kb * OZM_BK, brow);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {               // ===== MMA issue (leader CTA) =====
+            uint32_t it = 0, acc_it = 0;
+            for (int u = pair; u < units; u += npairs) {
+                const OzTile t = oz2_unit_tile(a, u);
+                const uint32_t idesc = oz_instr_desc(OZ2_BM, t.ncols);
+                for (int pass = 0; pass < 4; pass++, acc_it++) {
+                    mbar_wait(tmem_empty, (acc_it & 1u) ^ 1u);
+                    tc_fence_after();
+                    for (int kb = 0; kb < a.kblocks; kb++, it++) {
+                        const uint32_t s = it % OZ2_STAGES, ph = (it / OZ2_STAGES) & 1u;
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + s * OZ2_STAGE_BYTES);
+                        const uint64_t d1 = oz_smem_desc(sa), d2 = oz_smem_desc(sa + OZ2_A_BYTES), db = oz_smem_desc(sa + 2 * OZ2_A_BYTES);
+#pragma unroll
+                        for (int k4 = 0; k4 < OZM_BK / OZM_UK; k4++) {
+                            const uint64_t adv = (uint64_t)(k4 * OZM_UK >> 4);
+                            const uint32_t acc = (kb | k4) != 0;
+                            tc2_mma_i8(tmem_base, d1 + adv, db + adv, idesc, acc);
+                            tc2_mma_i8(tmem_base + OZM_BN, d2 + adv, db + adv, idesc, acc);
+                        }
+                        tc2_commit(&empty[s]);
+                    }
+                    tc2_commit(tmem_full);
+                }
+            }
+        }
+    } else {                                        // ===== epilogue (both CTAs): this CTA's 128 accumulator lanes =====
+        const int q = warp & 3;
+        const uint32_t te = cluster_map(smem_u32(tmem_empty), 0);
+        uint32_t acc_it = 0;
+        for (int u = pair; u < units; u += npairs) {
+            const OzTile t = oz2_unit_tile(a, u);
+            const long long col = (long long)t.m0 + (long long)rank * 128 + 32 * q + lane;
+            const bool col_ok = col < a.Mtot;
+            const int e = col_ok ? a.expo[col] : OZ_EXP_EMPTY;
+            for (int pass = 0; pass < 4; pass++, acc_it++) {
+                mbar_wait(tmem_full, acc_it & 1u);
+                tc_fence_after();
+                const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+                for (int ch = 0; ch < OZM_BN / 32; ch++) {
+                    const long long s_first = (long long)t.n0 + ch * 32;
+                    if (s_first >= a.B) break;
+                    uint32_t hi[32], lo[32];
+                    tc_ld32(tlane + ch * 32, hi);
+                    tc_ld32(tlane + OZM_BN + ch * 32, lo);
+                    tc_wait_ld();
+                    if (col_ok) {
+                        double* cp = a.C + s_first * a.ldc + col;
+                        double acc[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) acc[j] = (pass > 0 && s_first + j < a.B) ? cp[(long long)j * a.ldc] : 0.0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            double v = (acc[j] + (double)(int)hi[j]) * 0.0078125;
+                            v = (v + (double)(int)lo[j]) * 0.0078125;
+                            if (pass == 3) v = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(v, e + 1);
+                            if (s_first + j < a.B) cp[(long long)j * a.ldc] = v;
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(te);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tc2_dealloc(tmem_base, 512);
 }
 
 }  // namespace crm

@@ -138,8 +138,8 @@ CRM_API int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, con
 
 /* K0 on caller-supplied operands: C[B][cols] (ldc) = G' X by the exact int8 split -- 8 digit planes of the real matrix X [n][cols]
  * (ldx) against the integer-valued matrix G [n][B] (ldg); replaces the same `Q0.T @` products as crm_gemm (cellregmap/_math.py:72-73)
- * when the genotypes are integer dosages.  route 0: hand-written tcgen05 kernel with fused fp64 recombination; 1: cuBLASLt int8 GEMM +
- * recombination kernel (bit-identical).  flags2 (host) = {G not integer in [-127,127], max |g|}; contraction_ms (host, optional) =
+ * when the genotypes are integer dosages.  route 0: hand-written tcgen05 kernel with fused fp64 recombination (the product path); 1: cuBLASLt int8
+ * GEMM + recombination kernel; 2: the CTA-pair (cta_group::2) variant of the tcgen05 kernel -- all bit-identical.  flags2 (host) = {G not integer in [-127,127], max |g|}; contraction_ms (host, optional) =
  * CUDA-event time of the contraction alone.  Synchronises the stream. */
 CRM_API int crm_int8_split_gemm(const double* X, int64_t ldx, int64_t cols, const double* G, int64_t ldg, int64_t B, int64_t n, int route,
                         double* C, int64_t ldc, int32_t* flags2, float* contraction_ms, void* stream);

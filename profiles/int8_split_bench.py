@@ -11,7 +11,8 @@ X = torch.randn((n, cols), dtype=torch.float64, device=dev, generator=g)
 G = torch.randint(0, 3, (n, B), device=dev, generator=g).to(torch.float64)
 out = {}
 res = {}
-for route in (0, 1, 0, 1):
+routes = (0, 0, 0) if len(sys.argv) > 4 else (0, 1, 0, 1)
+for route in routes:
     C = torch.empty((B, cols), dtype=torch.float64, device=dev)
     flags = (ctypes.c_int32 * 2)(); ms = ctypes.c_float(0.0)
     _lib.call("crm_int8_split_gemm", ctypes.c_void_p(X.data_ptr()), cols, cols, ctypes.c_void_p(G.data_ptr()), B, B, n, route,
@@ -20,5 +21,5 @@ for route in (0, 1, 0, 1):
     out.setdefault(route, []).append({"ms": ms.value, "TOPs": ops / ms.value / 1e9})
     res[route] = C
     del C
-print(json.dumps({"n": n, "cols": cols, "B": B, "fused_tcgen05": out[0], "cublaslt_plus_combine": out[1],
-                  "bit_identical": bool(torch.equal(res[0], res[1]))}))
+print(json.dumps({"n": n, "cols": cols, "B": B, "fused_tcgen05": out[0], "cublaslt_plus_combine": out.get(1),
+                  "bit_identical": bool(torch.equal(res[0], res[1])) if 1 in res else None}))

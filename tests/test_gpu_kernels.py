@@ -55,8 +55,10 @@ def test_int8_split_contraction(cuda_device, n, cols, B):
     X[:, min(3, cols - 1)] = 0.0                              # an all-zero column (empty exponent)
     c_mma, f0, _ = _int8_split(X, G, 0, cuda_device)
     c_lt, f1, _ = _int8_split(X, G, 1, cuda_device)
-    assert f0 == f1 == (0, 2)
+    c_pair, f2, _ = _int8_split(X, G, 2, cuda_device)
+    assert f0 == f1 == f2 == (0, 2)
     assert np.array_equal(c_mma, c_lt)
+    assert np.array_equal(c_pair, c_lt)
     ref = G.T @ X
     scale = np.abs(G).T @ np.abs(X) + 1e-300
     assert np.max(np.abs(c_mma - ref) / scale) < 1e-14
