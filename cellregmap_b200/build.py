@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, _units()))
-    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcusolver", "-lcublasLt", "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
+    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcusolver", "-lcublas", "-lcublasLt", "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
     subprocess.check_call(cmd)
     return LIB
 

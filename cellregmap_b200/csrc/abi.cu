@@ -1,5 +1,6 @@
 // libcrm_b200.so -- C ABI (include/crm_b200.h) over the sm_100a kernels of this directory.
 // Host orchestration only: set-up of the per-gene state, batching of SNPs, kernel launches.
+#include <cublas_v2.h>
 #include <cusolverDn.h>
 #include <stdarg.h>
 #include <math.h>
@@ -93,7 +94,7 @@ struct DevBuf {
 
 // Creating a cuSOLVER handle costs tens of milliseconds, so one context per device lives in a process-wide pool and is
 // reused by every model object (set-up calls are serialised by the pool mutex).
-struct EigCtx { cusolverDnHandle_t solver = nullptr; cusolverDnParams_t params = nullptr; DevBuf mat, val, work; std::vector<char> host_work; };
+struct EigCtx { cusolverDnHandle_t solver = nullptr; cusolverDnParams_t params = nullptr; cublasHandle_t blas = nullptr; DevBuf mat, val, work, vec, ws, quality; std::vector<char> host_work; };
 struct EigPool { std::mutex mu; std::vector<EigCtx> ctx; };
 static EigPool g_eig_pool[16];
 
@@ -595,7 +596,60 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     // CRM_EIG_BATCHED=1 puts all grid points into one cusolverDnXsyevBatched call: 70 ms instead of 134 ms for
     // 11 x 1020^2 on B200, but its first call in a process costs 54 s of one-time initialisation, so it is opt-in.
     static const bool batched = [] { const char* v = getenv("CRM_EIG_BATCHED"); return v && atoi(v) != 0; }();
-    if (batched) {
+    // All grid points go through the batched solver of eig.cuh (tridiagonalisation of every matrix at once on its own group of
+    // SMs, multisection + inverse iteration + re-orthonormalisation, back-transformation): 33 ms instead of 122 ms for 11 problems
+    // of size 1020 (profiles/r01_eig_bench.txt).  The sequential cusolverDnDsyevd calls remain as the fall-back when a size is out
+    // of range or the residual / orthogonality check of a matrix fails, and as the reference point (CRM_EIG=cusolver).
+    static const bool native = [] { const char* v = getenv("CRM_EIG"); return !(v && !strcmp(v, "cusolver")); }();
+    bool native_done = false;
+    if (native && !batched && m >= 2 && m <= 2880 && R <= 64) {
+        std::vector<int> n_of(R), a0_of(R);
+        bool ok = true;
+        for (int r = 0; r < R; r++) {
+            int a0 = 0, ms = m;
+            if (mL > 0 && h->rho[r] == 1.0) { a0 = 0; ms = k1; }
+            else if (mL > 0 && h->rho[r] == 0.0) { a0 = k1; ms = (int)mL; }
+            n_of[r] = ms; a0_of[r] = a0;
+            if (ms < 2) ok = false;
+        }
+        if (ok) {
+            if (!e.blas && cublasCreate(&e.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CRM_ERR_SOLVER; }
+            size_t ws_bytes = 0;
+            CRM_CHECK(eig_workspace_bytes(m, R, &ws_bytes));
+            CRM_CHECK(e.mat.reserve((size_t)R * m * m * 8)); CRM_CHECK(e.vec.reserve((size_t)R * m * m * 8)); CRM_CHECK(e.val.reserve((size_t)R * m * 8));
+            CRM_CHECK(e.ws.reserve(ws_bytes)); CRM_CHECK(e.quality.reserve((size_t)R * 8 + (size_t)2 * R * 4));
+            int lib_lwork = 0;
+            CRM_CHECK(eig_lib_lwork(e.solver, m, &lib_lwork));
+            CRM_CHECK(e.work.reserve((size_t)std::max(lib_lwork, lwork) * 8));
+            for (int r = 0; r < R; r++) {
+                scale_gram_kernel<<<blocks_for((long long)n_of[r] * n_of[r], 256), 256, 0, st>>>(h->gram.as<double>(), ldH, a0_of[r], n_of[r], k1, h->rho[r], e.mat.as<double>() + (size_t)r * m * m);
+                CRM_CUDA(cudaGetLastError()); count_launch();
+            }
+            int* lib_info = reinterpret_cast<int*>(e.quality.as<double>() + R);
+            CRM_CUDA(cudaMemsetAsync(lib_info, 0, (size_t)2 * R * 4, st));
+            CRM_CHECK(eig_batched(e.solver, e.blas, e.mat.as<double>(), n_of.data(), m, R, e.val.as<double>(), e.vec.as<double>(), e.quality.as<double>(), e.ws.ptr,
+                                  e.work.as<double>(), std::max(lib_lwork, lwork), lib_info, st));
+            std::vector<double> q(R); std::vector<int> li(2 * R);
+            CRM_CUDA(cudaMemcpyAsync(q.data(), e.quality.ptr, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+            CRM_CUDA(cudaMemcpyAsync(li.data(), lib_info, (size_t)2 * R * 4, cudaMemcpyDeviceToHost, st));
+            CRM_CUDA(cudaStreamSynchronize(st));
+            native_done = true;
+            for (int r = 0; r < R; r++) if (!(q[r] < 1e-11) || li[r] != 0 || li[R + r] != 0) native_done = false;
+            static const bool verbose = [] { const char* v = getenv("CRM_TRACE"); return v && atoi(v) != 0; }();
+            if (verbose) { fprintf(stderr, "[crm trace] native eigensolver: %s; residuals", native_done ? "accepted" : "rejected"); for (int r = 0; r < R; r++) fprintf(stderr, " %.1e", q[r]); fprintf(stderr, "\n"); }
+            if (native_done) {
+                CRM_CUDA(cudaMemsetAsync(info_dev, 0, (size_t)R * 4, st));
+                for (int r = 0; r < R; r++) {
+                    build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
+                        e.vec.as<double>() + (size_t)r * m * m, e.val.as<double>() + (size_t)r * m, m, mp, a0_of[r], n_of[r], k1, h->rho[r], tall,
+                        h->S.as<double>() + (long long)r * mp, h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
+                    CRM_CUDA(cudaGetLastError()); count_launch();
+                }
+            }
+        }
+    }
+    if (native_done) {
+    } else if (batched) {
         CRM_CHECK(e.mat.reserve((size_t)R * m * m * 8));
         CRM_CHECK(e.val.reserve((size_t)R * m * 8));
         if (!e.params) CRM_SOLVER(cusolverDnCreateParams(&e.params));
@@ -1347,6 +1401,51 @@ int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const doubl
     op.A = A; op.lda = lda; op.a_cols = a_cols; op.B = B; op.ldb = ldb; op.b_cols = b_cols;
     op.B2 = B2 ? B2 : B; op.ldb2 = B2 ? ldb2 : ldb; op.b2_cols = B2 ? b2_cols : b_cols;
     return launch_gemm(mode, op, (int)K, m_begin, m_count, (int)n_begin, (int)n_count, out, ldc, kexp, (cudaStream_t)stream);
+}
+
+int crm_eigh_batched(const double* A, int n, int batch, double* W, double* V, double* quality_host, float* ms, void* stream) {
+    if (!A || !W || !V || n < 2 || batch < 1) { set_error("crm_eigh_batched: bad arguments"); return CRM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    CRM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { set_error("device index %d outside the supported range", dev); return CRM_ERR_UNSUPPORTED; }
+    EigPool& pool = g_eig_pool[dev];
+    std::lock_guard<std::mutex> pool_lock(pool.mu);
+    if (pool.ctx.empty()) pool.ctx.resize(1);
+    EigCtx& e = pool.ctx[0];
+    if (!e.solver) CRM_SOLVER(cusolverDnCreate(&e.solver));
+    if (!e.blas && cublasCreate(&e.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CRM_ERR_SOLVER; }
+    size_t ws_bytes = 0;
+    CRM_CHECK(eig_workspace_bytes(n, batch, &ws_bytes));
+    DevBuf mat, ws, quality, work;
+    const size_t nn = (size_t)n * n;
+    CRM_CHECK(mat.reserve((size_t)batch * nn * 8)); CRM_CHECK(ws.reserve(ws_bytes)); CRM_CHECK(quality.reserve((size_t)batch * 8 + (size_t)2 * batch * 4));
+    int lib_lwork = 0;
+    CRM_SOLVER(cusolverDnSetStream(e.solver, st));
+    CRM_CHECK(eig_lib_lwork(e.solver, n, &lib_lwork));
+    CRM_CHECK(work.reserve((size_t)lib_lwork * 8));
+    CRM_CUDA(cudaMemcpyAsync(mat.ptr, A, (size_t)batch * nn * 8, cudaMemcpyDeviceToDevice, st));
+    int* lib_info = reinterpret_cast<int*>(quality.as<double>() + batch);
+    CRM_CUDA(cudaMemsetAsync(lib_info, 0, (size_t)2 * batch * 4, st));
+    cudaEvent_t e0, e1;
+    CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
+    CRM_CUDA(cudaEventRecord(e0, st));
+    int status = eig_batched(e.solver, e.blas, mat.as<double>(), nullptr, n, batch, W, V, quality.as<double>(), ws.ptr, work.as<double>(), lib_lwork, lib_info, st);
+    cudaEventRecord(e1, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    float t = 0.f;
+    if (ce == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
+    if (ms) *ms = t;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (status == CRM_OK && ce != cudaSuccess) { set_error("crm_eigh_batched: %s", cudaGetErrorString(ce)); status = CRM_ERR_CUDA; }
+    if (status == CRM_OK && quality_host) {
+        std::vector<int> li(2 * batch);
+        cudaMemcpy(quality_host, quality.ptr, (size_t)batch * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(li.data(), lib_info, (size_t)2 * batch * 4, cudaMemcpyDeviceToHost);
+        for (int b = 0; b < batch; b++) if (li[b] != 0 || li[batch + b] != 0) quality_host[b] = INFINITY;
+    }
+    mat.release(); ws.release(); quality.release(); work.release();
+    return status;
 }
 
 int crm_int8_split_gemm(const double* X, int64_t ldx, int64_t cols, const double* G, int64_t ldg, int64_t B, int64_t n, int route, double* C, int64_t ldc,

@@ -54,4 +54,11 @@ int oz_launch_mma(const int8_t* A8, long long Mp, long long Mtot, const int* exp
                   long long ldc, cudaStream_t st, int variant = -1);   // variant: -1 process default, 1 single CTA, 2 CTA pairs
 int oz_int8_gemm(const int8_t* A8, long long Mrows, const int8_t* Gt8, long long Bp, long long Kp, int* D, long long ldd, cudaStream_t st);
 
+
+// batched symmetric eigensolver of the set-up (eig.cuh / kernels_eig.cu); solver / blas are cusolverDnHandle_t / cublasHandle_t
+int eig_workspace_bytes(int n, int batch, size_t* bytes);
+int eig_lib_lwork(void* solver, int n, int* lwork);
+int eig_batched(void* solver, void* blas, double* A, const int* n_of, int n, int batch, double* W, double* V, double* quality, void* ws, double* lib_work, int lib_lwork,
+                int* info_dev, cudaStream_t st);
+
 }  // namespace crm

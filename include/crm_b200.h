@@ -136,6 +136,13 @@ CRM_API int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, con
              const double* B2, int64_t ldb2, int64_t b2_cols, int64_t K, int m_begin, int m_count, int64_t n_begin,
              int64_t n_count, double* out, int64_t ldc, int kexp, void* stream);
 
+/* Set-up eigensolver on caller-supplied matrices: `batch` symmetric n x n matrices A [batch][n][n] (device, both triangles) ->
+ * eigenvalues W [batch][n] ascending and orthonormal eigenvectors V [batch][n][n] (V[b][t*n + i] = component i of vector t), the
+ * batched replacement of numpy_sugar.economic_qs_linear's eigh per rho (cellregmap/_cellregmap.py:129).  quality_host [batch]
+ * (optional) = largest residual |T z - lambda z|_inf / |T| of the tridiagonal eigenpairs (inf when a library step reported an
+ * error); ms (optional) = CUDA-event time.  Synchronises the stream. */
+CRM_API int crm_eigh_batched(const double* A, int n, int batch, double* W, double* V, double* quality_host, float* ms, void* stream);
+
 /* K0 on caller-supplied operands: C[B][cols] (ldc) = G' X by the exact int8 split -- 8 digit planes of the real matrix X [n][cols]
  * (ldx) against the integer-valued matrix G [n][B] (ldg); replaces the same `Q0.T @` products as crm_gemm (cellregmap/_math.py:72-73)
  * when the genotypes are integer dosages.  route 0: hand-written tcgen05 kernel with fused fp64 recombination (the product path); 1: cuBLASLt int8

@@ -45,6 +45,49 @@ def _int8_split(X, G, route, dev):
     return o[:, :cols], (flags[0], flags[1]), ms.value
 
 
+def _eigh_batched(mats, dev):
+    import torch
+    from cellregmap_b200 import _lib
+    batch, n, _ = mats.shape
+    At = _t(mats, dev)
+    W = torch.empty((batch, n), dtype=torch.float64, device=dev)
+    V = torch.empty((batch, n, n), dtype=torch.float64, device=dev)
+    q = (ctypes.c_double * batch)()
+    ms = ctypes.c_float(0.0)
+    _lib.call("crm_eigh_batched", _p(At), n, batch, _p(W), _p(V), q, ctypes.byref(ms), ctypes.c_void_p(0))
+    return W.cpu().numpy(), V.cpu().numpy(), np.array(list(q)), ms.value
+
+
+def _eig_test_matrices(n, rng):
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    X = rng.standard_normal((3 * n, n))
+    mats = [X.T @ X / n,                                                                   # generic positive definite
+            3.0 * np.eye(n),                                                               # fully degenerate
+            (q * np.repeat(rng.uniform(0.5, 2.0, (n + 7) // 8), 8)[:n]) @ q.T,              # clusters of 8 equal eigenvalues
+            (q[:, : n // 3] * rng.uniform(1.0, 5.0, n // 3)) @ q[:, : n // 3].T,            # rank n/3, null space of dimension 2n/3
+            (q * np.concatenate([np.full(n // 2, 1.0), 1.0 + 1e-9 * np.arange(n - n // 2)])) @ q.T,   # very close, not equal
+            np.diag(rng.uniform(-1.0, 1.0, n))]                                            # already diagonal (every reflector trivial)
+    return np.stack([(m + m.T) / 2 for m in mats])
+
+
+@pytest.mark.parametrize("n", [2, 5, 64, 257, 1020])
+def test_eigh_batched(cuda_device, n):
+    """Set-up eigensolver (eig.cuh): eigenvalues against LAPACK, orthonormality and residuals of the eigenvectors, including
+    degenerate, clustered and rank-deficient spectra."""
+    rng = np.random.default_rng(n)
+    mats = _eig_test_matrices(n, rng) if n >= 24 else np.stack([(lambda a: (a + a.T) / 2)(rng.standard_normal((n, n))) for _ in range(4)])
+    W, V, q, ms = _eigh_batched(mats, cuda_device)
+    for b in range(mats.shape[0]):
+        A = mats[b]
+        scale = max(np.abs(np.linalg.eigvalsh(A)).max(), 1e-300)
+        Vb = V[b].T                                   # V[b][t] = eigenvector t -> columns
+        assert np.isfinite(q[b]) and q[b] < 1e-11, (b, q[b])
+        assert np.all(np.diff(W[b]) >= -1e-14 * scale)
+        assert np.max(np.abs(W[b] - np.linalg.eigvalsh(A))) < 1e-13 * n * scale, b
+        assert np.max(np.abs(Vb.T @ Vb - np.eye(n))) < 1e-12, b
+        assert np.max(np.abs(A @ Vb - Vb * W[b])) < 1e-12 * n * scale, b
+
+
 @pytest.mark.parametrize("n,cols,B", [(16, 8, 5), (1000, 130, 37), (4099, 300, 260), (20000, 129, 515), (700, 1200, 3)])
 def test_int8_split_contraction(cuda_device, n, cols, B):
     """K0: the fused tcgen05 kernel equals the cuBLASLt + recombination route bit for bit, and both equal the exact
