@@ -9,6 +9,7 @@ arrays like the reference's.  All numerics run in the CUDA library; torch only o
 and streams.
 """
 import ctypes
+import os
 from typing import Optional
 
 import numpy as np
@@ -107,7 +108,7 @@ class CellRegMap:
         u ~ N(0, v1 (1-rho1) K o E2 E2'),  eps ~ N(0, v2 I)
     """
 
-    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None, device=None):
+    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None, device=None, _prefetch=None):
         self._device = _device(device)
         dev = self._device
         self._y = _to_dev(y, dev).flatten()
@@ -150,6 +151,14 @@ class CellRegMap:
         self._handle = ctypes.c_void_p(0)
         torch.cuda.set_device(dev)
         _lib.call("crm_create", ctypes.byref(self._handle), dev.index if dev.index is not None else torch.cuda.current_device())
+        # A host-resident genotype matrix handed over by run_* starts its transfer now, under the set-up.  Every other input is on
+        # the device already: a later host-to-device copy would queue behind this transfer on the copy engine.
+        self._prefetched = None
+        if _prefetch is not None and os.environ.get("CRM_NO_STAGE") != "1" and not (isinstance(_prefetch, torch.Tensor) and _prefetch.is_cuda) \
+                and getattr(_prefetch, "ndim", 0) == 2:
+            geno = _Genotypes(_prefetch, dev, int(_prefetch.shape[0]))
+            _lib.call("crm_stage_genotypes", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, int(_prefetch.shape[0]), geno.p, _stream())
+            self._prefetched = (_prefetch, geno)
         rho = np.ascontiguousarray(np.asarray(self._rho1, dtype=np.float64))
         mL = 0 if Lcat is None else int(Lcat.shape[1])
         _lib.call("crm_setup", self._handle, _ptr(self._y), _ptr(self._W), self._W.stride(0), _ptr(self._E0),
@@ -195,7 +204,11 @@ class CellRegMap:
         reference API)."""
         dev = self._device
         if donor_index is None:
-            geno = _Genotypes(G, dev, self.n_samples)
+            if self._prefetched is not None and self._prefetched[0] is G:       # staged by the constructor: same host buffer
+                geno, self._prefetched = self._prefetched[1], None
+                assert geno.keep.shape[0] == self.n_samples, "G must have one row per sample"
+            else:
+                geno = _Genotypes(G, dev, self.n_samples)
             return geno, geno.on_host
         idx = torch.as_tensor(np.asarray(donor_index.cpu() if isinstance(donor_index, torch.Tensor) else donor_index), device=dev).long().flatten()
         assert idx.numel() == self.n_samples, "donor_index needs one entry per cell"
@@ -361,19 +374,19 @@ def run_association_fast(y, W, E, G, hK=None, *, donor_index=None):
     return crm.scan_association_fast(G, donor_index=donor_index)
 
 
-def _make_interaction_model(y, E, W, E1, E2, hK, device=None):
+def _make_interaction_model(y, E, W, E1, E2, hK, device=None, prefetch=None):
     dev = _device(device)
     E1 = E if E1 is None else E1
     E2 = E if E2 is None else E2
     Ls = None if hK is None else _L_concat(_to_dev(hK, dev, two_d=True), _to_dev(E2, dev))
-    return CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev)
+    return CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev, _prefetch=prefetch)
 
 
 def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None, *, donor_index=None):
     """Interaction test (reference :547-587).  NB `idx_G` is forwarded as scan_interaction's second
     positional argument, i.e. it permutes the rows of E (reference :586); kept.
     Extension: with `donor_index` (n,), G is the d x p donor-level genotype matrix (G_cells = G[donor_index])."""
-    crm = _make_interaction_model(y, E, W, E1, E2, hK)
+    crm = _make_interaction_model(y, E, W, E1, E2, hK, prefetch=G if donor_index is None else None)
     return crm.scan_interaction(G, idx_G, donor_index=donor_index)
 
 

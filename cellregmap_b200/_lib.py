@@ -53,6 +53,7 @@ SIGNATURES = {
     "crm_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_int64)]),
     "crm_profile_int8": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
+    "crm_stage_genotypes": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     "crm_eigh_batched": (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),
     "crm_int8_split_gemm": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

@@ -9,7 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/crm_b200.h"
@@ -41,6 +43,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 // CRM_TRACE=1: per-phase device times (CUDA events on the launching stream) printed to stderr at the end of a call
+static double host_ms() { static const auto t0 = std::chrono::steady_clock::now(); return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+static bool trace_on() { static const bool on = [] { const char* v = getenv("CRM_TRACE"); return v && atoi(v) != 0; }(); return on; }
 struct PhaseTrace {
     bool on;
     cudaStream_t st;
@@ -137,12 +141,18 @@ struct Handle {
     std::vector<cudaEvent_t> prof_events;
     double prof_flops = 0.0;
     cudaStream_t copy_stream = nullptr;
+    // genotypes staged ahead of the scan (crm_stage_genotypes): the whole host matrix in device memory, copied in column chunks on
+    // the copy stream while the set-up runs; one event per chunk
+    DevBuf gstage;
+    const double* stage_src = nullptr; long long stage_ldg = 0, stage_p = 0, stage_rows = 0, stage_ld = 0; int stage_chunk = 0;
+    std::vector<cudaEvent_t> stage_events;          // one per chunk
+    bool stage_valid = false;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     void free_all() {
         DevBuf* all[] = {&A8, &a8expo, &Gt8, &G2t8, &D32, &ozflags, &A28, &a28expo, &HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
-                         &gtchunk[0], &gtchunk[1], &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
+                         &gtchunk[0], &gtchunk[1], &gstage, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -290,6 +300,21 @@ __global__ void extract_stats_kernel(const double* gram, int ldg, int m, int c, 
     if (threadIdx.x == 0) stats[0] = gram[(long long)m * ldg + m];
     for (int t = threadIdx.x; t < c; t += blockDim.x) stats[1 + t] = gram[(long long)m * ldg + m + 1 + t];
     for (int t = threadIdx.x; t < c * c; t += blockDim.x) { const int a = t / c, b = t - a * c; stats[1 + c + t] = gram[(long long)(m + 1 + a) * ldg + m + 1 + b]; }
+}
+// a handful of host doubles -> device memory through the kernel-argument path: a cudaMemcpyAsync from host memory would queue behind
+// the genotype transfer on the host-to-device copy engine (crm_stage_genotypes) and stall the compute stream until it ends
+struct SmallValues { double v[64]; };
+__global__ void set_values_kernel(double* dst, SmallValues vals, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = vals.v[i];
+}
+static int upload_small(double* dst, const double* src, int count, cudaStream_t st) {
+    if (count > 64) { set_error("upload_small: %d values", count); return CRM_ERR_UNSUPPORTED; }
+    SmallValues sv{};
+    for (int i = 0; i < count; i++) sv.v[i] = src[i];
+    set_values_kernel<<<1, 64, 0, st>>>(dst, sv, count);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
 }
 __global__ void finalize_interaction_kernel(const int* rho_idx, const double* v0, const double* v1, const double* grid, long long p,
                                             double* rho1, double* e2, double* g2, double* eps2) {
@@ -602,7 +627,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     // of range or the residual / orthogonality check of a matrix fails, and as the reference point (CRM_EIG=cusolver).
     static const bool native = [] { const char* v = getenv("CRM_EIG"); return !(v && !strcmp(v, "cusolver")); }();
     bool native_done = false;
-    if (native && !batched && m >= 2 && m <= 2880 && R <= 64) {
+    if (native && !batched && m >= 2 && m <= 4096 && R <= 64) {
         std::vector<int> n_of(R), a0_of(R);
         bool ok = true;
         for (int r = 0; r < R; r++) {
@@ -709,6 +734,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     h->ready = true;
     tr.mark("rotate null");
     tr.report("set-up");
+    if (trace_on()) fprintf(stderr, "[crm trace] host %.1f ms: set-up returns\n", host_ms());
     return CRM_OK;
 }
 
@@ -829,6 +855,44 @@ static int stage_host_block(Handle* h, const double* G, long long ldg, const dou
     return CRM_OK;
 }
 
+// Start copying a host genotype matrix (rows x p, leading dimension ldg) to the device in column chunks on the copy stream; returns
+// at once.  The next scan of the same matrix (same pointer, ldg, p) consumes it block by block as the chunks arrive -- called before
+// crm_setup, the transfer overlaps the set-up and the first blocks of the scan.
+static int do_stage_genotypes(Handle* h, const double* G, long long ldg, long long rows, long long p, cudaStream_t st) {
+    h->stage_valid = false;
+    if (!G || rows <= 0 || p <= 0 || ldg < p) { set_error("crm_stage_genotypes: bad arguments"); return CRM_ERR_INVALID; }
+    static size_t total_mem[16] = {0};
+    if (!total_mem[h->device]) { size_t f = 0; CRM_CUDA(cudaMemGetInfo(&f, &total_mem[h->device])); }
+    const long long ld = round_up(p, 2);
+    const double bytes = (double)rows * (double)ld * 8.0;
+    if (bytes > 0.25 * (double)total_mem[h->device]) return CRM_OK;          // too large to hold: the scan streams it in blocks instead
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, G) != cudaSuccess || pa.type != cudaMemoryTypeHost) { cudaGetLastError(); return CRM_OK; }   // pageable memory copies
+    // synchronously: nothing to gain from starting early
+    CRM_CHECK(ensure_streams(h));
+    CRM_CHECK(h->gstage.reserve((size_t)bytes));
+    // One copy stream, chunk after chunk: the copy engine drains one stream's queue before it turns to the next, so chunks spread
+    // over several streams would complete stream by stream instead of in column order (measured).  Strided (2-D) copies of this
+    // shape run at the full PCIe rate (profiles/h2d_probe.py: 55 GB/s for any chunk width from 512 columns).
+    const int chunk = 512;
+    const size_t nchunks = (size_t)((p + chunk - 1) / chunk);
+    while (h->stage_events.size() < nchunks) { cudaEvent_t e; CRM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->stage_events.push_back(e); }
+    // the buffer comes from the stream-ordered pool on the legacy stream; the copy stream is non-blocking: order it explicitly
+    CRM_CUDA(cudaEventRecord(h->ev_done[0], (cudaStream_t)0));
+    CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
+    CRM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
+    CRM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[1], 0));
+    for (size_t c = 0; c < nchunks; c++) {
+        const long long c0 = (long long)c * chunk, w = std::min<long long>(chunk, p - c0);
+        CRM_CUDA(cudaMemcpy2DAsync(h->gstage.as<double>() + c0, (size_t)ld * 8, G + c0, (size_t)ldg * 8, (size_t)w * 8, (size_t)rows, cudaMemcpyHostToDevice, h->copy_stream));
+        CRM_CUDA(cudaEventRecord(h->stage_events[c], h->copy_stream));
+    }
+    if (trace_on()) fprintf(stderr, "[crm trace] host %.1f ms: staging %lld x %lld genotypes in %zu chunks of %d columns\n", host_ms(), rows, p, nchunks, chunk);
+    h->stage_src = G; h->stage_ldg = ldg; h->stage_p = p; h->stage_rows = rows; h->stage_ld = ld; h->stage_chunk = chunk;
+    h->stage_valid = true;
+    return CRM_OK;
+}
+
 // A block of SNP columns as the kernels see it: device pointer, leading dimension, number of addressable columns.
 struct GBlock { const double* G; long long ld; long long cols; const double* G2; long long ld2; long long b; long long s0; };
 
@@ -862,14 +926,28 @@ static int for_each_block(Handle* h, const double* G, long long ldg, const doubl
     CRM_CHECK(ensure_streams(h));
     // block boundaries: a short first block (its copy is the only one that is not hidden behind compute), then blocks of B
     const long long Bp = round_up(B, 2);
+    const bool staged = h->stage_valid && !G2 && G == h->stage_src && ldg == h->stage_ldg && p == h->stage_p && h->gs->K == h->stage_rows;
     std::vector<long long> starts;
     {
-        const long long first = (p > B) ? std::min<long long>(B, 512) : std::min(B, p);
+        // streamed: a short first block (its copy is the only one not hidden behind compute); staged ahead: equal blocks
+        const long long first = staged ? std::min(B, p) : (p > B) ? std::min<long long>(B, 512) : std::min(B, p);
         starts.push_back(0);
         for (long long s0 = first; s0 < p; s0 += B) starts.push_back(s0);
         starts.push_back(p);
     }
     const long long nb = (long long)starts.size() - 1;
+    if (staged) {
+        // the matrix was staged ahead (crm_stage_genotypes): every block waits for the chunks that cover it
+        for (long long ib = 0; ib < nb; ib++) {
+            const long long s0 = starts[ib], b = starts[ib + 1] - s0;
+            const long long c_last = (s0 + b - 1) / h->stage_chunk;                       // chunks complete in order on the copy stream
+            CRM_CUDA(cudaStreamWaitEvent(st, h->stage_events[(size_t)c_last], 0));
+            GBlock blk{h->gstage.as<double>() + s0, h->stage_ld, h->stage_p - s0, nullptr, 0, b, s0};
+            CRM_CHECK(fn(blk));
+        }
+        h->stage_valid = false;         // one scan per staging: the host array may change afterwards
+        return CRM_OK;
+    }
     CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
     CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
     CRM_CHECK(stage_host_block(h, G, ldg, G2, ldg2, starts[0], starts[1] - starts[0], Bp, 0));
@@ -1017,7 +1095,7 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
     tr.mark("p-values");
     // 11. outputs
     double* grid_dev = h->scratch.as<double>();
-    CRM_CUDA(cudaMemcpyAsync(grid_dev, h->rho.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
+    CRM_CHECK(upload_small(grid_dev, h->rho.data(), R, st));
     finalize_interaction_kernel<<<blocks_for(B, 256), 256, 0, st>>>(h->rho_idx.as<int>(), h->v0.as<double>(), h->v1.as<double>(), grid_dev, B,
                                                                    out_rho1 + s0, out_e2 + s0, out_g2 + s0, out_eps2 + s0);
     CRM_CUDA(cudaGetLastError()); count_launch();
@@ -1099,10 +1177,10 @@ static int do_scan_association(Handle* h, int donor_level, const double* G, long
     for (int r = 0; r < R; r++) if (lml[r] > best) { best = lml[r]; rb = r; }
     const double v0 = scale[rb] * (1.0 - delta[rb]), v1 = scale[rb] * delta[rb], rho = h->rho[rb];
     const double info_host[4] = {rho, v0 * rho, v0 * (1.0 - rho), v1};
-    CRM_CUDA(cudaMemcpyAsync(info4, info_host, 32, cudaMemcpyHostToDevice, st));
-    if (out_null) CRM_CUDA(cudaMemcpyAsync(out_null, &best, 8, cudaMemcpyHostToDevice, st));
+    CRM_CHECK(upload_small(info4, info_host, 4, st));
+    if (out_null) CRM_CHECK(upload_small(out_null, &best, 1, st));
     double* xfix = h->scratch.as<double>() + R + 1;
-    CRM_CUDA(cudaMemcpyAsync(xfix, &xopt[rb], 8, cudaMemcpyHostToDevice, st));
+    CRM_CHECK(upload_small(xfix, &xopt[rb], 1, st));
     CRM_CUDA(cudaStreamSynchronize(st));   // host temporaries above go out of scope
     if (p == 0) return CRM_OK;
     return for_each_block(h, G, ldg, nullptr, 0, p, g_on_host, B, st, [&](const GBlock& k) -> int {
@@ -1180,7 +1258,7 @@ static int do_predict(Handle* h, int donor_level, const double* G, long long ldg
         CRM_CUDA(cudaGetLastError()); count_launch();
     }
     double* grid_dev = h->scratch.as<double>();
-    CRM_CUDA(cudaMemcpyAsync(grid_dev, h->rho.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
+    CRM_CHECK(upload_small(grid_dev, h->rho.data(), R, st));
     // ---- batches ----
     const double per_snp = 8.0 * ((double)kexp * ldH + 2.0 * h->ld2 + 2.0 * (double)kexp * mp + (double)R * (P + k0 + 8));
     long long B = std::max<long long>(16, std::min<long long>(p, (long long)(4.0e9 / per_snp)));
@@ -1279,6 +1357,7 @@ int crm_destroy(crm_handle_t h) {
         cudaStreamDestroy(h->impl.copy_stream);
         for (int i = 0; i < 2; i++) { cudaEventDestroy(h->impl.ev_copy[i]); cudaEventDestroy(h->impl.ev_done[i]); }
     }
+    for (cudaEvent_t e : h->impl.stage_events) cudaEventDestroy(e);
     delete h;
     return CRM_OK;
 }
@@ -1289,6 +1368,12 @@ int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t ldw, con
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     return do_setup(&h->impl, y, W, ldw, E0, lde0, E1, lde1, L, ldl, n, c, k0, k1, mL, rho_host, R, (cudaStream_t)stream);
+}
+
+int crm_stage_genotypes(crm_handle_t h, const double* G_host, int64_t ldg, int64_t rows, int64_t p, void* stream) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    return do_stage_genotypes(&h->impl, G_host, ldg, rows, p, (cudaStream_t)stream);
 }
 
 int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream) {

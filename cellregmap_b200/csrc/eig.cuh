@@ -8,7 +8,8 @@
 //                             derives the next one redundantly from the pivot row; the rank-2 update of a step is applied
 //                             while the next step's A v is accumulated, so the trailing matrix is read and written once per
 //                             column).  LAPACK dsytrd('L') storage (reflectors below the sub-diagonal, tau, d, e).
-//   4. crm_apply_q_kernel     back-transformation of the eigenvectors by the reflectors.
+//   4. back-transformation by cusolverDnDormtr (blocked reflectors, DMMA GEMMs): two hand-written one-warp-per-eigenvector
+//      kernels were measured at 10-20 ms against its 8 ms for 11 x 1020^2 and dropped.
 //   2. crm_tridiag_bisect     all eigenvalues by multisection on Sturm counts, one warp per eigenvalue.
 //   3. crm_tridiag_invit      eigenvectors by inverse iteration, one thread per eigenvalue (tridiagonal LU with partial
 //                             pivoting, random start vectors); orthogonality inside clusters is restored afterwards by a
@@ -21,7 +22,7 @@ namespace crm {
 constexpr int SY_MAX_GROUP = 16;      // CTAs per matrix (chosen at launch: SMs / batch, at most this)
 constexpr int SY_MAX_BATCH = 64;
 constexpr int SY_THREADS = 512;
-constexpr int SY_MAX_N = 2880;        // (EQ_COLS + 2) vectors of n doubles must fit the 227 KB of shared memory of a CTA
+constexpr int SY_MAX_N = 4096;        // four vectors of n doubles in shared memory
 
 struct SytrdArgs {
     double* A;            // [batch][nmax][nmax] slots; matrix b is n_of[b] x n_of[b] (leading dimension n_of[b]) at A + b * nmax * nmax
@@ -196,123 +197,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
     }
 }
 
-// ---- eigenvectors of A = Q Z: apply the Householder reflectors left in A by crm_sytrd_kernel, H_0 H_1 ... H_{n-3}, to EQ_COLS columns of
-// Z per CTA held in shared memory (one warp per column; the reflectors stream through L1/L2) ----
-constexpr int EQ_COLS = 8;
 struct EigSizes { int nmax, batch; int n_of[SY_MAX_BATCH]; };
-
-__global__ void __launch_bounds__(EQ_COLS * 32) crm_apply_q_kernel(const double* A_all, const double* tau_all, EigSizes sz, double* Z_all) {
-    extern __shared__ double eq_smem[];
-    const int b = blockIdx.y;
-    const int n = sz.n_of[b], nmax = sz.nmax;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-    constexpr int NT = EQ_COLS * 32, PRE = (SY_MAX_N + NT - 1) / NT;
-    const int t = blockIdx.x * EQ_COLS + warp;
-    if (blockIdx.x * EQ_COLS >= n) return;
-    const double* A = A_all + (size_t)b * nmax * nmax;
-    const double* tau = tau_all + (size_t)b * nmax;
-    double* z = eq_smem + (size_t)warp * nmax;
-    double* vs = eq_smem + (size_t)EQ_COLS * nmax;       // two reflector buffers: the next one is fetched while this one is applied
-    double* Zt = Z_all + (size_t)b * nmax * nmax + (size_t)t * n;
-    const bool live = t < n;
-    if (live) for (int i = lane; i < n; i += 32) z[i] = Zt[i];
-    if (n >= 3) { const double* v = A + (size_t)(n - 3) * n; for (int i = n - 1 + tid; i < n; i += NT) vs[i] = v[i]; }
-    __syncthreads();
-    for (int j = n - 3, cur = 0; j >= 0; j--, cur ^= 1) {
-        double pre[PRE];
-        if (j > 0) {                                       // reflector j - 1 occupies indices j + 1 .. n - 1
-            const double* vn = A + (size_t)(j - 1) * n;
-#pragma unroll
-            for (int u = 0; u < PRE; u++) { const int i = j + 1 + tid + NT * u; pre[u] = i < n ? vn[i] : 0.0; }
-        }
-        const double tj = tau[j];
-        if (live && tj != 0.0) {
-            const double* v = vs + (size_t)cur * nmax;     // v[i], i >= j + 2; v[j + 1] = 1 implied
-            double dot = 0.0;
-            for (int i = j + 2 + lane; i < n; i += 32) dot += v[i] * z[i];
-            dot = warp_sum(dot) + z[j + 1];
-            const double f = tj * dot;
-            __syncwarp();
-            for (int i = j + 2 + lane; i < n; i += 32) z[i] -= f * v[i];
-            if (lane == 0) z[j + 1] -= f;
-            __syncwarp();
-        }
-        if (j > 0) {
-            double* vw = vs + (size_t)(cur ^ 1) * nmax;
-#pragma unroll
-            for (int u = 0; u < PRE; u++) { const int i = j + 1 + tid + NT * u; if (i < n) vw[i] = pre[u]; }
-        }
-        __syncthreads();
-    }
-    if (live) for (int i = lane; i < n; i += 32) Zt[i] = z[i];
-}
-
-// The same with each warp's column of Z held in registers (n <= 32 * KREG): element i = 32 k + lane lives in zr[k] of that lane; only
-// the two reflector buffers stay in shared memory, so eight CTAs fit an SM.
-template <int KREG>
-__global__ void __launch_bounds__(EQ_COLS * 32) crm_apply_q_reg_kernel(const double* A_all, const double* tau_all, EigSizes sz, double* Z_all) {
-    extern __shared__ double eq_smem[];
-    const int b = blockIdx.y;
-    const int n = sz.n_of[b], nmax = sz.nmax;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-    constexpr int NT = EQ_COLS * 32, PRE = (32 * KREG + NT - 1) / NT;
-    const int t = blockIdx.x * EQ_COLS + warp;
-    if (blockIdx.x * EQ_COLS >= n) return;
-    const double* A = A_all + (size_t)b * nmax * nmax;
-    const double* tau = tau_all + (size_t)b * nmax;
-    double* vs = eq_smem;                                  // [2][32 * KREG]
-    double* Zt = Z_all + (size_t)b * nmax * nmax + (size_t)t * n;
-    const bool live = t < n;
-    double zr[KREG];
-#pragma unroll
-    for (int k = 0; k < KREG; k++) { const int i = 32 * k + lane; zr[k] = (live && i < n) ? Zt[i] : 0.0; }
-    for (int i = tid; i < 2 * 32 * KREG; i += NT) vs[i] = 0.0;
-    __syncthreads();
-    if (n >= 3 && tid == 0) vs[n - 1] = A[(size_t)(n - 3) * n + n - 1];
-    __syncthreads();
-    for (int j = n - 3, cur = 0; j >= 0; j--, cur ^= 1) {
-        double pre[PRE];
-        if (j > 0) {                                       // reflector j - 1 occupies indices j + 1 .. n - 1
-            const double* vn = A + (size_t)(j - 1) * n;
-#pragma unroll
-            for (int u = 0; u < PRE; u++) { const int i = j + 1 + tid + NT * u; pre[u] = i < n ? vn[i] : 0.0; }
-        }
-        const double tj = tau[j];
-        if (live && tj != 0.0) {
-            const double* v = vs + cur * (32 * KREG);      // v[i], i >= j + 2 (zero elsewhere is not guaranteed: masked below)
-            const int k0 = (j + 2) >> 5;                   // first 32-chunk that holds an index >= j + 2
-            double vr[KREG];
-            double dot = 0.0, dot2 = 0.0;
-#pragma unroll
-            for (int k = 0; k < KREG; k++) {
-                vr[k] = 0.0;
-                if (k >= k0) {
-                    const int i = 32 * k + lane;
-                    vr[k] = (i >= j + 2 && i < n) ? v[i] : 0.0;
-                    if (k & 1) dot2 += vr[k] * zr[k]; else dot += vr[k] * zr[k];
-                }
-            }
-            // z[j + 1] lives in lane (j + 1) & 31, slot (j + 1) >> 5: fold the implied v[j + 1] = 1 into that lane's v
-            const int kh = (j + 1) >> 5, lh = (j + 1) & 31;
-#pragma unroll
-            for (int k = 0; k < KREG; k++) if (k == kh && lane == lh) { vr[k] = 1.0; dot += zr[k]; }
-            dot = warp_sum(dot + dot2);
-            const double f = tj * dot;
-#pragma unroll
-            for (int k = 0; k < KREG; k++) if (k >= kh) zr[k] -= f * vr[k];
-        }
-        if (j > 0) {
-            double* vw = vs + (cur ^ 1) * (32 * KREG);
-#pragma unroll
-            for (int u = 0; u < PRE; u++) { const int i = j + 1 + tid + NT * u; if (i < n) vw[i] = pre[u]; }
-        }
-        __syncthreads();
-    }
-    if (live) {
-#pragma unroll
-        for (int k = 0; k < KREG; k++) { const int i = 32 * k + lane; if (i < n) Zt[i] = zr[k]; }
-    }
-}
 
 // ---- eigenvalues of symmetric tridiagonal matrices by multisection on Sturm counts ----
 constexpr int BS_LANES = 4;

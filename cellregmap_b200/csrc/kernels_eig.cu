@@ -183,16 +183,12 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
     eig_residual_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)batch), 128, 0, st>>>(d, e, V, tnorm, sz, rq, (unsigned long long*)quality);
     CRM_CUDA(cudaGetLastError()); count_launch();
     // 5. back-transformation: eigenvectors of A = Q Z, Q from the reflectors left in A
-    if (n <= 1024) {
-        crm_apply_q_reg_kernel<32><<<dim3((unsigned)((n + EQ_COLS - 1) / EQ_COLS), (unsigned)batch), EQ_COLS * 32, (size_t)2 * 1024 * 8, st>>>(A, tau, sz, V);
-        CRM_CUDA(cudaGetLastError()); count_launch();
-    } else {
-        static bool attr = false;
-        if (!attr) { CRM_CUDA(cudaFuncSetAttribute(crm_apply_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (EQ_COLS + 2) * SY_MAX_N * 8)); attr = true; }
-        crm_apply_q_kernel<<<dim3((unsigned)((n + EQ_COLS - 1) / EQ_COLS), (unsigned)batch), EQ_COLS * 32, (size_t)(EQ_COLS + 2) * n * 8, st>>>(A, tau, sz, V);
-        CRM_CUDA(cudaGetLastError()); count_launch();
+    CRM_SOLVER_(cusolverDnSetStream(solver, st));
+    for (int b = 0; b < batch; b++) {
+        const int nb = sz.n_of[b];
+        CRM_SOLVER_(cusolverDnDormtr(solver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, nb, nb, A + (size_t)b * nn, nb, tau + (size_t)b * n, V + (size_t)b * nn, nb,
+                                     lib_work, lib_lwork, info_dev + batch + b));
     }
-    (void)info_dev;
     return CRM_OK;
 }
 

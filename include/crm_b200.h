@@ -47,6 +47,14 @@ CRM_API int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t 
               const double* E1, int64_t lde1, const double* L, int64_t ldl, int64_t n, int c, int k0, int k1,
               int64_t mL, const double* rho_host, int R, void* stream);
 
+/* Start the host-to-device transfer of a host-resident genotype matrix (rows x p doubles, leading dimension ldg; pinned memory
+ * for an asynchronous copy) ahead of the scan: returns at once, the copy runs in column chunks on the handle's copy stream.  May be
+ * called right after crm_create, so that the transfer overlaps crm_setup; the next crm_scan_* call with g_on_host = 1 and the same
+ * (pointer, ldg, p) consumes the staged matrix block by block as the chunks arrive (one scan per staging).  A matrix larger than a
+ * quarter of the device memory is not staged (the scan streams it as usual).  The host array must stay alive and unchanged until that
+ * scan returns.  (Extension: the reference passes G to scan_interaction only, cellregmap/_cellregmap.py:317.) */
+CRM_API int crm_stage_genotypes(crm_handle_t h, const double* G_host, int64_t ldg, int64_t rows, int64_t p, void* stream);
+
 /* Replaces the tested-context matrix E0 (row-permuted contexts: idx_E of scan_interaction, _cellregmap.py:398-401). */
 CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream);
 

@@ -145,6 +145,22 @@ def test_host_and_device_genotypes_agree_bitwise(cuda_device):
     np.testing.assert_array_equal(np.concatenate([pv_a, pv_b]), pv_host)
 
 
+def test_staged_host_genotypes_agree_bitwise(cuda_device):
+    """run_interaction with a pinned host matrix starts the transfer under the set-up (crm_stage_genotypes); the scan then
+    consumes the staged copy: same bits as the streamed (pageable) and the device-resident routes."""
+    import torch
+    import cellregmap_b200 as crm
+    d = make_data(n=900, donors=60, k=6, p=1300, q=5, seed=12)
+    G_pinned = torch.from_numpy(d.G).pin_memory()
+    pv_staged, info_staged = crm.run_interaction(d.y, d.E, G_pinned, W=d.W, hK=d.hK)
+    pv_stream, info_stream = crm.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    pv_dev, info_dev = crm.run_interaction(d.y, d.E, torch.from_numpy(d.G).cuda(), W=d.W, hK=d.hK)
+    np.testing.assert_array_equal(pv_staged, pv_stream)
+    np.testing.assert_array_equal(pv_staged, pv_dev)
+    for k in info_staged:
+        np.testing.assert_array_equal(info_staged[k], info_dev[k])
+
+
 def test_association_scans(cuda_device):
     from cellregmap_b200 import run_association, run_association_fast
     from oracle import crm_port
