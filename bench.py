@@ -41,7 +41,7 @@ ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD = 465728855296 + 1766195200
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     # workload overrides (defaults = BASELINE configs[2]); used by the tests to run a tiny instance
@@ -122,7 +122,12 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.proc, self.lines, self.t_mark = gpu_index, None, [], 0.0
+
+    def mark(self):
+        """Samples from now on count (the sampler is started before the warm-up so that the start-up of nvidia-smi, which can
+        stall other CUDA work for hundreds of milliseconds, does not fall into the timed region)."""
+        self.t_mark = time.time()
 
     def start(self):
         try:
@@ -134,7 +139,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -142,7 +147,9 @@ class ClockSampler:
         self.proc.terminate()
         time.sleep(0.05)
         sm, smax, reasons = [], [], set()
-        for line in self.lines:
+        for t_line, line in self.lines:
+            if t_line < self.t_mark:
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -283,10 +290,12 @@ def run_b200_arm(a):
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall, r
 
-    for _ in range(a.warmup):
-        step_device()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(a.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    sampler.mark()
     api.PROFILE.update(on=True, rot_ms=0.0, rot_flops=0.0, rot_launches=0, int8_ms=0.0, int8_ops=0.0, int8_launches=0)
     launches0 = lib.crm_launch_count()
     ms_total, wall, res = timed(step_device, a.steps)

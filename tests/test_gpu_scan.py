@@ -161,6 +161,27 @@ def test_staged_host_genotypes_agree_bitwise(cuda_device):
         np.testing.assert_array_equal(info_staged[k], info_dev[k])
 
 
+def test_native_eigensolver_matches_cusolver_setup(cuda_device, tmp_path):
+    """K6 (batched set-up eigensolver, default) against the sequential cusolverDnDsyevd set-up (CRM_EIG=cusolver, read once per
+    process: run in a child process): same selected rho1, p-values to 1e-6 in log10, variance components to 1e-7."""
+    import json, os, subprocess, sys
+    import cellregmap_b200 as crm
+    d = make_data(n=800, donors=40, k=5, p=60, q=7, seed=21)
+    np.savez(tmp_path / "in.npz", y=d.y, E=d.E, G=d.G, W=d.W, hK=d.hK)
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import cellregmap_b200 as crm; z = np.load(%r); "
+            "pv, info = crm.run_interaction(z['y'], z['E'], z['G'], W=z['W'], hK=z['hK']); "
+            "print(json.dumps({'pv': pv.tolist(), 'rho1': info['rho1'].tolist(), 'e2': info['e2'].tolist(), 'eps2': info['eps2'].tolist()}))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "in.npz")))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CRM_EIG="cusolver"), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    ref = json.loads(out.stdout.strip().splitlines()[-1])
+    pv, info = crm.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    np.testing.assert_array_equal(info["rho1"], np.array(ref["rho1"]))
+    assert np.max(np.abs(np.log10(pv) - np.log10(np.array(ref["pv"])))) < 1e-6
+    np.testing.assert_allclose(info["e2"], np.array(ref["e2"]), rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(info["eps2"], np.array(ref["eps2"]), rtol=1e-7, atol=1e-12)
+
+
 def test_association_scans(cuda_device):
     from cellregmap_b200 import run_association, run_association_fast
     from oracle import crm_port
