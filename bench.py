@@ -36,13 +36,18 @@ FP64_TENSOR_PEAK_TFLOPS = 37.1
 # algorithmic bytes (G 8 GB + pre-expanded basis 17.2 GB + output 1.7 GB) -- operand panels are re-read through L2 by the
 # 13 272 CTAs; 395 GB/s = 6 % of the HBM peak, the kernel is bound by the FP64 tensor pipe (99 % active).
 ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD = 465728855296 + 1766195200
+# the same for one launch of oz_mma_kernel at the default workload (profiles/r01_ncu_oz_mma_kernel.txt): 320.7 GB read + 6.9 GB
+# written against 19.9 GB of algorithmic bytes (17.2 GB digit planes + 1.0 GB int8 dosages + 1.7 GB output) -- the 148 persistent
+# CTAs re-stream their operand panels through L2 (hit rate 64 %); 3.0 TB/s = 36 % of the HBM peak, the kernel is bound by the int8
+# tensor pipe under the power cap and by L2 -> SM bandwidth (47.7 B/clk/SM)
+OZ_MMA_DRAM_BYTES_DEFAULT_WORKLOAD = 320706872000 + 6889898000
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     # workload overrides (defaults = BASELINE configs[2]); used by the tests to run a tiny instance
     ap.add_argument("--cells", type=int, default=100000)
@@ -117,6 +122,27 @@ def add_causal_effects(gene, Gd_rank0, a):
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(device_index):
+    """Bind this process to the CPUs NVML reports as local to the GPU, so that the pinned host buffers of the e2e arm (first touch)
+    and the driver calls stay on the GPU's socket: a buffer on the far socket halves the host-to-device rate.  Best effort."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:       # NVML missing, no affinity information, restricted container ...
+        return None
+
+
 class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -130,6 +156,8 @@ class ClockSampler:
         self.t_mark = time.time()
 
     def start(self):
+        if os.environ.get("CRM_BENCH_NO_SAMPLER") == "1":       # A/B switch for the sampler's own footprint
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -224,6 +252,8 @@ def run_b200_arm(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    full_affinity = os.sched_getaffinity(0)
+    local_cpus = None if os.environ.get("CRM_BENCH_NO_PIN") == "1" else pin_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
@@ -322,7 +352,10 @@ def run_b200_arm(a):
             pass
         int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
         int8_tops = int8_ops / (int8_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": int8_tops / int8_peak, "traffic": None,
+        fused = os.environ.get("CRM_INT8_GEMM") != "lt" and os.environ.get("CRM_INT8_MMA") != "2cta"
+        roofline = {"bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": int8_tops / int8_peak,
+                    "traffic": OZ_MMA_DRAM_BYTES_DEFAULT_WORKLOAD if default_workload and fused else None,
+                    "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_oz_mma_kernel.txt)",
                     "kernel": ("cuBLASLt int8 GEMM + oz_combine_kernel" if os.environ.get("CRM_INT8_GEMM") == "lt" else
                                "oz_mma_kernel (hand-written tcgen05.mma kind::i8 + TMA, TMEM accumulators, fused fp64 recombination)") +
                               ": 8 digit planes of [Hx|Hx.E_j] against int8 dosages, the exact int8 split of the rotation",
@@ -416,7 +449,10 @@ def run_b200_arm(a):
     # ---- e2e through the public API with (pinned) host buffers ----
     e2e = None
     if not a.no_e2e:
-        G_h = torch.empty((a.cells, p), dtype=torch.float64, pin_memory=True)
+        try:
+            G_h = torch.empty((a.cells, p), dtype=torch.float64, pin_memory=True)
+        except RuntimeError:        # the host cannot page-lock 8 GB per rank: pageable memory (block-streamed transfer)
+            G_h = torch.empty((a.cells, p), dtype=torch.float64)
         G_h.copy_(G_d)
         y_h, W_h, E_h, hK_h = (torch.from_numpy(gene[key]).pin_memory() for key in ("y", "W", "E", "hK"))
         torch.cuda.synchronize()
@@ -435,9 +471,32 @@ def run_b200_arm(a):
         e2e = {"value": world * p / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(5 * p * 8),
                "ms_per_step": ms_e}
         assert np.array_equal(pv_h, res[5 * rank if world > 1 else 0].cpu().numpy()), "host and device paths disagree"
+        # the same call with the dosages stored as int8 on the host (8x less PCIe traffic); reported beside the float64 headline
+        try:
+            G_h8 = torch.empty((a.cells, p), dtype=torch.int8, pin_memory=True)
+        except RuntimeError:
+            G_h8 = torch.empty((a.cells, p), dtype=torch.int8)
+        G_h8.copy_(G_d)
         del G_h
 
+        def step_host8():
+            pv8, info8 = crm.run_interaction(y_h, E_h, G_h8, W=W_h, hK=hK_h)
+            if world > 1:
+                res8 = torch.from_numpy(np.stack([pv8, info8["rho1"], info8["e2"], info8["g2"], info8["eps2"]])).to(dev)
+                dist.all_gather_into_tensor(gathered, res8)
+            return pv8
+
+        step_host8()
+        ms_8, wall_8, pv_8 = timed(step_host8, a.steps)
+        ms_8 = max(ms_8, wall_8 * 1e3) / a.steps
+        assert np.array_equal(pv_8, pv_h), "int8 and float64 host genotypes disagree"
+        e2e["int8_host_genotypes"] = {"value": world * p / (ms_8 / 1e3), "unit": UNIT, "ms_per_step": ms_8,
+                                      "h2d_bytes_per_step": int(G_h8.numel() + sum(t.numel() * 8 for t in (y_h, W_h, E_h, hK_h))),
+                                      "note": "same API call with the genotype matrix stored as int8 on the host; not the headline e2e"}
+        del G_h8
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
+    os.sched_setaffinity(0, full_affinity)      # the CPU arm uses every host core again
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         ns = max(1, min(a.cpu_sample_snps, p))
@@ -451,6 +510,7 @@ def run_b200_arm(a):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": workload_name(a), "snps_per_gpu": p, "l2": "inputs (8 GB genotypes, 0.8 GB basis) far larger than L2",
+                           "host_affinity": ("%d CPUs local to the GPU (NVML)" % len(local_cpus)) if local_cpus else "unchanged",
                            "step": "constructor set-up + scan of the rank's SNP shard + all-gather of results"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "fp64_route": fp64_route,

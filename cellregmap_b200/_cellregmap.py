@@ -76,9 +76,20 @@ def get_L_values(hK, E):
 
 
 class _Genotypes:
-    """Genotype matrix handed to the library: device tensor, or host memory streamed in column blocks."""
+    """Genotype matrix handed to the library: device tensor, or host memory streamed in column blocks.  Host matrices of an
+    integer dtype (dosages stored as int8 ... int32) cross PCIe in their own width and are widened to float64 on the device
+    (8x less traffic for int8) when the float64 image fits a quarter of the device memory."""
 
     def __init__(self, G, device, n):
+        if not (isinstance(G, torch.Tensor) and G.is_cuda):
+            t = G if isinstance(G, torch.Tensor) else None
+            if t is None:
+                arr = np.asarray(G)
+                if arr.dtype.kind in "iub" and arr.dtype.itemsize <= 4 and arr.ndim == 2:
+                    t = torch.from_numpy(np.ascontiguousarray(arr if arr.dtype.kind != "b" else arr.astype(np.uint8)))
+            if t is not None and not t.is_floating_point() and t.ndim == 2 and t.element_size() <= 4 \
+                    and 8 * t.numel() <= 0.25 * torch.cuda.get_device_properties(device).total_memory:
+                G = t.to(device, non_blocking=True).to(torch.float64)
         if isinstance(G, torch.Tensor) and G.is_cuda:
             G = G.to(device=device, dtype=torch.float64)
             if G.ndim != 2 or G.stride(1) != 1 or G.stride(0) < G.shape[1]:
@@ -157,7 +168,8 @@ class CellRegMap:
         if _prefetch is not None and os.environ.get("CRM_NO_STAGE") != "1" and not (isinstance(_prefetch, torch.Tensor) and _prefetch.is_cuda) \
                 and getattr(_prefetch, "ndim", 0) == 2:
             geno = _Genotypes(_prefetch, dev, int(_prefetch.shape[0]))
-            _lib.call("crm_stage_genotypes", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, int(_prefetch.shape[0]), geno.p, _stream())
+            if geno.on_host:
+                _lib.call("crm_stage_genotypes", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, int(_prefetch.shape[0]), geno.p, _stream())
             self._prefetched = (_prefetch, geno)
         rho = np.ascontiguousarray(np.asarray(self._rho1, dtype=np.float64))
         mL = 0 if Lcat is None else int(Lcat.shape[1])

@@ -22,7 +22,7 @@ namespace crm {
 constexpr int SY_MAX_GROUP = 16;      // CTAs per matrix (chosen at launch: SMs / batch, at most this)
 constexpr int SY_MAX_BATCH = 64;
 constexpr int SY_THREADS = 512;
-constexpr int SY_MAX_N = 4096;        // four vectors of n doubles in shared memory
+constexpr int SY_MAX_N = 4096;        // five vectors of n doubles in shared memory
 
 struct SytrdArgs {
     double* A;            // [batch][nmax][nmax] slots; matrix b is n_of[b] x n_of[b] (leading dimension n_of[b]) at A + b * nmax * nmax
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
     double* w_prev = sy_smem + npad;
     double* v_cur = sy_smem + 2 * npad;
     double* buf = sy_smem + 3 * npad;    // staging: next column / A v
+    double* rowbuf = sy_smem + 4 * npad; // pivot row of the next step, fetched together with A v
     __shared__ double s_red[SY_THREADS / 32];
     __shared__ double s_scalar[4];       // beta, tau, scale of the current step; p'v
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SY_THREADS / 32;
@@ -81,12 +82,12 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
     // Column jn of the current matrix = its row jn (symmetry), which its owner finished updating in the previous pass; with the
     // pending rank-2 update of the previous step applied on the fly.  Every CTA of the group computes the same Householder vector
     // from it (same reduction tree), so no exchange is needed: d[jn], e[jn], tau[jn], v_cur.
-    auto next_column = [&](int jn) {
+    auto next_column = [&](int jn, bool staged) {
         const double vpj = v_prev[jn], wpj = w_prev[jn];
         const double* rowj = A + (size_t)jn * n;
         double nrm = 0.0;
         for (int c = jn + tid; c < n; c += SY_THREADS) {
-            const double x = __ldcg(&rowj[c]) - (vpj * w_prev[c] + wpj * v_prev[c]);
+            const double x = (staged ? rowbuf[c] : __ldcg(&rowj[c])) - (vpj * w_prev[c] + wpj * v_prev[c]);
             if (c == jn) { if (r == 0) dout[jn] = x; }
             else { buf[c] = x; if (c >= jn + 2) nrm += x * x; }
         }
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
         __syncthreads();
     };
 
-    next_column(0);
+    next_column(0, false);
     for (int j = 0; j + 1 < n; j++) {
         const double tau = s_scalar[1], beta = s_scalar[0];
         double* pbuf = (j & 1) ? pbuf_odd : pbuf_even;
@@ -177,7 +178,10 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
         if (tid == 0) { double s = 0.0; for (int w = 0; w < nwarps; w++) s += s_red[w]; part2[r] = s; }
         group_barrier(bar, epoch, (unsigned)SY_GROUP);          // the one exchange per column: A v and p'v
         if (warp == 0) { double s = lane < SY_GROUP ? __ldcg(&part2[lane]) : 0.0; s = warp_sum(s); if (lane == 0) s_scalar[3] = s; }
-        for (int i = j + 1 + tid; i < n; i += SY_THREADS) buf[i] = __ldcg(&pbuf[i]);
+        {   // A v and the pivot row of the next step (final since the pass above) in one round trip to L2
+            const double* rown = A + (size_t)(j + 1) * n;
+            for (int i = j + 1 + tid; i < n; i += SY_THREADS) { const double pi = __ldcg(&pbuf[i]), ri = __ldcg(&rown[i]); buf[i] = pi; rowbuf[i] = ri; }
+        }
         __syncthreads();
         // w = tau p - (tau^2 p'v / 2) v, identical in every CTA; roll the vectors
         const double half = 0.5 * tau * tau * s_scalar[3];
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
             for (int i = j + 2 + tid; i < n; i += SY_THREADS) A[(size_t)j * n + i] = v_prev[i];
             if (tid == 0) A[(size_t)j * n + j + 1] = beta;
         }
-        next_column(j + 1);
+        next_column(j + 1, true);
     }
 }
 

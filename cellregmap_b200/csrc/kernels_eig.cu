@@ -118,7 +118,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
     // 1. tridiagonalisation: every group of SY_GROUP CTAs must be resident -> cooperative launch
     {
         static bool attr = false;
-        if (!attr) { CRM_CUDA(cudaFuncSetAttribute(crm_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (SY_MAX_N + 1) * 8)); attr = true; }
+        if (!attr) { CRM_CUDA(cudaFuncSetAttribute(crm_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * (SY_MAX_N + 1) * 8)); attr = true; }
         static int sms = 0;
         if (!sms) { int dev = 0; CRM_CUDA(cudaGetDevice(&dev)); CRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
         SytrdArgs sa{};
@@ -126,7 +126,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
         for (int b = 0; b < batch; b++) sa.n_of[b] = sz.n_of[b];
         sa.A = A; sa.nmax = n; sa.batch = batch; sa.d = d; sa.e = e; sa.tau = tau; sa.xbuf = xbuf; sa.pbuf = pbuf; sa.part = part; sa.bar = bar;
         void* params[] = {&sa};
-        CRM_CUDA(cudaLaunchCooperativeKernel((const void*)crm_sytrd_kernel, dim3((unsigned)(batch * sa.group)), dim3(SY_THREADS), params, (size_t)4 * (n + 1) * 8, st));
+        CRM_CUDA(cudaLaunchCooperativeKernel((const void*)crm_sytrd_kernel, dim3((unsigned)(batch * sa.group)), dim3(SY_THREADS), params, (size_t)5 * (n + 1) * 8, st));
         count_launch();
     }
     // 2. eigenvalues

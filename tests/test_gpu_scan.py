@@ -161,6 +161,20 @@ def test_staged_host_genotypes_agree_bitwise(cuda_device):
         np.testing.assert_array_equal(info_staged[k], info_dev[k])
 
 
+def test_integer_dtype_genotypes(cuda_device):
+    """Dosages stored as int8 / int16 / uint8 on the host (numpy or pinned torch) give the bits of the float64 matrix."""
+    import torch
+    import cellregmap_b200 as crm
+    d = make_data(n=600, donors=40, k=5, p=150, q=5, seed=13)
+    pv_ref, info_ref = crm.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    for G in (d.G.astype(np.int8), d.G.astype(np.int16), d.G.astype(np.uint8), torch.from_numpy(d.G.astype(np.int8)).pin_memory()):
+        pv, info = crm.run_interaction(d.y, d.E, G, W=d.W, hK=d.hK)
+        np.testing.assert_array_equal(pv, pv_ref)
+        np.testing.assert_array_equal(info["rho1"], info_ref["rho1"])
+    pa_ref = crm.run_association(d.y, d.W, d.E, d.G, hK=d.hK)[0]
+    np.testing.assert_array_equal(crm.run_association(d.y, d.W, d.E, d.G.astype(np.int8), hK=d.hK)[0], pa_ref)
+
+
 def test_native_eigensolver_matches_cusolver_setup(cuda_device, tmp_path):
     """K6 (batched set-up eigensolver, default) against the sequential cusolverDnDsyevd set-up (CRM_EIG=cusolver, read once per
     process: run in a child process): same selected rho1, p-values to 1e-6 in log10, variance components to 1e-7."""
