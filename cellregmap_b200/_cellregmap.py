@@ -75,6 +75,23 @@ def get_L_values(hK, E):
     return [us[:, i][:, None] * hK for i in range(us.shape[1])]
 
 
+_WIDEN_CACHE = {}
+
+
+def _widen_on_device(t, device):
+    """float64 image of an integer host matrix: the narrow data cross PCIe, the widening runs on the device into a buffer that is
+    kept for the next call of the same shape (re-allocating 8 bytes per dosage per call costs more than the transfer; work on the
+    buffer is ordered by the current stream)."""
+    key = (device.index, tuple(t.shape))
+    buf = _WIDEN_CACHE.get(key)
+    if buf is None:
+        _WIDEN_CACHE.clear()                      # at most one matrix is kept
+        buf = torch.empty(tuple(t.shape), dtype=torch.float64, device=device)
+        _WIDEN_CACHE[key] = buf
+    buf.copy_(t.to(device, non_blocking=True))
+    return buf
+
+
 class _Genotypes:
     """Genotype matrix handed to the library: device tensor, or host memory streamed in column blocks.  Host matrices of an
     integer dtype (dosages stored as int8 ... int32) cross PCIe in their own width and are widened to float64 on the device
@@ -89,7 +106,7 @@ class _Genotypes:
                     t = torch.from_numpy(np.ascontiguousarray(arr if arr.dtype.kind != "b" else arr.astype(np.uint8)))
             if t is not None and not t.is_floating_point() and t.ndim == 2 and t.element_size() <= 4 \
                     and 8 * t.numel() <= 0.25 * torch.cuda.get_device_properties(device).total_memory:
-                G = t.to(device, non_blocking=True).to(torch.float64)
+                G = _widen_on_device(t, device)
         if isinstance(G, torch.Tensor) and G.is_cuda:
             G = G.to(device=device, dtype=torch.float64)
             if G.ndim != 2 or G.stride(1) != 1 or G.stride(0) < G.shape[1]:
