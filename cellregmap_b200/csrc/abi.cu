@@ -98,7 +98,7 @@ struct DevBuf {
 
 // Creating a cuSOLVER handle costs tens of milliseconds, so one context per device lives in a process-wide pool and is
 // reused by every model object (set-up calls are serialised by the pool mutex).
-struct EigCtx { cusolverDnHandle_t solver = nullptr; cusolverDnParams_t params = nullptr; cublasHandle_t blas = nullptr; DevBuf mat, val, work, vec, ws, quality; std::vector<char> host_work; };
+struct EigCtx { cusolverDnHandle_t solver = nullptr; cublasHandle_t blas = nullptr; DevBuf mat, val, work, vec, ws, quality; std::vector<char> host_work; };
 struct EigPool { std::mutex mu; std::vector<EigCtx> ctx; };
 static EigPool g_eig_pool[16];
 
@@ -618,16 +618,13 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     int* info_dev = h->devinfo.as<int>();
     int* rank_dev = h->devinfo.as<int>() + R;
     const int tall = n > m ? 1 : 0;
-    // CRM_EIG_BATCHED=1 puts all grid points into one cusolverDnXsyevBatched call: 70 ms instead of 134 ms for
-    // 11 x 1020^2 on B200, but its first call in a process costs 54 s of one-time initialisation, so it is opt-in.
-    static const bool batched = [] { const char* v = getenv("CRM_EIG_BATCHED"); return v && atoi(v) != 0; }();
     // All grid points go through the batched solver of eig.cuh (tridiagonalisation of every matrix at once on its own group of
     // SMs, multisection + inverse iteration + re-orthonormalisation, back-transformation): 33 ms instead of 122 ms for 11 problems
     // of size 1020 (profiles/r01_eig_bench.txt).  The sequential cusolverDnDsyevd calls remain as the fall-back when a size is out
     // of range or the residual / orthogonality check of a matrix fails, and as the reference point (CRM_EIG=cusolver).
     static const bool native = [] { const char* v = getenv("CRM_EIG"); return !(v && !strcmp(v, "cusolver")); }();
     bool native_done = false;
-    if (native && !batched && m >= 2 && m <= 4096 && R <= 64) {
+    if (native && m >= 2 && m <= 4096 && R <= 64) {
         std::vector<int> n_of(R), a0_of(R);
         bool ok = true;
         for (int r = 0; r < R; r++) {
@@ -673,29 +670,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
             }
         }
     }
-    if (native_done) {
-    } else if (batched) {
-        CRM_CHECK(e.mat.reserve((size_t)R * m * m * 8));
-        CRM_CHECK(e.val.reserve((size_t)R * m * 8));
-        if (!e.params) CRM_SOLVER(cusolverDnCreateParams(&e.params));
-        for (int r = 0; r < R; r++) {
-            scale_gram_kernel<<<blocks_for((long long)m * m, 256), 256, 0, st>>>(h->gram.as<double>(), ldH, 0, m, k1, h->rho[r], e.mat.as<double>() + (size_t)r * m * m);
-            CRM_CUDA(cudaGetLastError()); count_launch();
-        }
-        size_t ws_dev = 0, ws_host = 0;
-        CRM_SOLVER(cusolverDnXsyevBatched_bufferSize(e.solver, e.params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, CUDA_R_64F, e.mat.ptr, m, CUDA_R_64F,
-                                                     e.val.ptr, CUDA_R_64F, &ws_dev, &ws_host, R));
-        CRM_CHECK(e.work.reserve(ws_dev + 256));
-        if (e.host_work.size() < ws_host + 16) e.host_work.resize(ws_host + 16);
-        CRM_SOLVER(cusolverDnXsyevBatched(e.solver, e.params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, CUDA_R_64F, e.mat.ptr, m, CUDA_R_64F, e.val.ptr,
-                                          CUDA_R_64F, e.work.ptr, ws_dev, e.host_work.data(), ws_host, info_dev, R));
-        for (int r = 0; r < R; r++) {
-            build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
-                e.mat.as<double>() + (size_t)r * m * m, e.val.as<double>() + (size_t)r * m, m, mp, 0, m, k1, h->rho[r], tall, h->S.as<double>() + (long long)r * mp,
-                h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
-            CRM_CUDA(cudaGetLastError()); count_launch();
-        }
-    } else {
+    if (!native_done) {
         for (int r = 0; r < R; r++) {
             // rho = 1 / rho = 0 zero one diagonal block of D: only the surviving block is decomposed
             int a0 = 0, ms = m;
