@@ -17,6 +17,18 @@ namespace crm {
 constexpr int OZ_TILE = 32;
 
 
+
+// One balanced base-128 digit of x (|x| <= 1/2): d = rint(128 x), x <- 128 x - d.  rint and the float -> int conversion are both
+// taken from one addition of 1.5 * 2^52 (round-to-nearest-even puts the integer into the low mantissa bits): conversion
+// instructions run at a fraction of the FP64 add rate, and this loop is the whole cost of the digit planes.
+__device__ __forceinline__ int oz_next_digit(double& x) {
+    const double t = x * 128.0;                                  // exact
+    const double s = __dadd_rn(t, 6755399441055744.0);
+    const int q = __double2loint(s);
+    x = t - __dadd_rn(s, -6755399441055744.0);                   // exact: |t - d| <= 1/2
+    return q;
+}
+
 // exponent e with |x| < 2^e for the largest |x| of each column of HxE = Eext[:, j] * Hx[:, a]  (col = j * ldH + a);
 // expo must be pre-filled with OZ_EXP_EMPTY; rows are split over blockIdx.z and merged with atomicMax
 __global__ void oz_column_exponent_kernel(const double* Hx, int ldH, const double* Eext, int epitch, long long n, int* expo) {
@@ -54,15 +66,16 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* Hx, int ldH
             if (a < ldH && i < Kp) {
                 const long long col = (long long)j * ldH + a;
                 const int e = expo[col];
+                const double scale = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(1.0, -(e + 1));     // exact power of two
                 double x[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) x[u] = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(tile[4 * tx + u][r], -(e + 1));   // |x| < 1/2
+                for (int u = 0; u < 4; u++) x[u] = tile[4 * tx + u][r] * scale;               // |x| < 1/2
 #pragma unroll
                 for (int t = 0; t < OZ_SLICES; t++) {
                     char4 q;
                     signed char* qq = reinterpret_cast<signed char*>(&q);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { x[u] *= 128.0; const double d = rint(x[u]); x[u] -= d; qq[u] = (signed char)(int)d; }
+                    for (int u = 0; u < 4; u++) qq[u] = (signed char)oz_next_digit(x[u]);
                     *reinterpret_cast<char4*>(A8 + (long long)t * Mp * Kp + col * Kp + i) = q;
                 }
             }
@@ -95,15 +108,16 @@ __global__ void __launch_bounds__(256) oz_matrix_slice_kernel(const double* X, l
         const int a = a0 + r; const long long i = i0 + 4 * tx;
         if (a < cols && i < Kp) {
             const int e = expo[a];
+            const double scale = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(1.0, -(e + 1));
             double x[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) x[u] = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(tile[4 * tx + u][r], -(e + 1));
+            for (int u = 0; u < 4; u++) x[u] = tile[4 * tx + u][r] * scale;
 #pragma unroll
             for (int t = 0; t < OZ_SLICES; t++) {
                 char4 q;
                 signed char* qq = reinterpret_cast<signed char*>(&q);
 #pragma unroll
-                for (int u = 0; u < 4; u++) { x[u] *= 128.0; const double d = rint(x[u]); x[u] -= d; qq[u] = (signed char)(int)d; }
+                for (int u = 0; u < 4; u++) qq[u] = (signed char)oz_next_digit(x[u]);
                 *reinterpret_cast<char4*>(P8 + (long long)t * Mp * Kp + (long long)a * Kp + i) = q;
             }
         }
