@@ -50,17 +50,25 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _economic_svd(E):
-    """numpy_sugar.linalg.economic_svd on a torch tensor: thin SVD, singular values >= sqrt(eps)."""
-    U, S, Vh = torch.linalg.svd(E, full_matrices=False)
+def _scaled_left_vectors(E):
+    """U S of the thin SVD of the tall matrix E with singular values >= sqrt(eps) (numpy_sugar.linalg.economic_svd), up to the sign
+    of each column.  Through the triangular factor: E = Q R, R = Ur S V' (k x k, on the host: one 3 KB read-back) and U S = E V.
+    torch.linalg.svd on the device runs an iterative cuSOLVER routine with dozens of small launches and host round trips per call
+    (25-45 ms of an otherwise 210 ms run_interaction); the QR route is two launches, one tiny SVD and one thin GEMM."""
+    if E.shape[0] < E.shape[1]:
+        U, S, _ = torch.linalg.svd(E, full_matrices=False)
+        keep = S >= EPS_SMALL
+        return U[:, keep] * S[keep]
+    R = torch.linalg.qr(E, mode="r").R
+    _, S, Vh = np.linalg.svd(R.cpu().numpy())
     keep = S >= EPS_SMALL
-    return U[:, keep], S[keep], Vh[keep, :]
+    V = torch.from_numpy(np.ascontiguousarray(Vh[keep, :].T)).to(E.device)
+    return E @ V
 
 
 def _L_concat(hK, E):
     """[L_1 | ... | L_k] with L_i = diag(U_i S_i) hK  (reference get_L_values, :533-545), one device tensor."""
-    U, S, _ = _economic_svd(E)
-    us = U * S
+    us = _scaled_left_vectors(E)
     n = hK.shape[0]
     return (us[:, :, None] * hK[:, None, :]).reshape(n, us.shape[1] * hK.shape[1]).contiguous()
 
