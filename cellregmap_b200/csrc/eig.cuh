@@ -8,12 +8,12 @@
 //                             derives the next one redundantly from the pivot row; the rank-2 update of a step is applied
 //                             while the next step's A v is accumulated, so the trailing matrix is read and written once per
 //                             column).  LAPACK dsytrd('L') storage (reflectors below the sub-diagonal, tau, d, e).
-//   4. back-transformation by cusolverDnDormtr (blocked reflectors, DMMA GEMMs): two hand-written one-warp-per-eigenvector
-//      kernels were measured at 10-20 ms against its 8 ms for 11 x 1020^2 and dropped.
-//   2. crm_tridiag_bisect     all eigenvalues by multisection on Sturm counts, one warp per eigenvalue.
+//   2. crm_tridiag_bisect     all eigenvalues by multisection on Sturm counts, BS_LANES lanes per eigenvalue.
 //   3. crm_tridiag_invit      eigenvectors by inverse iteration, one thread per eigenvalue (tridiagonal LU with partial
-//                             pivoting, random start vectors); orthogonality inside clusters is restored afterwards by a
-//                             Cholesky-QR pass on all vectors (kernels_eig.cu).
+//                             pivoting, random start vectors); orthogonality inside clusters of close eigenvalues is restored
+//                             afterwards on all vectors together (kernels_eig.cu: Gram matrix, first-order or Cholesky-QR step).
+//   4. back-transformation    cusolverDnDormtr on the reflectors of step 1 (blocked, DMMA GEMMs; 4 ms for 11 x 1020^2 -- two
+//                             hand-written one-warp-per-eigenvector kernels were measured at 10-20 ms and dropped).
 #pragma once
 #include "common.cuh"
 
