@@ -18,7 +18,7 @@ def qscov_dot(Q0, S0, a, b, v):
     """(a K + b I) v with K = Q0 S0 Q0'.  _math.py:53-56."""
     t = Q0.T @ v
     t = (S0 * t.T).T
-    return a * (Q0 @ t) + b * v
+    return (a * Q0) @ t + b * v          # same association as the reference: a * Q0 @ (...) binds as (a * Q0) @ (...)
 
 
 def qscov_solve(Q0, S0, a, b, v):
