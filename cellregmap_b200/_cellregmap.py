@@ -83,58 +83,59 @@ def get_L_values(hK, E):
     return [us[:, i][:, None] * hK for i in range(us.shape[1])]
 
 
-_WIDEN_CACHE = {}
-
-
-def _widen_on_device(t, device):
-    """float64 image of an integer host matrix: the narrow data cross PCIe, the widening runs on the device into a buffer that is
-    kept for the next call of the same shape (re-allocating 8 bytes per dosage per call costs more than the transfer; work on the
-    buffer is ordered by the current stream)."""
-    key = (device.index, tuple(t.shape))
-    buf = _WIDEN_CACHE.get(key)
-    if buf is None:
-        _WIDEN_CACHE.clear()                      # at most one matrix is kept
-        buf = torch.empty(tuple(t.shape), dtype=torch.float64, device=device)
-        _WIDEN_CACHE[key] = buf
-    buf.copy_(t.to(device, non_blocking=True))
-    return buf
+# element types of genotype matrices understood by the C ABI (include/crm_b200.h: CRM_G_*)
+_G_DTYPES = {np.dtype(np.float64): 0, np.dtype(np.int8): 1, np.dtype(np.uint8): 2, np.dtype(np.bool_): 2, np.dtype(np.int16): 3,
+             np.dtype(np.int32): 4, np.dtype(np.float32): 5, np.dtype(np.int64): 6}
 
 
 class _Genotypes:
-    """Genotype matrix handed to the library: device tensor, or host memory streamed in column blocks.  Host matrices of an
-    integer dtype (dosages stored as int8 ... int32) cross PCIe in their own width and are widened to float64 on the device
-    (8x less traffic for int8) when the float64 image fits a quarter of the device memory."""
+    """Genotype matrix as handed to the library: pointer, leading dimension (in elements), element type, placement.
 
-    def __init__(self, G, device, n):
-        if not (isinstance(G, torch.Tensor) and G.is_cuda):
-            t = G if isinstance(G, torch.Tensor) else None
-            if t is None:
-                arr = np.asarray(G)
-                if arr.dtype.kind in "iub" and arr.dtype.itemsize <= 4 and arr.ndim == 2:
-                    t = torch.from_numpy(np.ascontiguousarray(arr if arr.dtype.kind != "b" else arr.astype(np.uint8)))
-            if t is not None and not t.is_floating_point() and t.ndim == 2 and t.element_size() <= 4 \
-                    and 8 * t.numel() <= 0.25 * torch.cuda.get_device_properties(device).total_memory:
-                G = _widen_on_device(t, device)
+    Device tensors are used in place (float64, or int8 dosages; other types are converted on the device).  Host matrices -- numpy
+    arrays or CPU tensors, pageable or pinned, float64 like the reference's `asarray(G, float)` or any integer / float32 storage --
+    are passed as they are, including column slices of a larger row-major array: the library converts them to int8 dosage blocks with
+    its host threads (or moves pinned float64 by DMA) while the device works, see crm_stage_genotypes_typed."""
+
+    def __init__(self, G, device, n, force_float64=False):
         if isinstance(G, torch.Tensor) and G.is_cuda:
-            G = G.to(device=device, dtype=torch.float64)
-            if G.ndim != 2 or G.stride(1) != 1 or G.stride(0) < G.shape[1]:
-                G = G.contiguous()
-            self.keep, self.on_host = G, 0
-            self.ptr, self.ld = G.data_ptr(), G.stride(0) if G.shape[0] > 1 else G.shape[1]
-        else:
-            if isinstance(G, torch.Tensor):
+            G = G.to(device=device)
+            if G.dtype != torch.int8 or force_float64:
                 G = G.to(dtype=torch.float64)
-                if G.ndim != 2 or not G.is_contiguous():
-                    G = G.contiguous()
-                self.ptr = G.data_ptr()
-            else:
-                G = np.ascontiguousarray(np.asarray(G, dtype=np.float64))
-                self.ptr = G.ctypes.data
-            self.keep, self.on_host = G, 1
-            self.ld = G.shape[1] if G.ndim == 2 else 1
-        assert G.ndim == 2, "G must be n x p"
-        assert G.shape[0] == n, "G must have one row per sample"
-        self.p = int(G.shape[1])
+            if G.ndim == 2 and (G.stride(1) != 1 or G.stride(0) < G.shape[1]):
+                G = G.contiguous()
+            assert G.ndim == 2, "G must be n x p"
+            self.keep, self.on_host = G, 0
+            self.ptr, self.ld = G.data_ptr(), (G.stride(0) if G.shape[0] > 1 else G.shape[1])
+            self.dtype = 1 if G.dtype == torch.int8 else 0
+        else:
+            arr = G.detach().numpy() if isinstance(G, torch.Tensor) else np.asarray(G)
+            assert arr.ndim == 2, "G must be n x p"
+            if arr.dtype not in _G_DTYPES or force_float64:
+                arr = np.asarray(arr, dtype=np.float64)
+            item = arr.dtype.itemsize
+            if arr.shape[1] > 0 and arr.shape[0] > 1 and (arr.strides[1] != item or arr.strides[0] % item or arr.strides[0] < arr.shape[1] * item):
+                arr = np.ascontiguousarray(arr)
+            elif arr.shape[1] > 0 and arr.shape[0] <= 1 and arr.strides[1] != item:
+                arr = np.ascontiguousarray(arr)
+            self.keep = (G, arr)                  # the caller's object owns the memory
+            self.on_host = 1
+            self.ptr = arr.ctypes.data
+            self.ld = arr.strides[0] // item if arr.shape[0] > 1 else arr.shape[1]
+            self.dtype = _G_DTYPES[arr.dtype]
+            self.host_array = arr
+        shape = self.keep.shape if not self.on_host else self.keep[1].shape
+        assert shape[0] == n, "G must have one row per sample"
+        self.p = int(shape[1])
+        self.rows = int(shape[0])
+
+    def flags(self, donor_level=False):
+        return self.on_host | (2 if donor_level else 0) | (self.dtype << 4)
+
+    def rows_permuted(self, idx, device):
+        """G[idx, :] for the permuted tested design (float64; a rare path)."""
+        if self.on_host:
+            return _Genotypes(np.ascontiguousarray(np.asarray(self.host_array, dtype=np.float64)[np.asarray(idx), :]), device, self.rows)
+        return _Genotypes(self.keep[torch.as_tensor(np.asarray(idx), device=device), :].to(torch.float64).contiguous(), device, self.rows)
 
 
 class CellRegMap:
@@ -163,10 +164,6 @@ class CellRegMap:
                 assert n == L.shape[0]
             n_blocks = len(blocks)
             Lcat = torch.cat(blocks, dim=1).contiguous() if n_blocks else None
-        if not bool(torch.isfinite(self._y).all()):
-            raise ValueError("There are non-finite values in the outcome.")          # glimix_core.lmm.LMM
-        if not bool(torch.isfinite(self._W).all()):
-            raise ValueError("There are non-finite values in the covariates matrix.")
         assert self._W.ndim == 2
         assert self._E0.ndim == 2
         assert self._E1.ndim == 2
@@ -184,6 +181,13 @@ class CellRegMap:
         else:
             self._rho1 = np.linspace(0, 1, 11)           # reference :117-131 (hK ignored)
         self._L = Lcat
+        # one read-back for all finiteness checks.  y and W: the ValueErrors of glimix_core.lmm.LMM; E, E1, Ls/hK: the reference fails
+        # inside LAPACK (SVD of the half-covariance) instead
+        checked = [("the outcome", self._y), ("the covariates matrix", self._W), ("E", self._E0), ("E1", self._E1)] + ([("Ls / hK", Lcat)] if Lcat is not None else [])
+        finite = torch.stack([torch.isfinite(t).all() for _, t in checked]).cpu().numpy()
+        for ok, (name, _) in zip(finite, checked):
+            if not ok:
+                raise ValueError(f"There are non-finite values in {name}.")
         self._handle = ctypes.c_void_p(0)
         torch.cuda.set_device(dev)
         _lib.call("crm_create", ctypes.byref(self._handle), dev.index if dev.index is not None else torch.cuda.current_device())
@@ -193,8 +197,10 @@ class CellRegMap:
         if _prefetch is not None and os.environ.get("CRM_NO_STAGE") != "1" and not (isinstance(_prefetch, torch.Tensor) and _prefetch.is_cuda) \
                 and getattr(_prefetch, "ndim", 0) == 2:
             geno = _Genotypes(_prefetch, dev, int(_prefetch.shape[0]))
-            if geno.on_host:
-                _lib.call("crm_stage_genotypes", self._handle, ctypes.c_void_p(geno.ptr), geno.ld, int(_prefetch.shape[0]), geno.p, _stream())
+            if geno.on_host and geno.p > 0:
+                width = int(self._E1.shape[1]) + (0 if Lcat is None else int(Lcat.shape[1])) + 1 + int(self._W.shape[1])
+                basis_cols = (1 + int(self._E0.shape[1])) * (width + (width & 1))
+                _lib.call("crm_stage_genotypes_typed", self._handle, ctypes.c_void_p(geno.ptr), geno.dtype, geno.ld, geno.rows, geno.p, basis_cols, _stream())
             self._prefetched = (_prefetch, geno)
         rho = np.ascontiguousarray(np.asarray(self._rho1, dtype=np.float64))
         mL = 0 if Lcat is None else int(Lcat.shape[1])
@@ -243,10 +249,10 @@ class CellRegMap:
         if donor_index is None:
             if self._prefetched is not None and self._prefetched[0] is G:       # staged by the constructor: same host buffer
                 geno, self._prefetched = self._prefetched[1], None
-                assert geno.keep.shape[0] == self.n_samples, "G must have one row per sample"
+                assert geno.rows == self.n_samples, "G must have one row per sample"
             else:
                 geno = _Genotypes(G, dev, self.n_samples)
-            return geno, geno.on_host
+            return geno, geno.flags()
         idx = torch.as_tensor(np.asarray(donor_index.cpu() if isinstance(donor_index, torch.Tensor) else donor_index), device=dev).long().flatten()
         assert idx.numel() == self.n_samples, "donor_index needs one entry per cell"
         d = int(G.shape[0])
@@ -262,7 +268,7 @@ class CellRegMap:
             self._donor_key = key
             self._donor_idx = idx
         geno = _Genotypes(G, dev, d)
-        return geno, geno.on_host | 2
+        return geno, geno.flags(donor_level=True)
 
     def _expand(self, G, donor_index):
         idx = np.asarray(donor_index.cpu() if isinstance(donor_index, torch.Tensor) else donor_index).ravel()
@@ -300,12 +306,11 @@ class CellRegMap:
             keep += [ridx, ov0, ov1]
             diag.ov_rho_idx, diag.ov_v0, diag.ov_v1 = ridx.data_ptr(), ov0.data_ptr(), ov1.data_ptr()
         gtest = None
-        if idx_G is not None:      # row-permuted genotypes in the tested design only (reference :410-413)
-            if geno.on_host:
-                src = geno.keep if isinstance(geno.keep, np.ndarray) else geno.keep.numpy()
-                gtest = _Genotypes(np.ascontiguousarray(src[np.asarray(idx_G), :]), dev, self.n_samples)
-            else:
-                gtest = _Genotypes(geno.keep[torch.as_tensor(np.asarray(idx_G), device=dev), :].contiguous(), dev, self.n_samples)
+        if idx_G is not None:      # row-permuted genotypes in the tested design only (reference :410-413); both designs in float64
+            if geno.dtype != 0:
+                geno = _Genotypes(geno.host_array if geno.on_host else geno.keep, dev, self.n_samples, force_float64=True)
+                gflags = geno.flags()
+            gtest = geno.rows_permuted(idx_G, dev)
         if idx_E is not None:      # row-permuted contexts in the tested design only (reference :398-401)
             idx = torch.as_tensor(np.asarray(idx_E), device=dev)
             Etest = self._E0[idx, :].contiguous()
@@ -389,12 +394,10 @@ class CellRegMap:
 
 def lrt_pvalues(null_lml, alt_lmls, dof=1):
     """Likelihood-ratio p-values (reference :443-469)."""
-    if dof != 1:
-        raise NotImplementedError("only dof=1 is used by the reference path")
     dev = _device()
     alt = _to_dev(np.atleast_1d(np.asarray(alt_lmls, float)), dev)
     pv = torch.empty_like(alt)
-    _lib.call("crm_lrt_pvalues", _ptr(alt), float(null_lml), alt.numel(), _ptr(pv), _stream())
+    _lib.call("crm_lrt_pvalues_dof", _ptr(alt), float(null_lml), alt.numel(), float(dof), _ptr(pv), _stream())
     return pv.cpu().numpy()
 
 

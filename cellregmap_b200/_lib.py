@@ -33,6 +33,7 @@ SIGNATURES = {
     "crm_last_error": (ctypes.c_char_p, []),
     "crm_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     "crm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "crm_trim_pool": (ctypes.c_int, [ctypes.c_int]),
     "crm_setup": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int64,
                                  c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                  ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_double), ctypes.c_int,
@@ -54,6 +55,9 @@ SIGNATURES = {
                                    ctypes.POINTER(ctypes.c_int64)]),
     "crm_profile_int8": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "crm_stage_genotypes": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "crm_stage_genotypes_typed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                 ctypes.c_void_p]),
+    "crm_host_threads": (ctypes.c_int, []),
     "crm_eigh_batched": (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),
     "crm_int8_split_gemm": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
@@ -73,6 +77,7 @@ SIGNATURES = {
     "crm_liu_params": (ctypes.c_int, [c_double_p, c_double_p, c_int32_p, ctypes.c_int, ctypes.c_int64, c_double_p, ctypes.c_void_p]),
     "crm_qmin": (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int64, c_double_p, ctypes.c_void_p]),
     "crm_lrt_pvalues": (ctypes.c_int, [c_double_p, ctypes.c_double, ctypes.c_int64, c_double_p, ctypes.c_void_p]),
+    "crm_lrt_pvalues_dof": (ctypes.c_int, [c_double_p, ctypes.c_double, ctypes.c_int64, ctypes.c_double, c_double_p, ctypes.c_void_p]),
 }
 
 _lib = None
@@ -99,7 +104,10 @@ def load():
 def check(status):
     if status != 0:
         msg = load().crm_last_error()
-        raise CrmError(status, msg.decode("utf-8", "replace") if msg else "")
+        text = msg.decode("utf-8", "replace") if msg else ""
+        if status == -4:       # CRM_ERR_NONFINITE: glimix_core.lmm.LMM raises ValueError on a non-finite design [W g]
+            raise ValueError("There are non-finite values in the covariates matrix. " + text)
+        raise CrmError(status, text)
 
 
 def call(name, *args):

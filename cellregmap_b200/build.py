@@ -17,7 +17,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def _units():
-    return [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    return [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cu") or f.endswith(".cpp")]
 
 
 def _deps():
@@ -36,26 +36,29 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.path.join(CUDA_HOME, "bin", "nvcc")
     os.makedirs(OBJDIR, exist_ok=True)
-    newest_header = max(os.path.getmtime(s) for s in _deps() if not s.endswith(".cu"))
+    newest_header = max(os.path.getmtime(s) for s in _deps() if not (s.endswith(".cu") or s.endswith(".cpp")))
 
     def compile_one(unit):
         src = os.path.join(CSRC, unit)
-        obj = os.path.join(OBJDIR, unit[:-3] + ".o")
+        obj = os.path.join(OBJDIR, os.path.splitext(unit)[0] + ".o")
         stamp = max(os.path.getmtime(src), newest_header)
         if unit == "kernels_fit_null.cu":
             stamp = max(stamp, os.path.getmtime(os.path.join(CSRC, "kernels_fit_g.cu")))
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > stamp:
             return obj
-        cmd = [nvcc] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-                               "-c", src, "-o", obj]
-        if verbose:
-            cmd[1:1] = ["-Xptxas", "-v"]
+        if unit.endswith(".cpp"):      # host-only translation units (worker pool, narrowing loops): plain g++
+            cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-pthread", "-I" + os.path.join(CUDA_HOME, "include"), "-c", src, "-o", obj]
+        else:
+            cmd = [nvcc] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+                                   "-c", src, "-o", obj]
+            if verbose:
+                cmd[1:1] = ["-Xptxas", "-v"]
         subprocess.check_call(cmd)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, _units()))
-    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcusolver", "-lcublas", "-lcublasLt", "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
+    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcusolver", "-lcublas", "-lcublasLt", "-Xcompiler", "-pthread", "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
     subprocess.check_call(cmd)
     return LIB
 

@@ -17,6 +17,7 @@
 #include "../../include/crm_b200.h"
 #include "common.cuh"
 #include "launch.cuh"
+#include "feeder.hpp"
 
 namespace crm {
 
@@ -65,18 +66,44 @@ struct PhaseTrace {
     }
 };
 
-// Grow-only device buffer.  Allocation goes through the device's default CUDA memory pool (cudaMallocAsync on the
-// legacy default stream) with an unlimited release threshold, so that creating and destroying model objects in a loop
-// (one per gene) reuses the same physical memory instead of paying cudaMalloc/cudaFree of tens of GB every time.
-static void configure_pool_once(int device) {
-    static std::atomic<unsigned> done{0};
-    if (device < 0 || device >= 32 || (done.load() >> device & 1u)) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+// Grow-only device buffer.  Allocation is stream-ordered on the stream of the ABI call in flight (AllocScope, set by every entry
+// point that takes a stream): memory is obtained and returned in the same order as the kernels that use it, so a buffer that grows
+// while earlier launches on that stream still read the old one is released only after them.  (Calls on one handle must be ordered by
+// the caller anyway -- a scan reads what the set-up wrote.)  The memory comes from a private per-device pool with an unlimited release
+// threshold, so that creating and destroying model objects in a loop (one per gene) reuses the same physical memory instead of paying
+// cudaMalloc/cudaFree of tens of GB every time; the device's default pool is left untouched.  crm_trim_pool() hands cached memory back.
+static thread_local cudaStream_t g_alloc_stream = (cudaStream_t)0;
+struct AllocScope {
+    cudaStream_t saved;
+    explicit AllocScope(cudaStream_t st) : saved(g_alloc_stream) { g_alloc_stream = st; }
+    ~AllocScope() { g_alloc_stream = saved; }
+};
+static cudaMemPool_t g_pools[32] = {};
+static std::mutex g_pool_mu;
+static cudaMemPool_t device_pool(int device) {
+    if (device < 0 || device >= 32) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (!g_pools[device]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         unsigned long long threshold = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        g_pools[device] = pool;
     }
-    done.fetch_or(1u << device);
+    return g_pools[device];
+}
+// bytes held by the pool beyond what is in use (reusable by the next reserve)
+static size_t pool_cached_bytes(int device) {
+    cudaMemPool_t pool = device_pool(device);
+    unsigned long long reserved = 0, used = 0;
+    if (pool && cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used) return (size_t)(reserved - used);
+    return 0;
 }
 struct DevBuf {
     void* ptr = nullptr;
@@ -86,13 +113,13 @@ struct DevBuf {
         release();
         int dev = 0;
         cudaGetDevice(&dev);
-        configure_pool_once(dev);
-        cudaError_t e = cudaMallocAsync(&ptr, bytes, (cudaStream_t)0);
-        if (e != cudaSuccess) { set_error("cudaMallocAsync of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); ptr = nullptr; cudaGetLastError(); return CRM_ERR_CUDA; }
+        cudaMemPool_t pool = device_pool(dev);
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(&ptr, bytes, pool, g_alloc_stream) : cudaMallocAsync(&ptr, bytes, g_alloc_stream);
+        if (e != cudaSuccess) { set_error("stream-ordered allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); ptr = nullptr; cudaGetLastError(); return CRM_ERR_CUDA; }
         cap = bytes;
         return CRM_OK;
     }
-    void release() { if (ptr) cudaFreeAsync(ptr, (cudaStream_t)0); ptr = nullptr; cap = 0; }
+    void release() { if (ptr) cudaFreeAsync(ptr, g_alloc_stream); ptr = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
@@ -141,6 +168,7 @@ struct Handle {
     std::vector<cudaEvent_t> prof_events;
     double prof_flops = 0.0;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t last_stream = nullptr;   // stream of the latest ABI call on this handle: the buffers are released in its order
     // genotypes staged ahead of the scan (crm_stage_genotypes): the whole host matrix in device memory, copied in column chunks on
     // the copy stream while the set-up runs; one event per chunk
     DevBuf gstage;
@@ -148,11 +176,15 @@ struct Handle {
     std::vector<cudaEvent_t> stage_events;          // one per chunk
     bool stage_valid = false;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // host genotypes converted to int8 blocks by the feeder (feeder.hpp): job in flight, the matrix it describes, device landing buffers
+    std::shared_ptr<FeedJob> feed;
+    const void* feed_src = nullptr; long long feed_ld = 0, feed_p = 0, feed_rows = 0; int feed_dtype = 0;
+    DevBuf g8dev[2], gwide, gwide2;
     void free_all() {
         DevBuf* all[] = {&A8, &a8expo, &Gt8, &G2t8, &D32, &ozflags, &A28, &a28expo, &HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
-                         &gtchunk[0], &gtchunk[1], &gstage, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
+                         &gtchunk[0], &gtchunk[1], &gstage, &g8dev[0], &g8dev[1], &gwide, &gwide2, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -411,6 +443,25 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
 // factor is applied to the genotype fragments on the fly (EXPAND mode, ~90% of peak, no extra memory).
 // Rotation through the exact int8 split (ozaki.cuh): *used = 1 when the block was integer-valued and the route was taken.
 // CRM_INT8_GEMM=lt routes the int8 contraction through cuBLASLt + oz_combine_kernel instead of the fused tcgen05 kernel
+// A genotype matrix as the ABI receives it: float64 or int8 on the device, any HostDtype on the host.
+struct GSource { const void* ptr; long long ld; int dtype; int on_host; };
+// A block of SNP columns as the kernels see it.  Either image may be missing: `G` (float64, device pointer, leading dimension, number
+// of addressable columns) is produced on demand from `G8` (int8 dosages, row-major, leading dimension in bytes) by block_f64();
+// gmax = largest |dosage| of the int8 image when the host already knows it (-1: unknown).
+struct GBlock { const double* G; long long ld; long long cols; const double* G2; long long ld2; long long b; long long s0;
+                const int8_t* G8; long long ld8; int gmax; };
+
+// float64 image of a block that arrived as int8 (consumers without an int8 route: DMMA contractions, permuted designs)
+static int block_f64(Handle* h, GBlock& k, cudaStream_t st) {
+    if (k.G) return CRM_OK;
+    if (!k.G8) { set_error("genotype block without data"); return CRM_ERR_INVALID; }
+    const long long rows = h->gs->K, ld = round_up(k.b, 2);
+    CRM_CHECK(h->gwide.reserve((size_t)rows * ld * 8));
+    CRM_CHECK(oz_launch_widen_i8(k.G8, k.ld8, rows, k.b, h->gwide.as<double>(), ld, st));
+    k.G = h->gwide.as<double>(); k.ld = ld; k.cols = k.b;
+    return CRM_OK;
+}
+
 static bool int8_route_library() {
     static const bool lt = [] { const char* v = getenv("CRM_INT8_GEMM"); return v && !strcmp(v, "lt"); }();
     return lt;
@@ -424,8 +475,9 @@ static int int8_split_contract(Handle* h, const int8_t* P8, long long Mp, long l
     return oz_launch_combine(h->D32.as<int>(), Mp, Bp, expo, Mtot, B, C, ldc, st);
 }
 
-static int rotation_int8_split(Handle* h, const double* G, long long ldg, long long B, double* C, cudaStream_t st, int* used) {
+static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStream_t st, int* used) {
     *used = 0;
+    const long long B = blk.b;
     const long long n = h->n, Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
     const size_t a8_bytes = (size_t)OZAKI_SLICES * Mp * Kp;
     if (!h->oz_built && h->A8.cap < a8_bytes) {      // room for the digit planes?  (cudaMemGetInfo costs milliseconds: only asked for large requests)
@@ -435,9 +487,7 @@ static int rotation_int8_split(Handle* h, const double* G, long long ldg, long l
         if (need > 0.2 * (double)total_mem[h->device]) {
             size_t free_b = 0, total_b = 0;
             CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            cudaMemPool_t mp_; unsigned long long reserved = 0, usedb = 0;
-            if (cudaDeviceGetDefaultMemPool(&mp_, h->device) == cudaSuccess && cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-                cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrUsedMemCurrent, &usedb) == cudaSuccess && reserved > usedb) free_b += (size_t)(reserved - usedb);
+            free_b += pool_cached_bytes(h->device);
             if (need > 0.5 * (double)free_b) return CRM_OK;
         }
     }
@@ -446,13 +496,22 @@ static int rotation_int8_split(Handle* h, const double* G, long long ldg, long l
     CRM_CHECK(h->Gt8.reserve((size_t)Bp * Kp));
     CRM_CHECK(h->G2t8.reserve((size_t)Bp * Kp));
     CRM_CHECK(h->ozflags.reserve(64));
-    CRM_CHECK(oz_launch_genotypes(G, ldg, n, B, h->Gt8.as<int8_t>(), h->G2t8.as<int8_t>(), Bp, Kp, h->ozflags.as<int>(), st));
-    int flags[2] = {0, 0};
-    CRM_CUDA(cudaMemcpyAsync(flags, h->ozflags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
-    CRM_CUDA(cudaStreamSynchronize(st));
+    int flags[4] = {0, 0, 0, 0};
+    if (blk.G8 && blk.gmax >= 0) {
+        // int8 dosages whose range the host already knows (converted by the feeder): no flag read-back, no host synchronisation
+        if ((double)Kp * 64.0 * (double)std::max(blk.gmax, 1) >= 2147483648.0) return CRM_OK;
+        CRM_CHECK(oz_launch_transpose_i8(blk.G8, blk.ld8, n, B, h->Gt8.as<int8_t>(), h->G2t8.as<int8_t>(), Bp, Kp, nullptr, st));
+        flags[1] = blk.gmax;
+    } else {
+        if (blk.G8) CRM_CHECK(oz_launch_transpose_i8(blk.G8, blk.ld8, n, B, h->Gt8.as<int8_t>(), h->G2t8.as<int8_t>(), Bp, Kp, h->ozflags.as<int>(), st));
+        else CRM_CHECK(oz_launch_genotypes(blk.G, blk.ld, n, B, h->Gt8.as<int8_t>(), h->G2t8.as<int8_t>(), Bp, Kp, h->ozflags.as<int>(), st));
+        CRM_CUDA(cudaMemcpyAsync(flags, h->ozflags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        CRM_CUDA(cudaStreamSynchronize(st));
+        if (flags[2] != 0) { set_error("There are non-finite values in the genotype matrix (SNP columns %lld..%lld).", blk.s0, blk.s0 + B - 1); return CRM_ERR_NONFINITE; }
+        if (flags[0] != 0) return CRM_OK;                                              // not integer dosages
+        if ((double)Kp * 64.0 * (double)std::max(flags[1], 1) >= 2147483648.0) return CRM_OK;   // int32 accumulation could overflow
+    }
     tr.mark("genotypes->int8");
-    if (flags[0] != 0) return CRM_OK;                                              // not integer dosages
-    if ((double)Kp * 64.0 * (double)std::max(flags[1], 1) >= 2147483648.0) return CRM_OK;   // int32 accumulation could overflow
     if (!h->oz_built) {
         if (h->A8.reserve(a8_bytes) != CRM_OK) return CRM_OK;      // no room after all: the fp64 route takes over
         CRM_CHECK(h->a8expo.reserve((size_t)Mtot * sizeof(int)));
@@ -478,21 +537,39 @@ static int rotation_int8_split(Handle* h, const double* G, long long ldg, long l
     return CRM_OK;
 }
 
-static int launch_rotation(Handle* h, const double* G, long long ldg, long long gcols, long long B, double* C, cudaStream_t st) {
+// non-finite genotypes make every later stage meaningless (the reference's LMM raises on them): checked where no other kernel does
+static int check_block_finite(Handle* h, const GBlock& blk, cudaStream_t st) {
+    if (!blk.G) return CRM_OK;          // int8 images are finite by construction
+    CRM_CHECK(h->ozflags.reserve(64));
+    int flags[4] = {0, 0, 0, 0};
+    CRM_CUDA(cudaMemsetAsync(h->ozflags.ptr, 0, sizeof(flags), st));
+    CRM_CHECK(oz_launch_finite_check(blk.G, blk.ld, h->gs->K, blk.b, h->ozflags.as<int>(), st));
+    CRM_CUDA(cudaMemcpyAsync(flags, h->ozflags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaStreamSynchronize(st));
+    if (flags[2] != 0) { set_error("There are non-finite values in the genotype matrix (SNP columns %lld..%lld).", blk.s0, blk.s0 + blk.b - 1); return CRM_ERR_NONFINITE; }
+    return CRM_OK;
+}
+
+static int launch_rotation(Handle* h, GBlock& blk, double* C, cudaStream_t st) {
     const Handle::GenoSpace& gs = *h->gs;
-    const long long ldE = (long long)h->kexp * h->ldH;
+    const long long ldE = (long long)h->kexp * h->ldH, B = blk.b;
     GemmOperands op{};
-    op.B = G; op.ldb = ldg; op.b_cols = gcols; op.B2 = G; op.ldb2 = ldg; op.b2_cols = gcols;
     if (h->gs == &h->donors) {                       // donor-level operands are always fully expanded (d rows only)
+        CRM_CHECK(block_f64(h, blk, st));
+        CRM_CHECK(check_block_finite(h, blk, st));
+        op.B = blk.G; op.ldb = blk.ld; op.b_cols = blk.cols; op.B2 = blk.G; op.ldb2 = blk.ld; op.b2_cols = blk.cols;
         op.A = gs.HxE; op.lda = gs.ldE; op.a_cols = gs.ldE;
         return launch_gemm(GEMM_PLAIN, op, (int)gs.K, 0, (int)gs.ldE, 0, (int)B, C, gs.ldE, 1, st);
     }
     if (h->rotation_mode != 1) {
         int used = 0;
-        CRM_CHECK(rotation_int8_split(h, G, ldg, B, C, st, &used));
+        CRM_CHECK(rotation_int8_split(h, blk, C, st, &used));
         if (used) return CRM_OK;
         if (h->rotation_mode == 2) { set_error("CRM_ROTATION=int8 but the genotype block is not integer-valued in [-127, 127] (or memory is short)"); return CRM_ERR_UNSUPPORTED; }
     }
+    CRM_CHECK(block_f64(h, blk, st));
+    if (h->rotation_mode == 1) CRM_CHECK(check_block_finite(h, blk, st));     // (the int8 conversion kernel reported it otherwise)
+    op.B = blk.G; op.ldb = blk.ld; op.b_cols = blk.cols; op.B2 = blk.G; op.ldb2 = blk.ld; op.b2_cols = blk.cols;
     if (h->use_hxe) {
         const int nb = h->hxe_blocks;
         CRM_CHECK(h->HxE.reserve((size_t)h->n * nb * h->ldH * 8));
@@ -563,13 +640,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         const size_t bytes = (size_t)n * h->kexp * ldH * 8;
         size_t free_b = 0, total_b = 0;
         CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        {   // memory cached in the allocation pool is reusable as well
-            cudaMemPool_t mp_; unsigned long long reserved = 0, used = 0;
-            if (cudaDeviceGetDefaultMemPool(&mp_, h->device) == cudaSuccess &&
-                cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-                cudaMemPoolGetAttribute(mp_, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
-                free_b += (size_t)(reserved - used);
-        }
+        free_b += pool_cached_bytes(h->device);     // memory cached in the allocation pool is reusable as well
         const char* env = getenv("CRM_NO_HXE");
         const char* envb = getenv("CRM_HXE_BLOCKS");       // tests: force streaming in groups of this many context blocks
         const double budget = 0.45 * (double)(free_b + h->HxE.cap);
@@ -830,20 +901,71 @@ static int stage_host_block(Handle* h, const double* G, long long ldg, const dou
     return CRM_OK;
 }
 
-// Start copying a host genotype matrix (rows x p, leading dimension ldg) to the device in column chunks on the copy stream; returns
-// at once.  The next scan of the same matrix (same pointer, ldg, p) consumes it block by block as the chunks arrive -- called before
-// crm_setup, the transfer overlaps the set-up and the first blocks of the scan.
-static int do_stage_genotypes(Handle* h, const double* G, long long ldg, long long rows, long long p, cudaStream_t st) {
+// Column blocks of the feeder: a whole number of 256-SNP tiles of the int8 contraction, chosen so that (SNP tiles x basis tiles) fills
+// the 148 SMs in whole waves (basis_cols = columns of the expanded basis, 0 when unknown); a short matrix is one block.
+static long long feeder_block_cols(long long p, long long basis_cols) {
+    if (const char* env = getenv("CRM_FEEDER_BLOCK")) { if (atoll(env) > 0) return std::min<long long>(p, atoll(env)); }     // tests: many small blocks
+    long long best_t = 8;
+    if (basis_cols > 0) {
+        const long long mt = (basis_cols + 127) / 128;
+        double best = -1.0;
+        for (long long t = 6; t <= 16; t++) {
+            const long long tiles = t * mt, waves = (tiles + 147) / 148;
+            const double eff = (double)tiles / (double)(waves * 148);
+            if (eff > best + 0.004) { best = eff; best_t = t; }
+        }
+    }
+    const long long block = 256 * best_t;
+    return (p <= block + block / 4) ? p : block;
+}
+
+static void drop_feed(Handle* h) {
+    if (h->feed) { feeder_cancel(*h->feed); h->feed.reset(); }
+    h->feed_src = nullptr;
+}
+
+// Starts the conversion of a host genotype matrix into int8 blocks (feeder.hpp); returns at once.
+static int start_feed(Handle* h, const void* G, int dtype, long long ldg, long long rows, long long p, long long basis_cols) {
+    drop_feed(h);
+    static const bool off = [] { const char* v = getenv("CRM_NO_FEEDER"); return v && atoi(v) != 0; }();
+    if (off || host_dtype_size(dtype) == 0) return CRM_OK;
+    auto job = std::make_shared<FeedJob>();
+    job->src = G; job->dtype = dtype; job->ld = ldg; job->rows = rows; job->p = p;
+    const long long block = feeder_block_cols(p, basis_cols);
+    for (long long s0 = 0; s0 < p; s0 += block) job->starts.push_back(s0);
+    job->starts.push_back(p);
+    job->slot_ld = round_up(std::min(block, p), 16);
+    job->nslots = (int)std::min<long long>(3, job->nblocks());
+    for (int i = 0; i < job->nslots; i++) {
+        job->slots[i] = pinned_slot(i, (size_t)rows * job->slot_ld);
+        if (!job->slots[i]) return CRM_OK;                  // cannot page-lock that much: the scan streams the matrix as float64 instead
+    }
+    feeder_submit(job);
+    h->feed = job; h->feed_src = G; h->feed_ld = ldg; h->feed_p = p; h->feed_rows = rows; h->feed_dtype = dtype;
+    if (trace_on()) fprintf(stderr, "[crm trace] host %.1f ms: feeder started, %lld x %lld genotypes (dtype %d) in %lld blocks of %lld columns, %d threads\n", host_ms(), rows, p, dtype,
+                            job->nblocks(), block, host_threads());
+    return CRM_OK;
+}
+
+// Start moving a host genotype matrix (rows x p, leading dimension ldg) to the device ahead of the scan; returns at once.  Pinned float64:
+// plain DMA in column chunks on the copy stream.  Anything else (pageable float64 -- what a reference user passes -- or integer / float32
+// storage): conversion to int8 dosage blocks by the host feeder.  The next scan of the same matrix (same pointer, ldg, p) consumes it
+// block by block as the data arrive -- called before crm_setup, the transfer overlaps the set-up and the first blocks of the scan.
+static int do_stage_genotypes(Handle* h, const void* Gv, int dtype, long long ldg, long long rows, long long p, long long basis_cols, cudaStream_t st) {
     h->stage_valid = false;
-    if (!G || rows <= 0 || p <= 0 || ldg < p) { set_error("crm_stage_genotypes: bad arguments"); return CRM_ERR_INVALID; }
+    drop_feed(h);
+    if (!Gv || rows <= 0 || p <= 0 || ldg < p) { set_error("crm_stage_genotypes: bad arguments"); return CRM_ERR_INVALID; }
     static size_t total_mem[16] = {0};
     if (!total_mem[h->device]) { size_t f = 0; CRM_CUDA(cudaMemGetInfo(&f, &total_mem[h->device])); }
+    cudaPointerAttributes pa{};
+    const bool pinned = cudaPointerGetAttributes(&pa, Gv) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    static const bool force_feeder = [] { const char* v = getenv("CRM_FEEDER"); return v && atoi(v) != 0; }();
+    if (dtype != HD_F64 || !pinned || force_feeder) return start_feed(h, Gv, dtype, ldg, rows, p, basis_cols);
+    const double* G = static_cast<const double*>(Gv);
     const long long ld = round_up(p, 2);
     const double bytes = (double)rows * (double)ld * 8.0;
     if (bytes > 0.25 * (double)total_mem[h->device]) return CRM_OK;          // too large to hold: the scan streams it in blocks instead
-    cudaPointerAttributes pa{};
-    if (cudaPointerGetAttributes(&pa, G) != cudaSuccess || pa.type != cudaMemoryTypeHost) { cudaGetLastError(); return CRM_OK; }   // pageable memory copies
-    // synchronously: nothing to gain from starting early
     CRM_CHECK(ensure_streams(h));
     CRM_CHECK(h->gstage.reserve((size_t)bytes));
     // One copy stream, chunk after chunk: the copy engine drains one stream's queue before it turns to the next, so chunks spread
@@ -852,10 +974,8 @@ static int do_stage_genotypes(Handle* h, const double* G, long long ldg, long lo
     const int chunk = 512;
     const size_t nchunks = (size_t)((p + chunk - 1) / chunk);
     while (h->stage_events.size() < nchunks) { cudaEvent_t e; CRM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->stage_events.push_back(e); }
-    // the buffer comes from the stream-ordered pool on the legacy stream; the copy stream is non-blocking: order it explicitly
-    CRM_CUDA(cudaEventRecord(h->ev_done[0], (cudaStream_t)0));
+    // the buffer comes from the stream-ordered pool on `st`; the copy stream is non-blocking: order it explicitly
     CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
-    CRM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
     CRM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[1], 0));
     for (size_t c = 0; c < nchunks; c++) {
         const long long c0 = (long long)c * chunk, w = std::min<long long>(chunk, p - c0);
@@ -868,29 +988,72 @@ static int do_stage_genotypes(Handle* h, const double* G, long long ldg, long lo
     return CRM_OK;
 }
 
-// A block of SNP columns as the kernels see it: device pointer, leading dimension, number of addressable columns.
-struct GBlock { const double* G; long long ld; long long cols; const double* G2; long long ld2; long long b; long long s0; };
+// Columns [s0, s0 + b) of a host matrix of any element type as a float64 device block (gchunk[0], leading dimension round_up(b, 2)),
+// through two pinned bounce buffers filled by the worker pool: the route of blocks that are not integer dosages.
+static int bounce_block_f64(Handle* h, const GSource& src, long long s0, long long b, cudaStream_t st, GBlock* blk) {
+    const long long rows = h->gs->K, ldd = round_up(b, 2);
+    CRM_CHECK(ensure_streams(h));
+    CRM_CHECK(h->gchunk[0].reserve((size_t)rows * ldd * 8));
+    const size_t slot_bytes = std::max<size_t>((size_t)128 << 20, (size_t)rows * 16 * 8);
+    const long long sub = std::max<long long>(16, std::min<long long>(b, (long long)(slot_bytes / ((size_t)rows * 8))));
+    int it = 0;
+    for (long long c0 = 0; c0 < b; c0 += sub, it++) {
+        const long long w = std::min(sub, b - c0);
+        const int slot = it & 1;
+        double* bounce = reinterpret_cast<double*>(pinned_slot(4 + slot, slot_bytes));
+        if (!bounce) { set_error("cannot page-lock a %zu-byte bounce buffer", slot_bytes); return CRM_ERR_CUDA; }
+        if (it >= 2) CRM_CUDA(cudaEventSynchronize(h->ev_copy[slot]));          // the copy that last read this buffer
+        host_parallel_widen(src.ptr, src.dtype, src.ld, rows, s0 + c0, w, bounce, w);
+        CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].as<double>() + c0, (size_t)ldd * 8, bounce, (size_t)w * 8, (size_t)w * 8, (size_t)rows, cudaMemcpyHostToDevice, st));
+        CRM_CUDA(cudaEventRecord(h->ev_copy[slot], st));
+    }
+    CRM_CUDA(cudaStreamSynchronize(st));          // the bounce buffers are process-wide
+    *blk = GBlock{h->gchunk[0].as<double>(), ldd, b, nullptr, 0, b, s0, nullptr, 0, -1};
+    return CRM_OK;
+}
 
-// Walks the columns of G (and of the optional second matrix G2) in blocks of at most B columns.  Device-resident
-// input is used in place when TMA can address it (16-byte aligned base, even leading dimension, even first column),
-// otherwise the block is repacked; host-resident input is staged through double-buffered chunks on the copy stream
-// so that the copy of block i+1 overlaps the compute of block i.
+// Walks the columns of G (and of the optional second matrix G2, same type and placement) in blocks of at most B columns.
+//  * device float64: used in place when TMA can address it (16-byte aligned base, even leading dimension, even first column), otherwise
+//    the block is repacked; device int8: handed over as an int8 block.
+//  * host float64 staged ahead by DMA (pinned, crm_stage_genotypes): blocks wait for the chunks that cover them.
+//  * other host matrices: int8 blocks from the feeder (started by crm_stage_genotypes, or here), copied to the device on the copy stream
+//    while earlier blocks are scanned; a block that is not integer-valued stops the feeder and the rest goes over as float64.
+//  * CRM_NO_FEEDER=1, or two host matrices (permuted tested genotypes): float64 blocks streamed through double-buffered chunks.
 template <class F>
-static int for_each_block(Handle* h, const double* G, long long ldg, const double* G2, long long ldg2, long long p, int on_host,
-                          long long B, cudaStream_t st, F&& fn) {
-    if (!on_host) {
+static int for_each_block(Handle* h, const GSource& src, const GSource* src2, long long p, long long B, cudaStream_t st, F&& fn) {
+    const long long rows = h->gs->K;
+    if (src2 && (src2->dtype != src.dtype || src2->on_host != src.on_host)) { set_error("the two genotype matrices must share type and placement"); return CRM_ERR_INVALID; }
+    if (!src.on_host) {
+        if (src.dtype == HD_I8) {
+            const int8_t* G8 = static_cast<const int8_t*>(src.ptr);
+            for (long long s0 = 0; s0 < p; s0 += B) {
+                const long long b = std::min(B, p - s0);
+                GBlock blk{nullptr, 0, 0, nullptr, 0, b, s0, G8 + s0, src.ld, -1};
+                if (src2) {
+                    const long long ld = round_up(b, 2);
+                    CRM_CHECK(h->gwide2.reserve((size_t)rows * ld * 8));
+                    CRM_CHECK(oz_launch_widen_i8(static_cast<const int8_t*>(src2->ptr) + s0, src2->ld, rows, b, h->gwide2.as<double>(), ld, st));
+                    blk.G2 = h->gwide2.as<double>(); blk.ld2 = ld;
+                }
+                CRM_CHECK(fn(blk));
+            }
+            return CRM_OK;
+        }
+        if (src.dtype != HD_F64) { set_error("device genotypes must be float64 or int8"); return CRM_ERR_UNSUPPORTED; }
+        const double* G = static_cast<const double*>(src.ptr); const long long ldg = src.ld;
+        const double* G2 = src2 ? static_cast<const double*>(src2->ptr) : nullptr; const long long ldg2 = src2 ? src2->ld : 0;
         const bool aligned = ((reinterpret_cast<uintptr_t>(G) & 15) == 0) && (ldg % 2 == 0);
         const bool aligned2 = !G2 || (((reinterpret_cast<uintptr_t>(G2) & 15) == 0) && (ldg2 % 2 == 0));
         for (long long s0 = 0; s0 < p; s0 += B) {
             const long long b = std::min(B, p - s0), bp = round_up(b, 2);
-            GBlock blk{G + s0, ldg, p - s0, G2 ? G2 + s0 : nullptr, ldg2, b, s0};
+            GBlock blk{G + s0, ldg, p - s0, G2 ? G2 + s0 : nullptr, ldg2, b, s0, nullptr, 0, -1};
             if (!aligned || !aligned2 || (s0 & 1)) {
-                CRM_CHECK(h->gchunk[0].reserve((size_t)h->gs->K * bp * 8));
-                CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)h->gs->K, cudaMemcpyDeviceToDevice, st));
+                CRM_CHECK(h->gchunk[0].reserve((size_t)rows * bp * 8));
+                CRM_CUDA(cudaMemcpy2DAsync(h->gchunk[0].ptr, (size_t)bp * 8, G + s0, (size_t)ldg * 8, (size_t)b * 8, (size_t)rows, cudaMemcpyDeviceToDevice, st));
                 blk.G = h->gchunk[0].as<double>(); blk.ld = bp; blk.cols = b;
                 if (G2) {
-                    CRM_CHECK(h->gtchunk[0].reserve((size_t)h->gs->K * bp * 8));
-                    CRM_CUDA(cudaMemcpy2DAsync(h->gtchunk[0].ptr, (size_t)bp * 8, G2 + s0, (size_t)ldg2 * 8, (size_t)b * 8, (size_t)h->gs->K, cudaMemcpyDeviceToDevice, st));
+                    CRM_CHECK(h->gtchunk[0].reserve((size_t)rows * bp * 8));
+                    CRM_CUDA(cudaMemcpy2DAsync(h->gtchunk[0].ptr, (size_t)bp * 8, G2 + s0, (size_t)ldg2 * 8, (size_t)b * 8, (size_t)rows, cudaMemcpyDeviceToDevice, st));
                     blk.G2 = h->gtchunk[0].as<double>(); blk.ld2 = bp;
                 }
             }
@@ -899,29 +1062,83 @@ static int for_each_block(Handle* h, const double* G, long long ldg, const doubl
         return CRM_OK;
     }
     CRM_CHECK(ensure_streams(h));
-    // block boundaries: a short first block (its copy is the only one that is not hidden behind compute), then blocks of B
+    // ---- host float64 staged ahead by DMA ----
+    if (src.dtype == HD_F64 && h->stage_valid && !src2 && src.ptr == h->stage_src && src.ld == h->stage_ldg && p == h->stage_p && rows == h->stage_rows) {
+        for (long long s0 = 0; s0 < p; s0 += B) {
+            const long long b = std::min(B, p - s0);
+            const long long c_last = (s0 + b - 1) / h->stage_chunk;                       // chunks complete in order on the copy stream
+            CRM_CUDA(cudaStreamWaitEvent(st, h->stage_events[(size_t)c_last], 0));
+            GBlock blk{h->gstage.as<double>() + s0, h->stage_ld, h->stage_p - s0, nullptr, 0, b, s0, nullptr, 0, -1};
+            CRM_CHECK(fn(blk));
+        }
+        h->stage_valid = false;         // one scan per staging: the host array may change afterwards
+        return CRM_OK;
+    }
+    // ---- int8 blocks from the feeder ----
+    long long done = 0;                 // columns handled so far
+    if (!src2) {
+        if (!(h->feed && h->feed_src == src.ptr && h->feed_ld == src.ld && h->feed_p == p && h->feed_rows == rows && h->feed_dtype == src.dtype))
+            CRM_CHECK(start_feed(h, src.ptr, src.dtype, src.ld, rows, p, h->gs == &h->cells ? (long long)h->kexp * h->ldH : 0));
+        if (h->feed) {
+            std::shared_ptr<FeedJob> job = h->feed;
+            const long long nb = job->nblocks();
+            const size_t slot_bytes = (size_t)rows * job->slot_ld;
+            int status = CRM_OK;
+            // landing buffers first: they are allocated in the order of `st`, and the events below carry that order to the copy stream
+            for (int d = 0; d < std::min<long long>(2, nb); d++) CRM_CHECK(h->g8dev[d].reserve(slot_bytes));
+            CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
+            CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
+            for (long long ib = 0; ib < nb && status == CRM_OK; ib++) {
+                int bad = 0, gmax = 0;
+                feeder_wait_block(*job, ib, &bad, &gmax);
+                if (bad) break;                                                      // not integer dosages: the rest goes over as float64
+                const int dslot = (int)(ib & 1);
+                const long long s0 = job->starts[ib], bw = job->starts[ib + 1] - s0;
+                cudaError_t ce = cudaStreamWaitEvent(h->copy_stream, h->ev_done[dslot], 0);          // scan of the block that used this buffer before
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->g8dev[dslot].ptr, job->slots[ib % job->nslots], slot_bytes, cudaMemcpyHostToDevice, h->copy_stream);
+                if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_copy[dslot], h->copy_stream);
+                if (ce == cudaSuccess) ce = feeder_release_after(job, ib, h->copy_stream);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, h->ev_copy[dslot], 0);
+                if (ce != cudaSuccess) { set_error("feeder copy failed: %s", cudaGetErrorString(ce)); status = CRM_ERR_CUDA; break; }
+                for (long long c0 = 0; c0 < bw && status == CRM_OK; c0 += B) {       // scan batches inside the block
+                    const long long b = std::min(B, bw - c0);
+                    GBlock blk{nullptr, 0, 0, nullptr, 0, b, s0 + c0, h->g8dev[dslot].as<int8_t>() + c0, job->slot_ld, gmax};
+                    status = fn(blk);
+                }
+                if (status == CRM_OK && cudaEventRecord(h->ev_done[dslot], st) != cudaSuccess) { set_error("cudaEventRecord failed"); status = CRM_ERR_CUDA; }
+                done = s0 + bw;
+            }
+            drop_feed(h);               // one scan per conversion (and the workers must not outlive the caller's array)
+            CRM_CHECK(status);
+            if (done >= p) return CRM_OK;
+            static const bool nofeed = [] { const char* v = getenv("CRM_NO_FEEDER"); return v && atoi(v) != 0; }();
+            if (!nofeed) {
+                for (long long s0 = done; s0 < p; s0 += B) {
+                    const long long b = std::min(B, p - s0);
+                    GBlock blk{};
+                    CRM_CHECK(bounce_block_f64(h, src, s0, b, st, &blk));
+                    CRM_CHECK(fn(blk));
+                }
+                return CRM_OK;
+            }
+        }
+    }
+    // ---- float64 blocks streamed through double-buffered chunks ----
+    if (src.dtype != HD_F64) { set_error("host genotypes of element type %d need the feeder (CRM_NO_FEEDER is set) or float64 storage", src.dtype); return CRM_ERR_UNSUPPORTED; }
+    const double* G = static_cast<const double*>(src.ptr); const long long ldg = src.ld;
+    const double* G2 = src2 ? static_cast<const double*>(src2->ptr) : nullptr; const long long ldg2 = src2 ? src2->ld : 0;
     const long long Bp = round_up(B, 2);
-    const bool staged = h->stage_valid && !G2 && G == h->stage_src && ldg == h->stage_ldg && p == h->stage_p && h->gs->K == h->stage_rows;
     std::vector<long long> starts;
-    {
-        // streamed: a short first block (its copy is the only one not hidden behind compute); staged ahead: equal blocks
-        const long long first = staged ? std::min(B, p) : (p > B) ? std::min<long long>(B, 512) : std::min(B, p);
+    {   // a short first block: its copy is the only one that is not hidden behind compute
+        const long long first = (p > B) ? std::min<long long>(B, 512) : std::min(B, p);
         starts.push_back(0);
         for (long long s0 = first; s0 < p; s0 += B) starts.push_back(s0);
         starts.push_back(p);
     }
     const long long nb = (long long)starts.size() - 1;
-    if (staged) {
-        // the matrix was staged ahead (crm_stage_genotypes): every block waits for the chunks that cover it
-        for (long long ib = 0; ib < nb; ib++) {
-            const long long s0 = starts[ib], b = starts[ib + 1] - s0;
-            const long long c_last = (s0 + b - 1) / h->stage_chunk;                       // chunks complete in order on the copy stream
-            CRM_CUDA(cudaStreamWaitEvent(st, h->stage_events[(size_t)c_last], 0));
-            GBlock blk{h->gstage.as<double>() + s0, h->stage_ld, h->stage_p - s0, nullptr, 0, b, s0};
-            CRM_CHECK(fn(blk));
-        }
-        h->stage_valid = false;         // one scan per staging: the host array may change afterwards
-        return CRM_OK;
+    for (int d = 0; d < std::min<long long>(2, nb); d++) {       // allocated in the order of `st`; the events below carry it to the copy stream
+        CRM_CHECK(h->gchunk[d].reserve((size_t)rows * Bp * 8));
+        if (G2) CRM_CHECK(h->gtchunk[d].reserve((size_t)rows * Bp * 8));
     }
     CRM_CUDA(cudaEventRecord(h->ev_done[0], st));
     CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
@@ -931,17 +1148,19 @@ static int for_each_block(Handle* h, const double* G, long long ldg, const doubl
         const long long s0 = starts[ib], b = starts[ib + 1] - s0;
         if (ib + 1 < nb) CRM_CHECK(stage_host_block(h, G, ldg, G2, ldg2, starts[ib + 1], starts[ib + 2] - starts[ib + 1], Bp, slot ^ 1));
         CRM_CUDA(cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
-        GBlock blk{h->gchunk[slot].as<double>(), Bp, b, G2 ? h->gtchunk[slot].as<double>() : nullptr, Bp, b, s0};
+        GBlock blk{h->gchunk[slot].as<double>(), Bp, b, G2 ? h->gtchunk[slot].as<double>() : nullptr, Bp, b, s0, nullptr, 0, -1};
         CRM_CHECK(fn(blk));
         CRM_CUDA(cudaEventRecord(h->ev_done[slot], st));
     }
     return CRM_OK;
 }
 
-static int interaction_batch(Handle* h, const double* Gd, long long ldg, long long gcols, const double* Gt, long long ldgt, long long B,
-                             double* out_pv, double* out_rho1, double* out_e2, double* out_g2, double* out_eps2,
-                             const crm_scan_diag_t* dg, long long s0, cudaStream_t st) {
+static int interaction_batch(Handle* h, GBlock blk, double* out_pv, double* out_rho1, double* out_e2, double* out_g2, double* out_eps2,
+                             const crm_scan_diag_t* dg, cudaStream_t st) {
     const int R = h->R, mp = h->mp, m = h->m, k = h->k0, kexp = h->kexp, c = h->c, ldH = h->ldH, Mx = h->Mx;
+    const long long B = blk.b, s0 = blk.s0;
+    const double* Gt = blk.G2; const long long ldgt = blk.ld2;
+    if (Gt) CRM_CHECK(block_f64(h, blk, st));        // permuted tested genotypes: both designs are contracted in float64
     double* C = h->C.as<double>();
     double* sq = h->sq.as<double>();
     PhaseTrace tr(st);
@@ -953,11 +1172,17 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
         h->prof_events.push_back(e0); h->prof_events.push_back(e1);
         h->prof_flops += 2.0 * (double)h->n * (double)h->m * (double)kexp * (double)B;   // algorithmic: 2 n m (1+k) per SNP
     }
-    CRM_CHECK(launch_rotation(h, Gt ? Gt : Gd, Gt ? ldgt : ldg, gcols, B, C, st));
+    if (Gt) {
+        GBlock tested{Gt, ldgt, blk.cols, nullptr, 0, B, s0, nullptr, 0, -1};
+        CRM_CHECK(launch_rotation(h, tested, C, st));
+    } else {
+        CRM_CHECK(launch_rotation(h, blk, C, st));
+    }
     if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_events.back(), st));
     tr.mark("rotation");
     // 2. squared-genotype Grams against [1 | E0 | pairs]:  g'g, (g.E0)'g, (g.E0)'(g.E0)
-    if (!Gt && h->gs == &h->cells && h->oz_block_valid && h->oz_block_gmax <= 11) {
+    if (!Gt && h->gs == &h->cells && h->oz_block_valid && h->oz_block_gmax <= 11 &&
+        (double)round_up(h->n, 16) * 64.0 * (double)(h->oz_block_gmax * h->oz_block_gmax) < 2147483648.0) {   // int32 accumulation of q * g^2
         // integer dosages: g^2 is an exact int8 operand as well -> same int8 split with the digit planes of A2
         const long long n = h->n, M2p = round_up(h->M2, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
         if (h->A28.cap == 0 || !h->oz_built_a2) {
@@ -968,12 +1193,14 @@ static int interaction_batch(Handle* h, const double* Gd, long long ldg, long lo
         }
         CRM_CHECK(int8_split_contract(h, h->A28.as<int8_t>(), M2p, h->M2, h->a28expo.as<int>(), h->G2t8.as<int8_t>(), Bp, B, Kp, sq, h->ld2, st));
     } else {
+        CRM_CHECK(block_f64(h, blk, st));
         GemmOperands op{};
         op.A = h->gs->A2; op.lda = h->gs->ld2; op.a_cols = h->M2;
-        op.B = Gt ? Gt : Gd; op.ldb = Gt ? ldgt : ldg; op.b_cols = gcols;
-        op.B2 = op.B; op.ldb2 = op.ldb; op.b2_cols = gcols;
+        op.B = Gt ? Gt : blk.G; op.ldb = Gt ? ldgt : blk.ld; op.b_cols = blk.cols;
+        op.B2 = op.B; op.ldb2 = op.ldb; op.b2_cols = blk.cols;
         CRM_CHECK(launch_gemm(GEMM_PRODUCT, op, (int)h->gs->K, 0, h->M2, 0, (int)B, sq, h->ld2, 1, st));
     }
+    const double* Gd = blk.G; const long long ldg = blk.ld, gcols = blk.cols;
     if (Gt) {
         // permuted tested genotypes (idx_G, reference :410-413): the null design still uses g itself, so the j = 0 rows of C
         // are overwritten with the rotation of g, column 0 of sq with g'g and columns 1..k with (gt * g)' E0
@@ -1099,33 +1326,33 @@ static int select_space(Handle* h, int donor_level, const char* who) {
     return CRM_OK;
 }
 
-static int do_scan_interaction(Handle* h, int donor_level, const double* G, long long ldg, long long p, int g_on_host, const double* Gtest, long long ldgt,
+static int do_scan_interaction(Handle* h, int donor_level, const GSource& G, long long p, const GSource* Gtest,
                                double* out_pv, double* out_rho1, double* out_e2, double* out_g2, double* out_eps2,
                                const crm_scan_diag_t* dg, cudaStream_t st) {
     if (!h->ready) { set_error("crm_scan_interaction: handle is not set up"); return CRM_ERR_STATE; }
     CRM_CHECK(select_space(h, donor_level, "crm_scan_interaction"));
     if (donor_level && Gtest) { set_error("crm_scan_interaction: permuted tested genotypes are not supported with donor-level input"); return CRM_ERR_UNSUPPORTED; }
     if (p == 0) return CRM_OK;
-    if (!G || p < 0 || ldg < p || !out_pv || !out_rho1 || !out_e2 || !out_g2 || !out_eps2) { set_error("crm_scan_interaction: bad arguments"); return CRM_ERR_INVALID; }
+    if (!G.ptr || p < 0 || G.ld < p || !out_pv || !out_rho1 || !out_e2 || !out_g2 || !out_eps2) { set_error("crm_scan_interaction: bad arguments"); return CRM_ERR_INVALID; }
     long long B = pick_batch(h, p, true);
-    if (g_on_host) B = host_chunk(h, B, p);
+    if (G.on_host) B = host_chunk(h, B, p);
     CRM_CHECK(reserve_scan(h, B, true));
-    return for_each_block(h, G, ldg, Gtest, ldgt, p, g_on_host, B, st, [&](const GBlock& k) -> int {
-        return interaction_batch(h, k.G, k.ld, k.cols, k.G2, k.ld2, k.b, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, k.s0, st);
+    return for_each_block(h, G, Gtest, p, B, st, [&](const GBlock& k) -> int {
+        return interaction_batch(h, k, out_pv, out_rho1, out_e2, out_g2, out_eps2, dg, st);
     });
 }
 
 // ------------------------------------------------------------------------------------------------
 // association scans
 // ------------------------------------------------------------------------------------------------
-static int do_scan_association(Handle* h, int donor_level, const double* G, long long ldg, long long p, int g_on_host, int fast, double* out_pv,
+static int do_scan_association(Handle* h, int donor_level, const GSource& G, long long p, int fast, double* out_pv,
                                double* out_alt, double* info4, double* out_null, cudaStream_t st) {
     if (!h->ready) { set_error("crm_scan_association: handle is not set up"); return CRM_ERR_STATE; }
     CRM_CHECK(select_space(h, donor_level, "crm_scan_association"));
-    if ((p > 0 && (!G || ldg < p || !out_pv)) || p < 0 || !info4) { set_error("crm_scan_association: bad arguments"); return CRM_ERR_INVALID; }
+    if ((p > 0 && (!G.ptr || G.ld < p || !out_pv)) || p < 0 || !info4) { set_error("crm_scan_association: bad arguments"); return CRM_ERR_INVALID; }
     const int R = h->R, mp = h->mp, m = h->m, c = h->c, ldH = h->ldH, Mx = h->Mx;
     long long B = pick_batch(h, std::max<long long>(p, 1), false);
-    if (g_on_host) B = host_chunk(h, B, p);
+    if (G.on_host) B = host_chunk(h, B, p);
     CRM_CHECK(reserve_scan(h, std::max<long long>(B, 1), false));
     // ---- null model: ML fit of y ~ W for every rho, best by strict '>' ----
     FitArgs fa{};
@@ -1158,7 +1385,10 @@ static int do_scan_association(Handle* h, int donor_level, const double* G, long
     CRM_CHECK(upload_small(xfix, &xopt[rb], 1, st));
     CRM_CUDA(cudaStreamSynchronize(st));   // host temporaries above go out of scope
     if (p == 0) return CRM_OK;
-    return for_each_block(h, G, ldg, nullptr, 0, p, g_on_host, B, st, [&](const GBlock& k) -> int {
+    return for_each_block(h, G, nullptr, p, B, st, [&](const GBlock& kb) -> int {
+        GBlock k = kb;
+        CRM_CHECK(block_f64(h, k, st));
+        CRM_CHECK(check_block_finite(h, k, st));
         const double* Gd = k.G; const long long ld = k.ld, cols = k.cols, b = k.b, s0 = k.s0;
         double* C = h->C.as<double>();
         double* sq = h->sq.as<double>();
@@ -1200,12 +1430,12 @@ static int do_scan_association(Handle* h, int donor_level, const double* G, long
 // ------------------------------------------------------------------------------------------------
 // effect sizes (predict_interaction)
 // ------------------------------------------------------------------------------------------------
-static int do_predict(Handle* h, int donor_level, const double* G, long long ldg, long long p, int g_on_host, const double* maf, int use_background,
+static int do_predict(Handle* h, int donor_level, const GSource& G, long long p, const double* maf, int use_background,
                       double* out_beta_g, double* out_beta_gxe, long long ldo, double* out_rho1, cudaStream_t st) {
     if (!h->ready) { set_error("crm_predict_interaction: handle is not set up"); return CRM_ERR_STATE; }
     CRM_CHECK(select_space(h, donor_level, "crm_predict_interaction"));
     if (p == 0) return CRM_OK;
-    if (!G || p < 0 || ldg < p || !maf || !out_beta_g || !out_beta_gxe || ldo < p) { set_error("crm_predict_interaction: bad arguments"); return CRM_ERR_INVALID; }
+    if (!G.ptr || p < 0 || G.ld < p || !maf || !out_beta_g || !out_beta_gxe || ldo < p) { set_error("crm_predict_interaction: bad arguments"); return CRM_ERR_INVALID; }
     const int R = h->R, mp = h->mp, c = h->c, k0 = h->k0, kexp = h->kexp, ldH = h->ldH, Mx = h->Mx;
     const int ns = 1 + c + k0, P = c + 1 + k0;
     int r0 = -1;
@@ -1238,7 +1468,7 @@ static int do_predict(Handle* h, int donor_level, const double* G, long long ldg
     const double per_snp = 8.0 * ((double)kexp * ldH + 2.0 * h->ld2 + 2.0 * (double)kexp * mp + (double)R * (P + k0 + 8));
     long long B = std::max<long long>(16, std::min<long long>(p, (long long)(4.0e9 / per_snp)));
     B = std::min<long long>(B, 65535LL * GEMM_TILE_N / kexp);
-    if (g_on_host) B = host_chunk(h, B, p);
+    if (G.on_host) B = host_chunk(h, B, p);
     CRM_CHECK(h->C.reserve((size_t)B * kexp * ldH * 8));
     CRM_CHECK(h->sq.reserve((size_t)B * h->ld2 * 8));
     CRM_CHECK(h->lin.reserve((size_t)B * h->ld2 * 8));
@@ -1253,10 +1483,12 @@ static int do_predict(Handle* h, int donor_level, const double* G, long long ldg
         CRM_CHECK(h->Vg.reserve((size_t)mB * round_up(B * kexp, 2) * 8));
         CRM_CHECK(h->Zp.reserve((size_t)B * kexp * mp * 8));
     }
-    return for_each_block(h, G, ldg, nullptr, 0, p, g_on_host, B, st, [&](const GBlock& k) -> int {
+    return for_each_block(h, G, nullptr, p, B, st, [&](const GBlock& kb) -> int {
+        GBlock k = kb;
         const long long b = k.b, s0 = k.s0;
         double* C = h->C.as<double>();
-        CRM_CHECK(launch_rotation(h, k.G, k.ld, k.cols, b, C, st));
+        CRM_CHECK(launch_rotation(h, k, C, st));
+        CRM_CHECK(block_f64(h, k, st));
         GemmOperands o2{};
         o2.A = h->gs->A2; o2.lda = h->gs->ld2; o2.a_cols = h->M2; o2.B = k.G; o2.ldb = k.ld; o2.b_cols = k.cols; o2.B2 = k.G; o2.ldb2 = k.ld; o2.b2_cols = k.cols;
         CRM_CHECK(launch_gemm(GEMM_PRODUCT, o2, (int)h->gs->K, 0, h->M2, 0, (int)b, h->sq.as<double>(), h->ld2, 1, st));
@@ -1326,14 +1558,36 @@ int crm_create(crm_handle_t* out, int device) {
 int crm_destroy(crm_handle_t h) {
     if (!h) return CRM_OK;
     cudaSetDevice(h->impl.device);
-    cudaDeviceSynchronize();   // every stream that may still read the buffers (they return to the pool in stream order)
-    h->impl.free_all();
+    // Buffers go back to the pool in the order of the stream that used them last, after the copy stream has drained into it; no
+    // device-wide synchronisation (other models and streams keep running).  A stream that no longer exists falls back to one.
+    drop_feed(&h->impl);
+    cudaStream_t st = h->impl.last_stream;
+    if (st && cudaStreamQuery(st) == cudaErrorInvalidResourceHandle) { cudaGetLastError(); cudaDeviceSynchronize(); st = nullptr; }
+    cudaGetLastError();
     if (h->impl.copy_stream) {
-        cudaStreamDestroy(h->impl.copy_stream);
+        cudaEvent_t drained = h->impl.ev_copy[0];
+        if (cudaEventRecord(drained, h->impl.copy_stream) == cudaSuccess) cudaStreamWaitEvent(st, drained, 0);
+    }
+    {
+        AllocScope alloc_scope(st);
+        h->impl.free_all();
+    }
+    if (h->impl.copy_stream) {
+        cudaStreamDestroy(h->impl.copy_stream);     // asynchronous: resources are released once the stream has drained
         for (int i = 0; i < 2; i++) { cudaEventDestroy(h->impl.ev_copy[i]); cudaEventDestroy(h->impl.ev_done[i]); }
     }
     for (cudaEvent_t e : h->impl.stage_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->impl.prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->impl.prof_oz_events) cudaEventDestroy(e);
     delete h;
+    return CRM_OK;
+}
+
+int crm_trim_pool(int device) {
+    cudaMemPool_t pool = device_pool(device);
+    if (!pool) { set_error("crm_trim_pool: no allocation pool for device %d", device); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaMemPoolTrimTo(pool, 0));
+    release_pinned_slots();
     return CRM_OK;
 }
 
@@ -1342,18 +1596,27 @@ int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t ldw, con
               void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
     return do_setup(&h->impl, y, W, ldw, E0, lde0, E1, lde1, L, ldl, n, c, k0, k1, mL, rho_host, R, (cudaStream_t)stream);
 }
 
 int crm_stage_genotypes(crm_handle_t h, const double* G_host, int64_t ldg, int64_t rows, int64_t p, void* stream) {
+    return crm_stage_genotypes_typed(h, G_host, CRM_G_F64, ldg, rows, p, 0, stream);
+}
+
+int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dtype, int64_t ldg, int64_t rows, int64_t p, int64_t basis_cols_hint, void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
-    return do_stage_genotypes(&h->impl, G_host, ldg, rows, p, (cudaStream_t)stream);
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    return do_stage_genotypes(&h->impl, G_host, dtype, ldg, rows, p, basis_cols_hint, (cudaStream_t)stream);
 }
+
+int crm_host_threads(void) { return host_threads(); }
 
 int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream) {
     if (!h || !h->impl.ready || !E0) { set_error("crm_set_test_contexts: handle not set up"); return CRM_ERR_STATE; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
     return build_test_contexts(&h->impl, E0, lde0, (cudaStream_t)stream);
 }
 
@@ -1382,6 +1645,7 @@ int crm_profile(crm_handle_t h, int enable, double* rot_ms, double* rot_flops, i
 int crm_update_phenotype(crm_handle_t h, const double* y, void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
     return do_update_phenotype(&h->impl, y, (cudaStream_t)stream);
 }
 
@@ -1391,6 +1655,7 @@ int crm_set_donors(crm_handle_t h, const int32_t* perm, const int32_t* offsets, 
     Handle& H = h->impl;
     CRM_CUDA(cudaSetDevice(H.device));
     cudaStream_t st = (cudaStream_t)stream;
+    AllocScope alloc_scope(st); H.last_stream = st;
     CRM_CHECK(H.dperm.reserve((size_t)H.n * 4));
     CRM_CHECK(H.doff.reserve((size_t)(d + 1) * 4));
     CRM_CUDA(cudaMemcpyAsync(H.dperm.ptr, perm, (size_t)H.n * 4, cudaMemcpyDeviceToDevice, st));
@@ -1436,21 +1701,27 @@ int crm_scan_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p
                          void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
-    return do_scan_interaction(&h->impl, (g_on_host >> 1) & 1, G, ldg, p, g_on_host & 1, Gtest, ldgt, out_pv, out_rho1, out_e2, out_g2, out_eps2, diag, (cudaStream_t)stream);
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    const GSource src{G, ldg, (g_on_host >> 4) & 15, g_on_host & 1}, tested{Gtest, ldgt, (g_on_host >> 4) & 15, g_on_host & 1};
+    return do_scan_interaction(&h->impl, (g_on_host >> 1) & 1, src, p, Gtest ? &tested : nullptr, out_pv, out_rho1, out_e2, out_g2, out_eps2, diag, (cudaStream_t)stream);
 }
 
 int crm_scan_association(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, int fast, double* out_pv,
                          double* out_alt_lml, double* info4, double* out_null_lml, void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
-    return do_scan_association(&h->impl, (g_on_host >> 1) & 1, G, ldg, p, g_on_host & 1, fast, out_pv, out_alt_lml, info4, out_null_lml, (cudaStream_t)stream);
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    const GSource src{G, ldg, (g_on_host >> 4) & 15, g_on_host & 1};
+    return do_scan_association(&h->impl, (g_on_host >> 1) & 1, src, p, fast, out_pv, out_alt_lml, info4, out_null_lml, (cudaStream_t)stream);
 }
 
 int crm_predict_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p, int g_on_host, const double* maf, int use_background,
                             double* out_beta_g, double* out_beta_gxe, int64_t ldo, double* out_rho1, void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
-    return do_predict(&h->impl, (g_on_host >> 1) & 1, G, ldg, p, g_on_host & 1, maf, use_background, out_beta_g, out_beta_gxe, ldo, out_rho1, (cudaStream_t)stream);
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    const GSource src{G, ldg, (g_on_host >> 4) & 15, g_on_host & 1};
+    return do_predict(&h->impl, (g_on_host >> 1) & 1, src, p, maf, use_background, out_beta_g, out_beta_gxe, ldo, out_rho1, (cudaStream_t)stream);
 }
 
 int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const double* B, int64_t ldb, int64_t b_cols, const double* B2,
@@ -1466,6 +1737,7 @@ int crm_gemm(int mode, const double* A, int64_t lda, int64_t a_cols, const doubl
 int crm_eigh_batched(const double* A, int n, int batch, double* W, double* V, double* quality_host, float* ms, void* stream) {
     if (!A || !W || !V || n < 2 || batch < 1) { set_error("crm_eigh_batched: bad arguments"); return CRM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    AllocScope alloc_scope(st);
     int dev = 0;
     CRM_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 16) { set_error("device index %d outside the supported range", dev); return CRM_ERR_UNSUPPORTED; }
@@ -1512,6 +1784,7 @@ int crm_int8_split_gemm(const double* X, int64_t ldx, int64_t cols, const double
                         int32_t* flags2, float* contraction_ms, void* stream) {
     if (!X || !G || !C || !flags2 || cols <= 0 || B <= 0 || n <= 0 || ldx < cols || ldg < B || ldc < cols || route < 0 || route > 2) { set_error("crm_int8_split_gemm: bad arguments"); return CRM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    AllocScope alloc_scope(st);
     const long long Mp = round_up(cols, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
     DevBuf P8, expo, Gt8, flags, D32;
     CRM_CHECK(P8.reserve((size_t)OZAKI_SLICES * Mp * Kp)); CRM_CHECK(expo.reserve((size_t)cols * 4)); CRM_CHECK(Gt8.reserve((size_t)Bp * Kp)); CRM_CHECK(flags.reserve(64));
@@ -1583,6 +1856,13 @@ int crm_lrt_pvalues(const double* alt_lml, double null_lml, int64_t count, doubl
     if (!alt_lml || !pv || count < 0) { set_error("crm_lrt_pvalues: bad arguments"); return CRM_ERR_INVALID; }
     if (count == 0) return CRM_OK;
     return launch_lrt(alt_lml, null_lml, count, pv, (cudaStream_t)stream);
+}
+
+int crm_lrt_pvalues_dof(const double* alt_lml, double null_lml, int64_t count, double dof, double* pv, void* stream) {
+    if (!alt_lml || !pv || count < 0 || !(dof > 0.0)) { set_error("crm_lrt_pvalues_dof: bad arguments"); return CRM_ERR_INVALID; }
+    if (count == 0) return CRM_OK;
+    if (dof == 1.0) return launch_lrt(alt_lml, null_lml, count, pv, (cudaStream_t)stream);
+    return launch_lrt_dof(alt_lml, null_lml, count, dof, pv, (cudaStream_t)stream);
 }
 
 }  // extern "C"

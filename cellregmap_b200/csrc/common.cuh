@@ -14,6 +14,7 @@ enum : int {
     CRM_ERR_INVALID = -1,      // invalid argument
     CRM_ERR_UNSUPPORTED = -2,  // shape outside the compiled limits
     CRM_ERR_STATE = -3,        // handle not set up
+    CRM_ERR_NONFINITE = -4,    // non-finite values in an input matrix
     CRM_ERR_CUDA = 1,          // CUDA runtime / driver error
     CRM_ERR_SOLVER = 2,        // cuSOLVER error or non-converged eigendecomposition
 };

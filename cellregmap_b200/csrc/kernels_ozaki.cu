@@ -45,9 +45,33 @@ int oz_launch_matrix_planes(const double* X, long long ldx, int cols, long long 
 }
 
 int oz_launch_genotypes(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st) {
-    CRM_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
+    CRM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
     dim3 grid((unsigned)((Kp + OZ_ROWS - 1) / OZ_ROWS), (unsigned)((Bp + OZ_TILE - 1) / OZ_TILE), 1);
     oz_genotype_kernel<<<grid, 256, 0, st>>>(G, ldg, n, B, Gt8, G2t8, Bp, Kp, flags);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
+int oz_launch_transpose_i8(const int8_t* G8, long long ld8, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st) {
+    if (flags) CRM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
+    dim3 grid((unsigned)((Kp + 127) / 128), (unsigned)((Bp + 127) / 128), 1);
+    oz_transpose_i8_kernel<<<grid, 256, 0, st>>>(G8, ld8, n, B, Gt8, G2t8, Bp, Kp, flags);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
+int oz_launch_widen_i8(const int8_t* G8, long long ld8, long long n, long long B, double* out, long long ldo, cudaStream_t st) {
+    const long long total = n * B;
+    if (total <= 0) return CRM_OK;
+    oz_widen_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(G8, ld8, n, B, out, ldo);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
+int oz_launch_finite_check(const double* G, long long ldg, long long n, long long B, int* flags, cudaStream_t st) {
+    const long long total = n * B;
+    if (total <= 0) return CRM_OK;
+    oz_finite_check_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(G, ldg, n, B, flags);
     CRM_CUDA(cudaGetLastError()); count_launch();
     return CRM_OK;
 }

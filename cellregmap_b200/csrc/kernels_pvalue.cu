@@ -17,6 +17,13 @@ int launch_lrt(const double* alt_lml, double null_lml, long long count, double* 
     return CRM_OK;
 }
 
+int launch_lrt_dof(const double* alt_lml, double null_lml, long long count, double dof, double* pv, cudaStream_t st) {
+    if (count <= 0) return CRM_OK;
+    crm_lrt_dof_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(alt_lml, null_lml, (int)count, dof, pv);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
 int launch_liu_params(const double* Q, const double* lam, const int* nlam, int lam_ld, long long count, double* out, cudaStream_t st) {
     if (count <= 0) return CRM_OK;
     crm_liu_params_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(Q, lam, nlam, lam_ld, (int)count, out);

@@ -40,6 +40,7 @@ int launch_beta_gxe(const double* E0, long long lde0, const double* coef, int k0
 int launch_liu_params(const double* Q, const double* lam, const int* nlam, int lam_ld, long long count, double* out, cudaStream_t st);
 int launch_qmin(const double* params, int nrho, long long count, double* out, cudaStream_t st);
 int launch_lrt(const double* alt_lml, double null_lml, long long count, double* pv, cudaStream_t st);
+int launch_lrt_dof(const double* alt_lml, double null_lml, long long count, double dof, double* pv, cudaStream_t st);
 
 // exact int8 split of the rotation (ozaki.cuh / kernels_ozaki.cu)
 constexpr int OZAKI_SLICES = 8;
@@ -47,6 +48,10 @@ int oz_launch_exponents(const double* Hx, int ldH, const double* Eext, int epitc
 int oz_launch_slices(const double* Hx, int ldH, const double* Eext, int epitch, int j0, int nj, long long n, const int* expo, int8_t* A8, long long Mp,
                      long long Kp, cudaStream_t st);
 int oz_launch_genotypes(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st);
+// int8 dosages stored row-major (cells x SNPs): K-major operands of the contraction (flags may be null), float64 image, finiteness
+int oz_launch_transpose_i8(const int8_t* G8, long long ld8, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st);
+int oz_launch_widen_i8(const int8_t* G8, long long ld8, long long n, long long B, double* out, long long ldo, cudaStream_t st);
+int oz_launch_finite_check(const double* G, long long ldg, long long n, long long B, int* flags, cudaStream_t st);
 int oz_launch_matrix_planes(const double* X, long long ldx, int cols, long long n, int* expo, int8_t* P8, long long Mp, long long Kp, cudaStream_t st);
 int oz_launch_combine(const int* D, long long Mp, long long ldd, const int* expo, long long Mtot, long long B, double* C, long long ldc, cudaStream_t st);
 // the same contraction + recombination in one hand-written tcgen05 kernel (oz_mma.cuh): C[s][col], bit-identical

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) oz_matrix_slice_kernel(const double* X, l
 }
 
 // Gt8[s][i] = (int8) G[i][s] for a block of SNP columns (K-major), zero padded to Bp x Kp; flags[0] |= 1 when some entry is
-// not an integer in [-127, 127]; flags[1] = max |g|
+// not an integer in [-127, 127]; flags[1] = max |g|; flags[2] |= 1 when some entry is not finite
 // G2t8 (may be null) receives the squares g^2 (valid when max |g| <= 11).  128 cells x 32 SNPs per block, char4 stores.
 __global__ void __launch_bounds__(256) oz_genotype_kernel(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp,
                                                           long long Kp, int* flags) {
@@ -142,14 +142,14 @@ __global__ void __launch_bounds__(256) oz_genotype_kernel(const double* G, long 
         double v = 0.0;
         if (i < n && s < B) {
             v = G[i * ldg + s];
-            if (!(v == rint(v)) || fabs(v) > 127.0) bad = 1; else gmax = max(gmax, (int)fabs(v));
+            if (!(v == rint(v)) || fabs(v) > 127.0) { bad = 1; if (!isfinite(v)) bad = 3; } else gmax = max(gmax, (int)fabs(v));
         }
         tile[r][tx] = v;
     }
-    bad = __any_sync(0xffffffffu, bad);
+    bad = __reduce_or_sync(0xffffffffu, bad);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    if (tx == 0) { if (bad) atomicOr(&s_bad, 1); atomicMax(&s_max, gmax); }
+    if (tx == 0) { if (bad) atomicOr(&s_bad, bad); atomicMax(&s_max, gmax); }
     __syncthreads();
     for (int r = ty; r < OZ_TILE; r += 8) {
         const long long s = s0 + r, i = i0 + 4 * tx;
@@ -165,8 +165,71 @@ __global__ void __launch_bounds__(256) oz_genotype_kernel(const double* G, long 
     }
     if (threadIdx.x == 0) {      // one (conditional) atomic per block
         if (s_bad) atomicOr(&flags[0], 1);
+        if (s_bad & 2) atomicOr(&flags[2], 1);
         if (s_max > *reinterpret_cast<volatile int*>(&flags[1])) atomicMax(&flags[1], s_max);
     }
+}
+
+// The same from int8 dosages stored row-major (cells x SNPs, row stride ld8 bytes): Gt8[s][i] = G8[i][s], G2t8[s][i] = G8[i][s]^2.
+// flags[0] |= 1 when some entry is -128 (outside the symmetric range the split uses); flags[1] = max |g|.  128 x 128 tiles.
+__global__ void __launch_bounds__(256) oz_transpose_i8_kernel(const int8_t* G8, long long ld8, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp,
+                                                              long long Kp, int* flags) {
+    __shared__ int8_t tile[128][129];          // row pitch = 1 (mod 32) bytes: the transposed reads of a warp hit 32 different banks
+    __shared__ int s_bad, s_max;
+    const long long i0 = (long long)blockIdx.x * 128, s0 = (long long)blockIdx.y * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_bad = 0; s_max = 0; }
+    __syncthreads();
+    int bad = 0, gmax = 0;
+    for (int r = warp; r < 128; r += 8) {
+        const long long i = i0 + r;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long s = s0 + 4 * lane + u;
+            int v = 0;
+            if (i < n && s < B) v = G8[i * ld8 + s];
+            if (v == -128) { bad = 1; v = 0; }
+            gmax = max(gmax, abs(v));
+            tile[r][4 * lane + u] = (int8_t)v;
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if (lane == 0) { if (bad) atomicOr(&s_bad, 1); atomicMax(&s_max, gmax); }
+    __syncthreads();
+    for (int r = warp; r < 128; r += 8) {
+        const long long s = s0 + r, i = i0 + 4 * lane;
+        if (s < Bp && i < Kp) {
+            char4 q, q2;
+            signed char* a = reinterpret_cast<signed char*>(&q);
+            signed char* b = reinterpret_cast<signed char*>(&q2);
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int gv = tile[4 * lane + u][r]; a[u] = (signed char)gv; b[u] = (signed char)(gv * gv); }
+            *reinterpret_cast<char4*>(Gt8 + s * Kp + i) = q;
+            if (G2t8) *reinterpret_cast<char4*>(G2t8 + s * Kp + i) = q2;
+        }
+    }
+    if (threadIdx.x == 0 && flags) {
+        if (s_bad) atomicOr(&flags[0], 1);
+        if (s_max > *reinterpret_cast<volatile int*>(&flags[1])) atomicMax(&flags[1], s_max);
+    }
+}
+
+// float64 image of a block of int8 dosages (row-major in, row-major out)
+__global__ void oz_widen_i8_kernel(const int8_t* G8, long long ld8, long long n, long long B, double* out, long long ldo) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * B) return;
+    const long long i = idx / B, s = idx - i * B;
+    out[i * ldo + s] = (double)G8[i * ld8 + s];
+}
+// flags[2] |= 1 when some entry of the block is not finite
+__global__ void oz_finite_check_kernel(const double* G, long long ldg, long long n, long long B, int* flags) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    if (idx < n * B) { const long long i = idx / B, s = idx - i * B; bad = !isfinite(G[i * ldg + s]); }
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicOr(&flags[2], 1);
 }
 
 // C[s][col] = 2^(e_col + 1) sum_t 2^(-7 (t + 1)) D[t * Mp + col][s]   (D int32, row stride ldd; C fp64, row stride ldc)

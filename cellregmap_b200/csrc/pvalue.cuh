@@ -408,4 +408,14 @@ __global__ void crm_lrt_kernel(const double* alt_lml, double null_lml, int count
     pv[i] = fmin(fmax(p, 2.2250738585072014e-308), 1.0 - CRM_EPS_TINY);
 }
 
+// the same for any number of degrees of freedom: chi2(dof).sf through the regularised upper incomplete gamma function
+__global__ void crm_lrt_dof_kernel(const double* alt_lml, double null_lml, int count, double dof, double* pv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double lr = -2.0 * null_lml + 2.0 * alt_lml[i];
+    lr = fmax(lr, 2.2250738585072014e-308);
+    const double p = chi2_sf(lr, dof);
+    pv[i] = fmin(fmax(p, 2.2250738585072014e-308), 1.0 - CRM_EPS_TINY);
+}
+
 }  // namespace crm

@@ -9,7 +9,7 @@
  * pointer is a DEVICE pointer unless the parameter name ends in `_host`; sizes are int64_t / int; `stream` is a
  * cudaStream_t passed as void* (NULL = default stream); the caller owns inputs and outputs (outputs must be
  * allocated by the caller), internal workspaces are owned by the handle.  Return value: 0 ok, <0 invalid
- * argument / unsupported shape / bad state, >0 CUDA or cuSOLVER failure; crm_last_error() gives the message of
+ * argument / unsupported shape / bad state (-4: non-finite values in an input matrix), >0 CUDA or cuSOLVER failure; crm_last_error() gives the message of
  * the last failure on the calling thread.  No exceptions cross the boundary.  A handle is not thread-safe;
  * different handles may be used from different threads.
  */
@@ -34,6 +34,10 @@ CRM_API const char* crm_last_error(void);
 /* Model object: replaces CellRegMap.__init__ state (cellregmap/_cellregmap.py:63-131). */
 CRM_API int crm_create(crm_handle_t* out, int device);
 CRM_API int crm_destroy(crm_handle_t h);
+/* Device memory is allocated stream-ordered (on the `stream` of the call in flight) from a private per-device pool that keeps freed
+ * blocks for the next model object; crm_destroy releases a handle's buffers in the order of the stream of its latest call, without a
+ * device-wide synchronisation.  crm_trim_pool returns the cached blocks of `device` to the driver. */
+CRM_API int crm_trim_pool(int device);
 
 /*
  * Constructor set-up (cellregmap/_cellregmap.py:93-131 + numpy_sugar.economic_qs_linear, semantics in
@@ -54,6 +58,24 @@ CRM_API int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t 
  * quarter of the device memory is not staged (the scan streams it as usual).  The host array must stay alive and unchanged until that
  * scan returns.  (Extension: the reference passes G to scan_interaction only, cellregmap/_cellregmap.py:317.) */
 CRM_API int crm_stage_genotypes(crm_handle_t h, const double* G_host, int64_t ldg, int64_t rows, int64_t p, void* stream);
+
+/* Element types of genotype matrices.  Device matrices may be CRM_G_F64 or CRM_G_I8; host matrices any of them.  The scan entry points
+ * take the type in bits 4..7 of their `g_on_host` argument (0 = float64, the reference's asarray(G, float)); the data pointer is then
+ * reinterpreted and the leading dimension counts elements of that type. */
+enum { CRM_G_F64 = 0, CRM_G_I8 = 1, CRM_G_U8 = 2, CRM_G_I16 = 3, CRM_G_I32 = 4, CRM_G_F32 = 5, CRM_G_I64 = 6 };
+#define CRM_G_FLAGS(on_host, donor_level, dtype) (((on_host) ? 1 : 0) | ((donor_level) ? 2 : 0) | ((dtype) << 4))
+
+/* crm_stage_genotypes for any element type and any host memory.  Pinned float64 is moved by DMA as above.  Everything else -- in
+ * particular a pageable float64 numpy array, which is what a user of the reference passes -- is converted to int8 dosage blocks by a
+ * pool of host threads (CRM_HOST_THREADS, default min(CPUs, 16)) into pinned buffers, block by block ahead of the device: 1 byte per
+ * dosage crosses PCIe, and the conversion overlaps the set-up and the scan of earlier blocks.  A block that is not integer-valued in
+ * [-127, 127] ends the conversion; the rest of the matrix is moved as float64.  basis_cols_hint: (1 + k0) * (m + 1 + c) rounded up to
+ * even, or 0 (sizes the blocks to whole waves of the int8 contraction).  The host array must stay alive and unchanged until the scan
+ * that consumes it returns (or the handle is destroyed). */
+CRM_API int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dtype, int64_t ldg, int64_t rows, int64_t p,
+                                      int64_t basis_cols_hint, void* stream);
+/* Worker threads of the host feeder. */
+CRM_API int crm_host_threads(void);
 
 /* Replaces the tested-context matrix E0 (row-permuted contexts: idx_E of scan_interaction, _cellregmap.py:398-401). */
 CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream);
@@ -183,6 +205,8 @@ CRM_API int crm_qmin(const double* params4, int nrho, int64_t count, double* out
 
 /* lrt_pvalues (cellregmap/_cellregmap.py:443-469) with dof = 1. */
 CRM_API int crm_lrt_pvalues(const double* alt_lml, double null_lml, int64_t count, double* pv, void* stream);
+/* The same for any dof > 0 (chi2(dof).sf; dof = 1 takes the erfc form above). */
+CRM_API int crm_lrt_pvalues_dof(const double* alt_lml, double null_lml, int64_t count, double dof, double* pv, void* stream);
 
 #ifdef __cplusplus
 }

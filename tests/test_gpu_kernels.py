@@ -209,6 +209,8 @@ def test_lrt_pvalues(cuda_device):
     got = lrt_pvalues(-100.0, alt)
     want = ref(-100.0, alt)
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    for dof in (2, 3, 7, 0.5):         # any number of degrees of freedom (reference :443-469 takes `dof`)
+        np.testing.assert_allclose(lrt_pvalues(-100.0, alt, dof=dof), ref(-100.0, alt, dof=dof), rtol=1e-11, atol=0)
 
 
 @pytest.mark.parametrize("restricted", [True, False])

@@ -13,11 +13,11 @@ import os
 import numpy as np
 import pytest
 
+from _parity import DLOG10_P, assert_pvalues, assert_variance_components
+
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-RTOL_VC = 1e-6
-DLOG10_P = 1e-4
 
 
 def _fixtures():
@@ -26,12 +26,8 @@ def _fixtures():
 
 def _check(pv, info, ref_pv, ref_info, ranking=True):
     np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
-    for key in ("e2", "g2", "eps2"):
-        np.testing.assert_allclose(info[key], ref_info[key], rtol=RTOL_VC, atol=1e-12)
-    big = ref_pv >= 1e-12
-    assert np.max(np.abs(np.log10(pv[big]) - np.log10(ref_pv[big]))) <= DLOG10_P
-    if ranking:
-        np.testing.assert_array_equal(np.argsort(pv, kind="stable"), np.argsort(ref_pv, kind="stable"))
+    assert_variance_components(info, ref_info)
+    assert_pvalues(pv, ref_pv, ranking)
 
 
 def _ref_info(g, prefix):
@@ -68,8 +64,7 @@ def test_association_scans_match_reference_source(cuda_device, path):
         ref_pv = g[key + "_pv"]
         np.testing.assert_array_equal(info["rho1"], g[key + "_rho1"])
         assert info["rho1"].shape == (1,)
-        for k in ("e2", "g2", "eps2"):
-            np.testing.assert_allclose(info[k], g[f"{key}_{k}"], rtol=RTOL_VC, atol=1e-12)
+        assert_variance_components(info, {k: g[f"{key}_{k}"] for k in ("e2", "g2", "eps2")})
         big = ref_pv >= 1e-12
         assert np.max(np.abs(np.log10(pv[big]) - np.log10(ref_pv[big]))) <= DLOG10_P
 

@@ -456,3 +456,112 @@ def test_int8_split_rotation_matches_fp64_rotation(cuda_device, monkeypatch):
     m_bad = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
     with pytest.raises(RuntimeError):
         m_bad.scan_interaction(Gf)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# genotype ingress: every storage a caller may pass gives the bits of the device-resident float64 call
+# ------------------------------------------------------------------------------------------------------------------
+def _scan_bits(model, G, **kw):
+    pv, info = model.scan_interaction(G, **kw)
+    return np.concatenate([pv] + [info[k] for k in ("rho1", "e2", "g2", "eps2")])
+
+
+@pytest.mark.parametrize("feeder_block", ["64", "0"])
+def test_host_genotype_storages_agree_bitwise(cuda_device, monkeypatch, feeder_block):
+    """Pageable float64 numpy (what a reference user passes: host feeder -> int8 blocks), pinned float64 (DMA), int8 / uint8 /
+    int16 / int32 / int64 / float32 host arrays, a column slice of a wider array, an int8 device tensor."""
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    if feeder_block != "0":
+        monkeypatch.setenv("CRM_FEEDER_BLOCK", feeder_block)      # several blocks through the ring of pinned slots
+    d = make_data(n=600, donors=40, k=6, p=333, q=5, seed=12)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    want = _scan_bits(model, torch.from_numpy(d.G).cuda())
+    wide = np.zeros((600, 400))
+    wide[:, 31:364] = d.G
+    for name, G in (("pageable float64", d.G), ("pinned float64", torch.from_numpy(d.G).pin_memory()), ("int8", d.G.astype(np.int8)),
+                    ("uint8", d.G.astype(np.uint8)), ("int16", d.G.astype(np.int16)), ("int32", d.G.astype(np.int32)), ("int64", d.G.astype(np.int64)),
+                    ("float32", d.G.astype(np.float32)), ("column slice", wide[:, 31:364]), ("int8 device", torch.from_numpy(d.G.astype(np.int8)).cuda()),
+                    ("int8 column slice", wide.astype(np.int8)[:, 31:364])):
+        np.testing.assert_array_equal(_scan_bits(model, G), want, err_msg=name)
+
+
+def test_run_interaction_prefetches_pageable_genotypes(cuda_device, monkeypatch):
+    """run_interaction starts the feeder in the constructor (under the set-up); same bits as the device call."""
+    import torch
+    from cellregmap_b200 import run_interaction
+    monkeypatch.setenv("CRM_FEEDER_BLOCK", "96")
+    d = make_data(n=500, donors=40, k=5, p=250, q=4, seed=13)
+    pv_dev, info_dev = run_interaction(d.y, d.E, torch.from_numpy(d.G).cuda(), W=d.W, hK=d.hK)
+    for G in (d.G, d.G.astype(np.int8), np.asfortranarray(d.G)):
+        pv, info = run_interaction(d.y, d.E, G, W=d.W, hK=d.hK)
+        np.testing.assert_array_equal(pv, pv_dev)
+        np.testing.assert_array_equal(info["eps2"], info_dev["eps2"])
+
+
+def test_non_integer_host_genotypes_leave_the_feeder(cuda_device, monkeypatch):
+    """Real-valued genotypes on the host: the feeder reports the first block that is not integer dosages and the rest of the matrix is
+    moved as float64 -- including a matrix whose first blocks are integer and whose later ones are not."""
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    monkeypatch.setenv("CRM_FEEDER_BLOCK", "64")
+    d = make_data(n=500, donors=40, k=5, p=200, q=4, seed=14)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    Gstd = np.ascontiguousarray((d.G - d.G.mean(0)) / d.G.std(0))
+    Gmix = d.G.copy()
+    Gmix[:, 130:] = Gstd[:, 130:]
+    for G in (Gstd, Gstd.astype(np.float32)):
+        want = _scan_bits(model, torch.from_numpy(np.asarray(G, dtype=np.float64)).cuda())
+        np.testing.assert_array_equal(_scan_bits(model, G), want)
+    # integer blocks take the int8 contraction, the device-resident call contracts the whole (non-integer) matrix in float64:
+    # same values up to the round-off of the two contractions
+    want = _scan_bits(model, torch.from_numpy(Gmix).cuda())
+    got = _scan_bits(model, Gmix)
+    np.testing.assert_array_equal(got[130:200], want[130:200])
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-12)
+
+
+def test_non_finite_inputs_raise_like_the_reference(cuda_device):
+    import torch
+    from cellregmap_b200 import CellRegMap, run_association, run_interaction
+    d = make_data(n=300, donors=30, k=4, p=40, q=3, seed=15)
+    G = d.G.copy()
+    G[17, 23] = np.nan
+    for Gbad in (G, torch.from_numpy(G).cuda(), G.astype(np.float32)):
+        with pytest.raises(ValueError, match="non-finite values in the covariates matrix"):     # glimix_core.lmm.LMM on X = [W g]
+            run_interaction(d.y, d.E, Gbad, W=d.W, hK=d.hK)
+    with pytest.raises(ValueError, match="non-finite"):
+        run_association(d.y, d.W, d.E, G, hK=d.hK)
+    E = d.E.copy()
+    E[3, 1] = np.inf
+    with pytest.raises(ValueError, match="non-finite values in E"):
+        CellRegMap(d.y, E, W=d.W, hK=d.hK)
+    y = d.y.copy()
+    y[0] = np.nan
+    with pytest.raises(ValueError, match="non-finite values in the outcome"):
+        CellRegMap(y, d.E, W=d.W)
+
+
+def test_scan_and_predict_on_a_side_stream(cuda_device, monkeypatch):
+    """Allocations are stream-ordered on the caller's stream: a scan and a predict with host-streamed genotypes under a
+    non-default, non-blocking torch stream (buffers grow between blocks) give the default-stream results."""
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    monkeypatch.setenv("CRM_FEEDER_BLOCK", "64")
+    d = make_data(n=500, donors=40, k=5, p=300, q=4, seed=16)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    want = _scan_bits(model, d.G)
+    maf = np.clip(d.G.mean(0) / 2, 0.01, 0.99)
+    bg0, bx0 = model.predict_interaction(d.G[:, :40], maf[:40])
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        m2 = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+        got = _scan_bits(m2, d.G)
+        bg1, bx1 = m2.predict_interaction(d.G[:, :40], maf[:40])
+        got_std = _scan_bits(m2, d.G / 3.0)          # float64 route, pageable
+    side.synchronize()
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(bg1, bg0)
+    np.testing.assert_array_equal(bx1, bx0)
+    np.testing.assert_array_equal(got_std, _scan_bits(model, torch.from_numpy(d.G / 3.0).cuda()))
+    del m2
