@@ -1,17 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: SNP-gene GxC interaction tests per second of `run_interaction`
-(BASELINE.json metric; workload = configs[2]: n = 100k cells, 1,000 donors, k = 20 contexts, low-rank hK
-(q = 50 -> m = 1,020), 10k SNPs per GPU).
+(BASELINE.json metric; default workload = configs[2]: n = 100k cells, 1,000 donors, k = 20 contexts, low-rank hK
+(q = 50 -> m = 1,020), 10k SNPs sharded over the GPUs).
 
-    python bench.py --gpus N --steps K --warmup W                 # this implementation (one rank per GPU)
-    python bench.py --impl reference --gpus N --steps K --warmup W  # CPU restatement of the reference path
+    python bench.py --gpus N --steps K --warmup W                   # this implementation (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's own code on the host cores
+    python bench.py --config 1|2|4|5                                # the other BASELINE.json configs (1 GPU; bench lines for BASELINE.md)
 
-One step = one whole `run_interaction` job over the rank's SNP shard: constructor set-up (Gram,
-11 eigendecompositions) + rotation + 11 REML fits/SNP + score statistic + Davies/Liu p-values.
-`value` times it with every input already resident in HBM; `e2e` times the public API call with host
-buffers (host->device copies of y, E, W, hK and the genotype matrix, device->host read of the results inside
-the timed region).  SNPs shard across ranks with no data-path collective except the final all-gather of the
-5 per-SNP outputs ("scaling": "weak": every rank scans its own 10k SNPs of the same gene).
+One step = one whole job: constructor set-up (Gram, 11 eigendecompositions) + rotation + 11 REML fits/SNP + score statistic +
+Davies/Liu p-values for every SNP.  `value` times it with every input already resident in HBM; `e2e` times the public API call
+with plain (pageable) numpy arrays -- what a user of the reference passes -- host->device transfers and the device->host read of
+the results inside the timed region.  N > 1 (`"scaling": "strong"`, configs[2] as written): the 10k SNPs of the one gene are sharded
+over the ranks (cellregmap_b200.distributed.run_interaction_sharded: shared set-up, per-rank column blocks, one all-gather of the
+5 per-SNP outputs); `weak_scaling` in the same line repeats the measurement with 10k SNPs per GPU.
 """
 import argparse
 import json
@@ -27,20 +28,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "SNP-gene GxC tests/sec (run_interaction, n=100k cells, k=20)"
 UNIT = "tests/s"
-# measured on this pool's B200 (profiles/r01_dmma_probe.txt): DMMA.8x8x4 issue-rate peak; cuBLAS DGEMM reaches 35.4
-FP64_TENSOR_PEAK_TFLOPS = 37.1
-# dram__bytes_read.sum + dram__bytes_write.sum of the rotation launch at the default workload, from one ncu capture
-# (profiles/r01_ncu_rotation_traffic_benchsize.csv): 465.7 GB read + 1.8 GB written per 10k-SNP launch, against 27 GB of
-# algorithmic bytes (G 8 GB + pre-expanded basis 17.2 GB + output 1.7 GB) -- operand panels are re-read through L2 by the
-# 13 272 CTAs; 395 GB/s = 6 % of the HBM peak, the kernel is bound by the FP64 tensor pipe (99 % active).
-ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD = 465728855296 + 1766195200
-# the same for one launch of oz_mma_kernel at the default workload (profiles/r01_ncu_oz_mma_kernel.txt): 320.7 GB read + 6.9 GB
-# written against 19.9 GB of algorithmic bytes (17.2 GB digit planes + 1.0 GB int8 dosages + 1.7 GB output) -- the 148 persistent
-# CTAs re-stream their operand panels through L2 (hit rate 64 %); 3.0 TB/s = 36 % of the HBM peak, the kernel is bound by the int8
-# tensor pipe under the power cap and by L2 -> SM bandwidth (47.7 B/clk/SM)
-OZ_MMA_DRAM_BYTES_DEFAULT_WORKLOAD = 320706872000 + 6889898000
+# BASELINE.json configs: (entry point, cells, donors, contexts, hK rank, SNPs)
+CONFIGS = {
+    1: ("run_interaction", 500, 50, 10, 50, 100),
+    2: ("run_interaction", 10000, 200, 20, 10, 2000),
+    3: ("run_interaction", 100000, 1000, 20, 50, 10000),
+    4: ("run_association", 50000, 1000, 20, 50, 10000),
+    5: ("estimate_betas", 50000, 1000, 20, 50, 1000),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from ncu --set full captures
+# of the same command (profiles/): kernel name -> bytes
+NCU_TRAFFIC = {}
+try:
+    NCU_TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+except (OSError, ValueError):
+    pass
 
 
 def parse_args():
@@ -49,27 +52,45 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    # workload overrides (defaults = BASELINE configs[2]); used by the tests to run a tiny instance
-    ap.add_argument("--cells", type=int, default=100000)
-    ap.add_argument("--donors", type=int, default=1000)
-    ap.add_argument("--contexts", type=int, default=20)
-    ap.add_argument("--hk-rank", type=int, default=50)
-    ap.add_argument("--snps", type=int, default=10000, help="SNPs per GPU")
-    ap.add_argument("--cpu-sample-snps", type=int, default=8)
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: --snps sharded over the ranks (configs[2]) or --snps per rank")
+    # workload overrides (defaults come from --config); used by the tests to run a tiny instance
+    ap.add_argument("--cells", type=int)
+    ap.add_argument("--donors", type=int)
+    ap.add_argument("--contexts", type=int)
+    ap.add_argument("--hk-rank", type=int)
+    ap.add_argument("--snps", type=int, help="SNPs of the job (strong scaling: in total)")
+    ap.add_argument("--cpu-sample-snps", type=int, default=0, help="SNPs of the CPU sample (0: sized for ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-donor-level", action="store_true")
-    ap.add_argument("--no-fp64-route", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary arms (fp64 route, donor-level ingress, shared set-up, weak scaling)")
+    a = ap.parse_args()
+    entry, cells, donors, contexts, q, snps = CONFIGS[a.config]
+    a.entry = entry
+    a.cells = a.cells or cells
+    a.donors = a.donors or donors
+    a.contexts = a.contexts or contexts
+    a.hk_rank = a.hk_rank or q
+    a.snps = a.snps or snps
+    return a
+
+
+def metric_name(a):
+    if a.entry == "run_interaction":
+        return f"SNP-gene GxC tests/sec (run_interaction, n={a.cells // 1000}k cells, k={a.contexts})" if a.cells >= 1000 else \
+            f"SNP-gene GxC tests/sec (run_interaction, n={a.cells} cells, k={a.contexts})"
+    if a.entry == "run_association":
+        return f"SNP-gene association tests/sec (run_association, n={a.cells // 1000}k cells, k={a.contexts})"
+    return f"SNPs/sec with effect sizes (estimate_betas, n={a.cells // 1000}k cells, k={a.contexts})"
 
 
 def workload_name(a):
-    return (f"run_interaction n={a.cells} cells, {a.donors} donors, k={a.contexts}, low-rank hK q={a.hk_rank} "
-            f"(m={a.contexts * (1 + a.hk_rank)}), {a.snps} SNPs per GPU")
+    return (f"configs[{a.config - 1}]: {a.entry} n={a.cells} cells, {a.donors} donors, k={a.contexts}, low-rank hK q={a.hk_rank} "
+            f"(m={a.contexts * (1 + a.hk_rank) if a.entry != 'run_association' else a.contexts + a.hk_rank}), {a.snps} SNPs")
 
 
 # ------------------------------------------------------------------------------------------------
-# synthetic gene: host part (small arrays) + genotype shard
+# synthetic gene: host part (small arrays) + genotypes
 # ------------------------------------------------------------------------------------------------
 def make_gene(a, seed=0):
     """y, W, E, hK of one gene (identical on every rank) -- recipe of cellregmap_b200/synth.py at scale."""
@@ -93,17 +114,18 @@ def make_gene(a, seed=0):
     return {"y": y, "W": W, "E": np.ascontiguousarray(E), "hK": hK, "donor": donor, "rng_state": seed}
 
 
-def donor_genotypes(a, rank, seed=0):
-    rng = np.random.default_rng(1000 + 17 * rank + seed)
-    maf = rng.uniform(0.05, 0.45, a.snps)
-    Gd = rng.binomial(2, maf, size=(a.donors, a.snps)).astype(np.float64)
+def donor_genotypes(a, part, snps, seed=0):
+    """donors x snps dosages; `part` selects an independent stream (weak scaling: one per rank)."""
+    rng = np.random.default_rng(1000 + 17 * part + seed)
+    maf = rng.uniform(0.05, 0.45, snps)
+    Gd = rng.binomial(2, maf, size=(a.donors, snps)).astype(np.float64)
     for j in np.where(Gd.std(0) == 0)[0]:
         Gd[rng.integers(0, a.donors), j] += 1.0
     return Gd
 
 
-def add_causal_effects(gene, Gd_rank0, a):
-    """persistent effects of SNPs 5, 6 and GxC effects of SNPs 10, 11 of rank 0's shard (reference test recipe)."""
+def add_causal_effects(gene, Gd, a):
+    """persistent effects of SNPs 5, 6 and GxC effects of SNPs 10, 11 (reference test recipe)."""
     rng = np.random.default_rng(99)
     donor, E, y = gene["donor"], gene["E"], gene["y"]
 
@@ -112,8 +134,8 @@ def add_causal_effects(gene, Gd_rank0, a):
         s = v.std()
         return v / s if s > 0 else v
 
-    if a.snps > 11:
-        g = np.stack([Gd_rank0[:, j][donor] for j in (5, 6, 10, 11)], 1)
+    if Gd.shape[1] > 11:
+        g = np.stack([Gd[:, j][donor] for j in (5, 6, 10, 11)], 1)
         y += np.sqrt(0.03) * norm(norm(g[:, 0]) * rng.standard_normal() + norm(g[:, 1]) * rng.standard_normal())
         y += np.sqrt(0.02) * norm(norm(g[:, 2]) * (E @ rng.standard_normal(E.shape[1])) + norm(g[:, 3]) * (E @ rng.standard_normal(E.shape[1])))
     return gene
@@ -122,9 +144,10 @@ def add_causal_effects(gene, Gd_rank0, a):
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
-def pin_to_gpu_numa_node(device_index):
-    """Bind this process to the CPUs NVML reports as local to the GPU, so that the pinned host buffers of the e2e arm (first touch)
-    and the driver calls stay on the GPU's socket: a buffer on the far socket halves the host-to-device rate.  Best effort."""
+def pin_to_gpu_numa_node(device_index, local_world=1, local_rank=0):
+    """Bind this process to the CPUs NVML reports as local to the GPU (a pinned buffer on the far socket halves the host-to-device
+    rate); with several ranks per box each takes its own slice of them, so that the host feeders of the ranks do not share cores.
+    Best effort; returns the CPU list."""
     try:
         import pynvml
         import torch
@@ -136,9 +159,14 @@ def pin_to_gpu_numa_node(device_index):
         mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
         cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
         cpus &= set(os.sched_getaffinity(0))
+        cpus = sorted(cpus)
+        if cpus and local_world > 1:
+            share = max(1, len(cpus) // local_world)
+            mine = cpus[local_rank * share:(local_rank + 1) * share] if (local_rank + 1) * share <= len(cpus) else cpus
+            cpus = mine or cpus
         if cpus:
-            os.sched_setaffinity(0, cpus)
-        return sorted(cpus)
+            os.sched_setaffinity(0, set(cpus))
+        return cpus
     except Exception:       # NVML missing, no affinity information, restricted container ...
         return None
 
@@ -193,47 +221,71 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle's restatement of the reference path, bounded sample
+# CPU arm: the reference's own source (oracle/_ref, over the dependency stand-ins of oracle/) or the oracle port, bounded sample
 # ------------------------------------------------------------------------------------------------
+def default_cpu_sample(a):
+    """SNPs for roughly 10-30 s of CPU work on a 16-core host (measured per-SNP costs of the reference path)."""
+    if a.cpu_sample_snps > 0:
+        return min(a.cpu_sample_snps, a.snps)
+    per_config = {1: 100, 2: 60, 3: 8, 4: 16, 5: 1}
+    return max(1, min(per_config[a.config], a.snps))
+
+
 def cpu_reference_sample(a, gene, Gd, n_snps, repeats=1):
-    """Times the reference algorithm (oracle port: per-(SNP, rho1) LMM construction + rotation + Brent,
-    structured projection, Davies) on the first `n_snps` SNPs.  Set-up (11 economic decompositions) is built
-    once, outside the timed region, via the Gram route (qs_method="gram") so that the run stays bounded; per-SNP
-    cost in the reference does not depend on the number of SNPs, so tests/s = SNPs / scan seconds."""
-    from oracle import crm_port
+    """Times the reference algorithm on the first `n_snps` SNPs with all host threads.  The code that runs is the reference's own
+    cellregmap/_cellregmap.py + _math.py (byte-compiled into oracle/_ref, imported over the stand-ins for glimix_core / numpy_sugar /
+    chiscore) when it is present, else the oracle's restatement of it (same arithmetic, tests/test_reference_source.py).  The per-rho
+    economic decompositions of the constructor take the Gram route (same Q0, S0; a thin SVD of 1e5 x 1020 eleven times would take
+    minutes) and are built once, outside the timed region; per-SNP cost in the reference does not depend on the number of SNPs, so
+    tests/s = SNPs / scan seconds."""
     from threadpoolctl import threadpool_limits
+    from oracle import crm_port, ref_shims
+    ref = ref_shims.load_reference(qs_method="gram")
     threads = os.cpu_count() or 1
+    code = "reference source (oracle/_ref) over ported dependencies" if ref is not None else "oracle port"
+    G = np.ascontiguousarray(Gd[:, :n_snps][gene["donor"]])
+    y, W, E, hK = gene["y"], gene["W"], gene["E"], gene["hK"]
     # torchrun exports OMP_NUM_THREADS=1; the reference's only parallelism is the BLAS under numpy, so give it every core
     with threadpool_limits(limits=threads):
         t0 = time.time()
-        Ls = crm_port.get_L_values(gene["hK"], gene["E"])
-        model = crm_port.CellRegMapOracle(y=gene["y"], E=gene["E"], W=gene["W"], E1=gene["E"], Ls=Ls, qs_method="gram")
+        if a.entry == "run_association":            # reference :471-500 (positional quirk: W and E swap roles)
+            model = ref.CellRegMap(y, W, E, hK=hK) if ref is not None else crm_port.CellRegMapOracle(y, W, E, hK=hK, qs_method="gram")
+            scan = lambda: model.scan_association(G)                       # noqa: E731
+        else:
+            get_L = sys.modules["cellregmap._cellregmap"].get_L_values if ref is not None else crm_port.get_L_values
+            Ls = get_L(hK, E)
+            model = ref.CellRegMap(y=y, E=E, W=W, E1=E, Ls=Ls) if ref is not None else crm_port.CellRegMapOracle(y=y, E=E, W=W, E1=E, Ls=Ls, qs_method="gram")
+            if a.entry == "estimate_betas":         # reference :640-682 (per (SNP, rho1) decompositions inside the timed region)
+                maf = crm_port.compute_maf(G)
+                scan = lambda: model.predict_interaction(G, maf)           # noqa: E731
+            else:
+                scan = lambda: model.scan_interaction(G)                   # noqa: E731
         setup_s = time.time() - t0
-        G = np.ascontiguousarray(Gd[:, :n_snps][gene["donor"]])
         times = []
         for _ in range(repeats):
             t0 = time.time()
-            model.scan_interaction(G)
+            scan()
             times.append(time.time() - t0)
-    return {"scan_s": times, "setup_s": setup_s, "cores": threads, "snps": n_snps}
+    return {"scan_s": times, "setup_s": setup_s, "cores": threads, "snps": n_snps, "code": code}
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ.setdefault("TQDM_DISABLE", "1")
     gene = make_gene(a)
-    Gd = donor_genotypes(a, 0)
+    ns = default_cpu_sample(a)
+    Gd = donor_genotypes(a, 0, a.snps)
     gene = add_causal_effects(gene, Gd, a)
-    ns = max(1, min(a.cpu_sample_snps, a.snps))
     res = cpu_reference_sample(a, gene, Gd, ns, repeats=a.warmup + a.steps)
     timed = res["scan_s"][a.warmup:]
     ms = 1e3 * float(np.mean(timed))
     value = ns / (ms / 1e3)
     sample = (f"first {ns} SNPs of the same gene per step, scan only; set-up ({res['setup_s']:.1f} s, Gram-route decompositions) "
-              f"built once outside the timed region; numpy/BLAS threads = {res['cores']}")
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+              f"built once outside the timed region; numpy/BLAS threads = {res['cores']}; code = {res['code']}")
+    line = {"metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": workload_name(a), "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -250,10 +302,15 @@ def run_b200_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if a.entry != "run_interaction" and world > 1:
+        raise SystemExit("--config 4 and 5 are single-GPU bench lines")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     full_affinity = os.sched_getaffinity(0)
-    local_cpus = None if os.environ.get("CRM_BENCH_NO_PIN") == "1" else pin_to_gpu_numa_node(local_rank)
+    local_cpus = None if os.environ.get("CRM_BENCH_NO_PIN") == "1" else pin_to_gpu_numa_node(local_rank, local_world, local_rank)
+    if local_cpus and "CRM_HOST_THREADS" not in os.environ:
+        os.environ["CRM_HOST_THREADS"] = str(max(1, min(16, len(local_cpus))))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
@@ -263,20 +320,24 @@ def run_b200_arm(a):
     import cellregmap_b200 as crm
     from cellregmap_b200 import _cellregmap as api
     from cellregmap_b200 import _lib
+    from cellregmap_b200 import distributed as crmd
 
     lib = _lib.load()
     gene = make_gene(a)
-    Gd0 = donor_genotypes(a, 0)
-    gene = add_causal_effects(gene, Gd0, a)
-    Gd = Gd0 if rank == 0 else donor_genotypes(a, rank)
-    p = a.snps
-    # device-resident inputs
+    p_total = a.snps                      # SNPs of the job the headline times
+    Gd = donor_genotypes(a, 0, p_total)   # the same matrix on every rank (strong scaling: each rank scans its column block)
+    gene = add_causal_effects(gene, Gd, a)
     y_d = torch.from_numpy(gene["y"]).to(dev)
     W_d = torch.from_numpy(gene["W"]).to(dev)
     E_d = torch.from_numpy(gene["E"]).to(dev)
     hK_d = torch.from_numpy(gene["hK"]).to(dev)
     donor_d = torch.from_numpy(gene["donor"]).to(dev)
-    G_d = torch.from_numpy(Gd).to(dev)[donor_d].contiguous()          # (n, p) float64 dosages, expanded donor -> cell
+    strong = world > 1 and a.scaling == "strong"
+    lo, hi = crmd.shard_range(p_total, rank, world) if strong else (0, p_total)
+    if world > 1 and not strong:          # weak scaling as the headline: every rank scans its own p_total SNPs
+        Gd = donor_genotypes(a, rank, p_total) if rank else Gd
+    # device-resident genotypes of this rank: (n, p_local) float64 dosages, expanded donor -> cell
+    G_d = torch.from_numpy(np.ascontiguousarray(Gd[:, lo:hi])).to(dev)[donor_d].contiguous()
     torch.cuda.synchronize()
 
     def barrier():
@@ -284,24 +345,29 @@ def run_b200_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gathered = torch.empty((world * 5, p), dtype=torch.float64, device=dev) if world > 1 else None
+    def stack5(out):
+        return torch.stack([out["pv"], out["rho1"], out["e2"], out["g2"], out["eps2"]])
 
-    debug = bool(os.environ.get("CRM_BENCH_DEBUG"))
+    gathered_weak = torch.empty((world * 5, p_total), dtype=torch.float64, device=dev) if world > 1 else None
 
+    # ---- the step, inputs resident in HBM ----
     def step_device():
-        t0 = time.time()
-        model = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev)
-        if debug:
-            torch.cuda.synchronize(); t1 = time.time()
+        if a.entry == "run_association":
+            return crm.run_association(y_d, W_d, E_d, G_d, hK=hK_d)[0]
+        if a.entry == "estimate_betas":
+            return crm.estimate_betas(y_d, W_d, E_d, G_d, maf=maf_d, hK=hK_d)[0]
+        model = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev, group=True if world > 1 else None)
         out = model._scan_interaction_device(G_d)
-        if debug:
-            torch.cuda.synchronize(); t2 = time.time()
-            print(f"[debug] rank {rank}: model {1e3 * (t1 - t0):.1f} ms, scan {1e3 * (t2 - t1):.1f} ms", file=sys.stderr)
-        res = torch.stack([out["pv"], out["rho1"], out["e2"], out["g2"], out["eps2"]])
-        if world > 1:   # the path's one exchange step: all-gather of the 5 per-SNP outputs
-            dist.all_gather_into_tensor(gathered, res)
-            return gathered
-        return res
+        if strong:      # the path's one exchange step: all-gather of the 5 per-SNP outputs
+            return crmd.gather_results(stack5(out), p_total)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered_weak, stack5(out))
+            return gathered_weak
+        return stack5(out)
+
+    maf_d = None
+    if a.entry == "estimate_betas":
+        maf_d = torch.from_numpy(crm.compute_maf(Gd[:, lo:hi])).to(dev)
 
     def timed(fn, steps):
         barrier()
@@ -318,7 +384,7 @@ def run_b200_arm(a):
             t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
-        return ms, wall, r
+        return max(ms, wall * 1e3) / steps, r          # device events and host wall clock bracket the same region
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -328,198 +394,212 @@ def run_b200_arm(a):
     sampler.mark()
     api.PROFILE.update(on=True, rot_ms=0.0, rot_flops=0.0, rot_launches=0, int8_ms=0.0, int8_ops=0.0, int8_launches=0)
     launches0 = lib.crm_launch_count()
-    ms_total, wall, res = timed(step_device, a.steps)
+    ms_per_step, res = timed(step_device, a.steps)
     launches = lib.crm_launch_count() - launches0
     api.PROFILE["on"] = False
     clocks = sampler.stop()
-    ms_per_step = max(ms_total, wall * 1e3) / a.steps     # device events and host wall clock bracket the same region
-    value = world * p / (ms_per_step / 1e3)
-    rot_ms, rot_flops, rot_launches = api.PROFILE["rot_ms"], api.PROFILE["rot_flops"], api.PROFILE["rot_launches"]
-    achieved = rot_flops / (rot_ms * 1e-3) / 1e12 if rot_ms > 0 else None
-    int8_ms, int8_ops, int8_launches = api.PROFILE["int8_ms"], api.PROFILE["int8_ops"], api.PROFILE["int8_launches"]
-    pv = res[0]
-    top = torch.argsort(pv)[:4].tolist()
-    alg_flop = 2.0 * a.cells * a.contexts * (1 + a.hk_rank) * (1 + a.contexts)
-    default_workload = (a.cells, a.donors, a.contexts, a.hk_rank, a.snps) == (100000, 1000, 20, 50, 10000)
-    if int8_launches > 0:
-        # Integer dosages: the rotation ran as the exact int8 split.  Its dominant kernel is oz_mma_kernel (hand-written
-        # tcgen05.mma kind::i8 + TMA + TMEM, fp64 recombination of the digit planes fused into the epilogue); its roofline is
-        # int8 TOP/s against 2 x the measured dense bf16 peak.  CRM_INT8_GEMM=lt swaps in cuBLASLt + a recombination kernel.
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
-        int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-        int8_tops = int8_ops / (int8_ms * 1e-3) / 1e12
-        fused = os.environ.get("CRM_INT8_GEMM") != "lt" and os.environ.get("CRM_INT8_MMA") != "2cta"
-        roofline = {"bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": int8_tops / int8_peak,
-                    "traffic": OZ_MMA_DRAM_BYTES_DEFAULT_WORKLOAD if default_workload and fused else None,
-                    "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_oz_mma_kernel.txt)",
-                    "kernel": ("cuBLASLt int8 GEMM + oz_combine_kernel" if os.environ.get("CRM_INT8_GEMM") == "lt" else
-                               "oz_mma_kernel (hand-written tcgen05.mma kind::i8 + TMA, TMEM accumulators, fused fp64 recombination)") +
-                              ": 8 digit planes of [Hx|Hx.E_j] against int8 dosages, the exact int8 split of the rotation",
-                    "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json" if peaks else "2 x 1.59 PFLOP/s fallback of B200_PROFILING.md") +
-                                   " (int8 dense = 2 x bf16 dense on B200; both the measured bf16 figure and this kernel are limited by the "
-                                   "power cap, so frac can exceed 1: against the nominal 4.5 POP/s the kernel reaches 0.73-0.76)",
-                    "launches": int(int8_launches), "ms_per_launch": int8_ms / max(1, int8_launches), "share_of_step": int8_ms / ms_total if ms_total else None,
-                    "rotation_fp64_equivalent": {"achieved": achieved, "unit": "TFLOP/s", "algorithmic_flop_per_test": alg_flop,
-                                                 "ms_per_launch": rot_ms / max(1, rot_launches), "share_of_step": rot_ms / ms_total if ms_total else None,
-                                                 "vs_fp64_tensor_peak": (achieved / FP64_TENSOR_PEAK_TFLOPS) if achieved else None,
-                                                 "note": "whole rotation (int8 conversion + digit planes + GEMM + fp64 recombination) in algorithmic fp64 flop; "
-                                                         "above the 37.1 TFLOP/s FP64 tensor peak because the work runs on the int8 tensor pipe"}}
-    else:
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                    "frac": (achieved / FP64_TENSOR_PEAK_TFLOPS) if achieved else None,
-                    "traffic": ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD if default_workload and api.PROFILE.get("pre_expanded_basis") else None,
-                    "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_rotation_traffic_benchsize.csv)",
-                    "kernel": ("crm_gemm_kernel<PLAIN> on the pre-expanded basis [Hx|Hx.E_j] (rotation of [g, g.E] onto [H|y|W])"
-                               if api.PROFILE.get("pre_expanded_basis") else "crm_gemm_kernel<EXPAND> (rotation, Hadamard on the fly)"),
-                    "algorithmic_flop_per_test": alg_flop, "launches": int(rot_launches), "ms_per_launch": rot_ms / max(1, rot_launches),
-                    "share_of_step": rot_ms / ms_total if ms_total else None,
-                    "peak_source": "FP64 DMMA issue-rate peak measured on this pool (profiles/r01_dmma_probe.txt); cuBLAS DGEMM 35.4"}
+    units = p_total if (world == 1 or strong) else world * p_total
+    value = units / (ms_per_step / 1e3)
+    ms_total = ms_per_step * a.steps
 
-    # ---- the same job on the fp64 tensor-core route (hand-written DMMA kernel; what non-integer genotypes get) ----
+    # ---- roofline of the dominant kernel (interaction configs) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    fp64_peak = ctypes_double(lib.crm_fp64_tensor_peak)     # DMMA issue-rate peak measured on this device, now
+    roofline, top = None, None
+    rot_ms, rot_flops, rot_launches = api.PROFILE["rot_ms"], api.PROFILE["rot_flops"], api.PROFILE["rot_launches"]
+    int8_ms, int8_ops, int8_launches = api.PROFILE["int8_ms"], api.PROFILE["int8_ops"], api.PROFILE["int8_launches"]
+    default_workload = (a.config, a.cells, a.donors, a.contexts, a.hk_rank, a.snps, world) == (3, 100000, 1000, 20, 50, 10000, 1)
+    if a.entry == "run_interaction":
+        achieved = rot_flops / (rot_ms * 1e-3) / 1e12 if rot_ms > 0 else None
+        alg_flop = 2.0 * a.cells * a.contexts * (1 + a.hk_rank) * (1 + a.contexts)
+        top = torch.argsort(res[0])[:4].tolist()
+        if int8_launches > 0:
+            # Integer dosages: the rotation ran as the exact int8 split.  Its dominant kernel is oz_mma_kernel (hand-written
+            # tcgen05.mma kind::i8 + TMA + TMEM, fp64 recombination of the digit planes fused into the epilogue); its roofline is
+            # int8 TOP/s against 2 x the measured dense bf16 peak.  CRM_INT8_GEMM=lt swaps in cuBLASLt + a recombination kernel.
+            int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+            int8_tops = int8_ops / (int8_ms * 1e-3) / 1e12
+            fused = os.environ.get("CRM_INT8_GEMM") != "lt" and os.environ.get("CRM_INT8_MMA") != "2cta"
+            roofline = {"bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": int8_tops / int8_peak,
+                        "traffic": NCU_TRAFFIC.get("oz_mma_kernel") if default_workload and fused else None,
+                        "traffic_unit": "bytes per launch (ncu --set full of this command, profiles/)",
+                        "kernel": ("cuBLASLt int8 GEMM + oz_combine_kernel" if os.environ.get("CRM_INT8_GEMM") == "lt" else
+                                   "oz_mma_kernel (hand-written tcgen05.mma kind::i8 + TMA, TMEM accumulators, fused fp64 recombination)") +
+                                  ": digit planes of [Hx|Hx.E_j] against int8 dosages, the exact int8 split of the rotation",
+                        "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json" if peaks else "2 x 1.59 PFLOP/s fallback of B200_PROFILING.md") +
+                                       " (int8 dense = 2 x bf16 dense on B200; both the measured bf16 figure and this kernel are limited by the "
+                                       "power cap, so frac can exceed 1: against the nominal 4.5 POP/s the kernel reaches 0.73-0.76)",
+                        "launches": int(int8_launches), "ms_per_launch": int8_ms / max(1, int8_launches), "share_of_step": int8_ms / ms_total if ms_total else None,
+                        # the path's algorithmic work is fp64 flop; reported against the FP64 tensor (DMMA) peak as well
+                        "achieved_fp64_equivalent": achieved, "fp64_tensor_peak": fp64_peak, "frac_fp64_equivalent": (achieved / fp64_peak) if achieved and fp64_peak else None,
+                        "fp64_equivalent_note": "whole rotation (int8 conversion + digit planes + contraction + fp64 recombination) in algorithmic fp64 flop "
+                                                "(2 n m (1+k) per test) over its CUDA-event time, against the DMMA peak measured in this run; above 1 because "
+                                                "the work runs on the int8 tensor pipe",
+                        "algorithmic_flop_per_test": alg_flop, "rotation_ms_per_launch": rot_ms / max(1, rot_launches),
+                        "rotation_share_of_step": rot_ms / ms_total if ms_total else None}
+        else:
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if achieved and fp64_peak else None,
+                        "traffic": NCU_TRAFFIC.get("crm_gemm_kernel") if default_workload and api.PROFILE.get("pre_expanded_basis") else None,
+                        "traffic_unit": "bytes per launch (ncu --set full of this command, profiles/)",
+                        "kernel": ("crm_gemm_kernel<PLAIN> on the pre-expanded basis [Hx|Hx.E_j] (rotation of [g, g.E] onto [H|y|W])"
+                                   if api.PROFILE.get("pre_expanded_basis") else "crm_gemm_kernel<EXPAND> (rotation, Hadamard on the fly)"),
+                        "algorithmic_flop_per_test": alg_flop, "launches": int(rot_launches), "ms_per_launch": rot_ms / max(1, rot_launches),
+                        "share_of_step": rot_ms / ms_total if ms_total else None, "frac_fp64_equivalent": (achieved / fp64_peak) if achieved and fp64_peak else None,
+                        "peak_source": "FP64 DMMA issue-rate peak measured in this run (crm_fp64_tensor_peak)"}
+
+    extras = not a.no_extras and a.entry == "run_interaction"
+    # ---- the same job on the fp64 tensor-core route (hand-written DMMA kernel; what real-valued genotypes get) ----
     fp64_route = None
-    if int8_launches > 0 and not a.no_fp64_route:
+    if extras and world == 1 and int8_launches > 0:
         os.environ["CRM_ROTATION"] = "dmma"
         try:
             step_device()
             api.PROFILE.update(on=True, rot_ms=0.0, rot_flops=0.0, rot_launches=0, int8_ms=0.0, int8_ops=0.0, int8_launches=0)
-            ms_f, wall_f, res_f = timed(step_device, a.steps)
+            ms_f, res_f = timed(step_device, max(2, a.steps // 2))
             api.PROFILE["on"] = False
         finally:
             del os.environ["CRM_ROTATION"]
-        ms_f = max(ms_f, wall_f * 1e3) / a.steps
         ach_f = api.PROFILE["rot_flops"] / (api.PROFILE["rot_ms"] * 1e-3) / 1e12 if api.PROFILE["rot_ms"] > 0 else None
         pos = (res[0] > 0) & (res_f[0] > 0)
-        fp64_route = {"value": world * p / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f,
+        fp64_route = {"value": p_total / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f,
                       "max_abs_dlog10p_vs_int8_split": float((torch.log10(res_f[0][pos]) - torch.log10(res[0][pos])).abs().max()),
-                      "roofline": {"bound": "tensor", "achieved": ach_f, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                                   "frac": (ach_f / FP64_TENSOR_PEAK_TFLOPS) if ach_f else None,
-                                   "traffic": ROTATION_DRAM_BYTES_DEFAULT_WORKLOAD if default_workload else None,
-                                   "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_rotation_traffic_benchsize.csv)",
+                      "roofline": {"bound": "tensor", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (ach_f / fp64_peak) if ach_f and fp64_peak else None,
+                                   "traffic": NCU_TRAFFIC.get("crm_gemm_kernel") if default_workload else None,
                                    "kernel": "crm_gemm_kernel<PLAIN> (hand-written DMMA + TMA) on the pre-expanded basis [Hx|Hx.E_j]",
                                    "launches": int(api.PROFILE["rot_launches"]), "ms_per_launch": api.PROFILE["rot_ms"] / max(1, api.PROFILE["rot_launches"]),
-                                   "peak_source": "FP64 DMMA issue-rate peak measured on this pool (profiles/r01_dmma_probe.txt); cuBLAS DGEMM 35.4"}}
+                                   "peak_source": "FP64 DMMA issue-rate peak measured in this run (crm_fp64_tensor_peak)"}}
 
-    # ---- extension: donor-level genotype ingress (same job, G given as donors x SNPs + donor index) ----
-    donor_level = None
-    if not a.no_donor_level:
+    # ---- extension: donor-level genotype ingress; model kept across genes (N = 1 only) ----
+    donor_level, shared_setup = None, None
+    if extras and world == 1:
         Gdon_d = torch.from_numpy(Gd).to(dev)
 
         def step_donor():
             model = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev)
-            out = model._scan_interaction_device(Gdon_d, donor_index=donor_d)
-            return torch.stack([out["pv"], out["rho1"], out["e2"], out["g2"], out["eps2"]])
+            return stack5(model._scan_interaction_device(Gdon_d, donor_index=donor_d))
 
         step_donor()
-        ms_d, wall_d, res_d = timed(step_donor, a.steps)
-        ms_d = max(ms_d, wall_d * 1e3) / a.steps
-        dl = None
-        if world == 1:      # compare where p > 0 (the strongest simulated hits underflow to exactly 0 in both paths)
-            pos = (res[0] > 0) & (res_d[0] > 0)
-            assert bool(((res[0] > 0) == (res_d[0] > 0)).all())
-            dl = float((torch.log10(res_d[0][pos]) - torch.log10(res[0][pos])).abs().max())
-        donor_level = {"value": world * p / (ms_d / 1e3), "unit": UNIT, "ms_per_step": ms_d, "max_abs_dlog10p_vs_expanded": dl,
+        ms_d, res_d = timed(step_donor, max(2, a.steps // 2))
+        pos = (res[0] > 0) & (res_d[0] > 0)
+        donor_level = {"value": p_total / (ms_d / 1e3), "unit": UNIT, "ms_per_step": ms_d,
+                       "max_abs_dlog10p_vs_expanded": float((torch.log10(res_d[0][pos]) - torch.log10(res[0][pos])).abs().max()),
                        "note": "same job with genotypes passed as a (donors x SNPs) matrix + donor index (keyword-only extension of the "
                                "reference API); the per-SNP contraction runs over donors instead of cells; not the headline value"}
-
-    # ---- extension: many genes over one data set -- the model is kept, only the phenotype changes per step ----
-    shared_setup = None
-    if not a.no_donor_level:
         keep = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev)
         y_alt = [y_d + 0.01 * i * torch.sin(torch.arange(a.cells, device=dev, dtype=torch.float64)) for i in range(1, 3)]
         counter = {"i": 0}
 
-        def step_shared(G_in, **kw):
+        def step_shared():
             counter["i"] += 1
             keep.set_phenotype(y_alt[counter["i"] % 2])
-            out = keep._scan_interaction_device(G_in, **kw)
-            return torch.stack([out["pv"], out["rho1"], out["e2"], out["g2"], out["eps2"]])
+            return stack5(keep._scan_interaction_device(G_d))
 
-        shared_setup = {"note": "model object kept across steps, CellRegMap.set_phenotype(y) per step (extension for scans of many genes "
-                                "over the same cells); not the headline value", "unit": UNIT}
-        for name, fn in (("expanded_genotypes", lambda: step_shared(G_d)), ("donor_level_genotypes", lambda: step_shared(Gdon_d, donor_index=donor_d))):
-            fn()
-            ms_s, wall_s, _ = timed(fn, a.steps)
-            ms_s = max(ms_s, wall_s * 1e3) / a.steps
-            shared_setup[name] = {"value": world * p / (ms_s / 1e3), "ms_per_step": ms_s}
-        del keep
+        step_shared()
+        ms_s, _ = timed(step_shared, max(2, a.steps // 2))
+        shared_setup = {"value": p_total / (ms_s / 1e3), "ms_per_step": ms_s, "unit": UNIT,
+                        "note": "model object kept across steps, CellRegMap.set_phenotype(y) per step (extension for scans of many genes "
+                                "over the same cells); not the headline value"}
+        del keep, Gdon_d
 
-    # ---- e2e through the public API with (pinned) host buffers ----
+    # ---- weak scaling beside the strong-scaling headline: every rank scans its own p_total SNPs of the same gene ----
+    weak = None
+    if extras and strong:
+        Gw_d = torch.from_numpy(donor_genotypes(a, rank, p_total) if rank else Gd).to(dev)[donor_d].contiguous()
+
+        def step_weak():
+            model = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev, group=True)
+            dist.all_gather_into_tensor(gathered_weak, stack5(model._scan_interaction_device(Gw_d)))
+            return gathered_weak
+
+        step_weak()
+        ms_w, _ = timed(step_weak, max(2, a.steps // 2))
+        weak = {"value": world * p_total / (ms_w / 1e3), "unit": UNIT, "ms_per_step": ms_w, "snps_per_gpu": p_total, "scaling": "weak"}
+        del Gw_d
+
+    # ---- e2e through the public API with plain numpy arrays (pageable host memory), what a user of the reference passes ----
     e2e = None
     if not a.no_e2e:
-        try:
-            G_h = torch.empty((a.cells, p), dtype=torch.float64, pin_memory=True)
-        except RuntimeError:        # the host cannot page-lock 8 GB per rank: pageable memory (block-streamed transfer)
-            G_h = torch.empty((a.cells, p), dtype=torch.float64)
-        G_h.copy_(G_d)
-        y_h, W_h, E_h, hK_h = (torch.from_numpy(gene[key]).pin_memory() for key in ("y", "W", "E", "hK"))
-        torch.cuda.synchronize()
+        del G_d
+        torch.cuda.empty_cache()
+        G_np = np.ascontiguousarray(Gd[gene["donor"]])         # (n, p_total) float64, pageable: the reference's asarray(G, float)
+        y_np, W_np, E_np, hK_np = gene["y"], gene["W"], gene["E"], gene["hK"]
 
-        def step_host():
-            pv_h, info_h = crm.run_interaction(y_h, E_h, G_h, W=W_h, hK=hK_h)     # numpy results = D2H inside
+        def call_api(G):
+            if a.entry == "run_association":
+                return crm.run_association(y_np, W_np, E_np, G, hK=hK_np)[0]
+            if a.entry == "estimate_betas":
+                return crm.estimate_betas(y_np, W_np, E_np, G, hK=hK_np)[0]
+            if world > 1 and strong:
+                return crmd.run_interaction_sharded(y_np, E_np, G, W=W_np, hK=hK_np)[0]
+            pv, info = crm.run_interaction(y_np, E_np, G, W=W_np, hK=hK_np)     # numpy results = D2H inside
             if world > 1:
-                res_h = torch.from_numpy(np.stack([pv_h, info_h["rho1"], info_h["e2"], info_h["g2"], info_h["eps2"]])).to(dev)
-                dist.all_gather_into_tensor(gathered, res_h)
-            return pv_h
+                dist.all_gather_into_tensor(gathered_weak, torch.from_numpy(np.stack([pv, info["rho1"], info["e2"], info["g2"], info["eps2"]])).to(dev))
+            return pv
 
-        step_host()
-        ms_e, wall_e, pv_h = timed(step_host, a.steps)
-        ms_e = max(ms_e, wall_e * 1e3) / a.steps
-        h2d = G_h.numel() * 8 + sum(t.numel() * 8 for t in (y_h, W_h, E_h, hK_h))
-        e2e = {"value": world * p / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(5 * p * 8),
-               "ms_per_step": ms_e}
-        assert np.array_equal(pv_h, res[5 * rank if world > 1 else 0].cpu().numpy()), "host and device paths disagree"
-        # the same call with the dosages stored as int8 on the host (8x less PCIe traffic); reported beside the float64 headline
-        try:
-            G_h8 = torch.empty((a.cells, p), dtype=torch.int8, pin_memory=True)
-        except RuntimeError:
-            G_h8 = torch.empty((a.cells, p), dtype=torch.int8)
-        G_h8.copy_(G_d)
-        del G_h
-
-        def step_host8():
-            pv8, info8 = crm.run_interaction(y_h, E_h, G_h8, W=W_h, hK=hK_h)
-            if world > 1:
-                res8 = torch.from_numpy(np.stack([pv8, info8["rho1"], info8["e2"], info8["g2"], info8["eps2"]])).to(dev)
-                dist.all_gather_into_tensor(gathered, res8)
-            return pv8
-
-        step_host8()
-        ms_8, wall_8, pv_8 = timed(step_host8, a.steps)
-        ms_8 = max(ms_8, wall_8 * 1e3) / a.steps
-        assert np.array_equal(pv_8, pv_h), "int8 and float64 host genotypes disagree"
-        e2e["int8_host_genotypes"] = {"value": world * p / (ms_8 / 1e3), "unit": UNIT, "ms_per_step": ms_8,
-                                      "h2d_bytes_per_step": int(G_h8.numel() + sum(t.numel() * 8 for t in (y_h, W_h, E_h, hK_h))),
-                                      "note": "same API call with the genotype matrix stored as int8 on the host; not the headline e2e"}
-        del G_h8
+        small = sum(x.size * 8 for x in (y_np, W_np, E_np, hK_np))
+        cols = (hi - lo) if strong else p_total
+        call_api(G_np)
+        ms_e, pv_e = timed(lambda: call_api(G_np), a.steps)
+        e2e_units = units
+        e2e = {"value": e2e_units / (ms_e / 1e3), "unit": UNIT, "ms_per_step": ms_e, "host_memory": "pageable numpy float64 (the reference's asarray(G, float))",
+               "host_threads": int(lib.crm_host_threads()),
+               # what crosses PCIe per step and rank: dosages as int8 after the host-side conversion (integer-valued input), the small arrays as float64
+               "h2d_bytes_per_step": int(a.cells * cols + small), "host_bytes_read_per_step": int(a.cells * cols * 8 + small),
+               "d2h_bytes_per_step": int(5 * cols * 8 if a.entry == "run_interaction" else cols * 8)}
+        if a.entry == "run_interaction" and world == 1:
+            assert np.array_equal(pv_e, res[0].cpu().numpy()), "host and device paths disagree"
+        if extras and world == 1:
+            # the same call with page-locked float64 genotypes (DMA staging, 8 bytes per dosage over PCIe) and with int8 dosages on the host
+            for key, G_alt, note in (("pinned_float64", lambda: torch.from_numpy(G_np).pin_memory(), "page-locked float64 host matrix: moved by DMA in column chunks"),
+                                     ("int8_host_genotypes", lambda: G_np.astype(np.int8), "dosages stored as int8 on the host (pageable)")):
+                try:
+                    G_x = G_alt()
+                except RuntimeError:
+                    continue
+                call_api(G_x)
+                ms_x, pv_x = timed(lambda: call_api(G_x), max(2, a.steps // 2))
+                assert np.array_equal(pv_x, pv_e), key
+                e2e[key] = {"value": e2e_units / (ms_x / 1e3), "unit": UNIT, "ms_per_step": ms_x, "note": note}
+                del G_x
+        del G_np
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     os.sched_setaffinity(0, full_affinity)      # the CPU arm uses every host core again
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        ns = max(1, min(a.cpu_sample_snps, p))
+        os.environ.setdefault("TQDM_DISABLE", "1")
+        ns = default_cpu_sample(a)
         r = cpu_reference_sample(a, gene, Gd, ns)
         v = ns / r["scan_s"][0]
         cpu = {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"first {ns} SNPs of the same gene, scan only ({r['scan_s'][0]:.1f} s); set-up ({r['setup_s']:.1f} s) excluded"}
+               "sample": f"first {ns} SNPs of the same gene, scan only ({r['scan_s'][0]:.1f} s); set-up ({r['setup_s']:.1f} s) excluded; code = {r['code']}"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        line = {"metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling if world > 1 else "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_name(a), "snps_per_gpu": p, "l2": "inputs (8 GB genotypes, 0.8 GB basis) far larger than L2",
+                "config": {"workload": workload_name(a), "snps_total": units, "snps_per_gpu": (hi - lo) if strong else p_total,
+                           "l2": "inputs (genotypes, basis) far larger than L2" if a.cells * a.snps * 8 > 4e8 else "small problem: inputs fit L2; every step rebuilds the model from its inputs",
                            "host_affinity": ("%d CPUs local to the GPU (NVML)" % len(local_cpus)) if local_cpus else "unchanged",
-                           "step": "constructor set-up + scan of the rank's SNP shard + all-gather of results"},
+                           "step": "constructor set-up (shared between ranks) + scan of the rank's SNP block + all-gather of results"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "fp64_route": fp64_route,
+                "roofline": roofline, "fp64_route": fp64_route, "weak_scaling": weak,
                 "cpu_baseline": cpu, "donor_level_ingress": donor_level, "shared_setup": shared_setup,
                 "top_hits": top}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ctypes_double(fn):
+    """value of a C-ABI probe `int fn(double* out, void* stream)`, None when it fails"""
+    import ctypes
+    v = ctypes.c_double(0.0)
+    return float(v.value) if fn(ctypes.byref(v), None) == 0 else None
 
 
 def main():

@@ -145,7 +145,7 @@ class CellRegMap:
         u ~ N(0, v1 (1-rho1) K o E2 E2'),  eps ~ N(0, v2 I)
     """
 
-    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None, device=None, _prefetch=None):
+    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None, device=None, _prefetch=None, _group=None):
         self._device = _device(device)
         dev = self._device
         self._y = _to_dev(y, dev).flatten()
@@ -204,15 +204,43 @@ class CellRegMap:
             self._prefetched = (_prefetch, geno)
         rho = np.ascontiguousarray(np.asarray(self._rho1, dtype=np.float64))
         mL = 0 if Lcat is None else int(Lcat.shape[1])
-        _lib.call("crm_setup", self._handle, _ptr(self._y), _ptr(self._W), self._W.stride(0), _ptr(self._E0),
-                  self._E0.stride(0), _ptr(self._E1), self._E1.stride(0), _ptr(Lcat), 0 if Lcat is None else Lcat.stride(0),
-                  n, int(self._W.shape[1]), int(self._E0.shape[1]), int(self._E1.shape[1]), mL,
-                  rho.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(rho.shape[0]), _stream())
+        setup_args = (self._handle, _ptr(self._y), _ptr(self._W), self._W.stride(0), _ptr(self._E0),
+                      self._E0.stride(0), _ptr(self._E1), self._E1.stride(0), _ptr(Lcat), 0 if Lcat is None else Lcat.stride(0),
+                      n, int(self._W.shape[1]), int(self._E0.shape[1]), int(self._E1.shape[1]), mL,
+                      rho.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(rho.shape[0]))
+        world = 1
+        if _group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(None if _group is True else _group)
+        if world > 1 and rho.shape[0] > 1:
+            self._shared_setup(setup_args, int(rho.shape[0]), None if _group is True else _group)
+        else:
+            _lib.call("crm_setup", *setup_args, _stream())
         dims = (ctypes.c_int64 * 8)()
         _lib.call("crm_get_dims", self._handle, dims)
         self._dims = {"n": dims[0], "c": dims[1], "k0": dims[2], "m": dims[3], "R": dims[4], "mp": dims[5], "max_rank": dims[6],
                       "pre_expanded_basis": bool(dims[7])}
         PROFILE["pre_expanded_basis"] = bool(dims[7])
+
+    def _shared_setup(self, setup_args, R, group):
+        """Set-up shared between the ranks of `group`: rank r decomposes the grid points r, r + world, ...; one all-gather of the packed
+        grid points (S0 and T_rho, ~8 MB each at m = 1 020) over NCCL / NVLink gives every rank the whole basis."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        _lib.call("crm_setup_partial", *setup_args, rank, world, _stream())
+        rec = int(_lib.load().crm_basis_record_size(self._handle))
+        slots = -(-R // world)                                  # grid points per rank, padded
+        mine = torch.zeros((slots, rec), dtype=torch.float64, device=self._device)
+        for j, r in enumerate(range(rank, R, world)):
+            _lib.call("crm_export_basis", self._handle, r, _ptr(mine[j]), _stream())
+        everything = torch.empty((world, slots, rec), dtype=torch.float64, device=self._device)
+        dist.all_gather_into_tensor(everything, mine, group=group)
+        for other in range(world):
+            if other == rank:
+                continue
+            for j, r in enumerate(range(other, R, world)):
+                _lib.call("crm_import_basis", self._handle, r, _ptr(everything[other, j]), _stream())
+        _lib.call("crm_setup_finish", self._handle, _stream())
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -414,12 +442,12 @@ def run_association_fast(y, W, E, G, hK=None, *, donor_index=None):
     return crm.scan_association_fast(G, donor_index=donor_index)
 
 
-def _make_interaction_model(y, E, W, E1, E2, hK, device=None, prefetch=None):
+def _make_interaction_model(y, E, W, E1, E2, hK, device=None, prefetch=None, group=None):
     dev = _device(device)
     E1 = E if E1 is None else E1
     E2 = E if E2 is None else E2
     Ls = None if hK is None else _L_concat(_to_dev(hK, dev, two_d=True), _to_dev(E2, dev))
-    return CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev, _prefetch=prefetch)
+    return CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev, _prefetch=prefetch, _group=group)
 
 
 def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None, *, donor_index=None):

@@ -38,6 +38,14 @@ SIGNATURES = {
                                  c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                  ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_double), ctypes.c_int,
                                  ctypes.c_void_p]),
+    "crm_setup_partial": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int64,
+                                         c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_double), ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "crm_basis_record_size": (ctypes.c_int64, [ctypes.c_void_p]),
+    "crm_export_basis": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_void_p]),
+    "crm_import_basis": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_void_p]),
+    "crm_setup_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "crm_set_test_contexts": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_void_p]),
     "crm_update_phenotype": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_void_p]),
     "crm_set_donors": (ctypes.c_int, [ctypes.c_void_p, c_int32_p, c_int32_p, ctypes.c_int64, ctypes.c_void_p]),
@@ -58,6 +66,7 @@ SIGNATURES = {
     "crm_stage_genotypes_typed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                  ctypes.c_void_p]),
     "crm_host_threads": (ctypes.c_int, []),
+    "crm_fp64_tensor_peak": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]),
     "crm_eigh_batched": (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),
     "crm_int8_split_gemm": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

@@ -591,13 +591,64 @@ static int launch_rotation(Handle* h, GBlock& blk, double* C, cudaStream_t st) {
     return launch_gemm(GEMM_EXPAND, op, (int)h->n, 0, h->Mx, 0, (int)(B * h->kexp), C, h->ldH, h->kexp, st);
 }
 
+// Last step of the set-up once S and T of every grid point are in place: rotated null design per rho, kept ranks.
+static int finish_setup(Handle* h, cudaStream_t st) {
+    const int R = h->R, mp = h->mp, m = h->m, c = h->c, ldH = h->ldH;
+    PhaseTrace tr(st);
+    rotate_null_kernel<<<blocks_for((long long)R * mp, 128), 128, 0, st>>>(h->Tt.as<double>(), (long long)R * mp, h->gram.as<double>(), ldH, m,
+                                                                         mp, R, c, h->yr.as<double>(), h->Wr.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    CRM_CHECK(h->YW.reserve((size_t)R * (1 + c) * mp * 8));
+    CRM_CHECK(h->ywgram.reserve((size_t)(1 + c) * (1 + c) * 8));
+    build_yw_kernel<<<blocks_for(std::max<long long>((long long)R * (1 + c) * mp, (long long)(1 + c) * (1 + c)), 256), 256, 0, st>>>(
+        h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    std::vector<int> info(2 * R, 0);
+    CRM_CUDA(cudaMemcpyAsync(info.data(), h->devinfo.as<int>(), (size_t)(2 * R) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaStreamSynchronize(st));
+    h->max_rank = 0;
+    for (int r = 0; r < R; r++) {
+        if (info[r] != 0) { set_error("cusolverDnDsyevd did not converge for grid point %d (devInfo=%d)", r, info[r]); return CRM_ERR_SOLVER; }
+        h->max_rank = std::max(h->max_rank, info[R + r]);
+    }
+    h->ready = true;
+    tr.mark("rotate null");
+    tr.report("set-up (finish)");
+    if (trace_on()) fprintf(stderr, "[crm trace] host %.1f ms: set-up returns\n", host_ms());
+    return CRM_OK;
+}
+
+// One grid point of the basis as a packed record of 2 + mp + m * mp doubles: [kept rank, solver info, S (mp), T block (m x mp)].
+__global__ void pack_basis_kernel(const double* S, const double* Tt, long long ldt, const int* info, int R, int r, int m, int mp, double* out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = 2 + (long long)mp + (long long)m * mp;
+    if (idx >= total) return;
+    double v;
+    if (idx == 0) v = (double)info[R + r];
+    else if (idx == 1) v = (double)info[r];
+    else if (idx < 2 + mp) v = S[(long long)r * mp + (idx - 2)];
+    else { const long long t = idx - 2 - mp; const long long a = t / mp, i = t - a * mp; v = Tt[a * ldt + (long long)r * mp + i]; }
+    out[idx] = v;
+}
+__global__ void unpack_basis_kernel(const double* in, int R, int r, int m, int mp, double* S, double* Tt, long long ldt, int* info) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = 2 + (long long)mp + (long long)m * mp;
+    if (idx >= total) return;
+    const double v = in[idx];
+    if (idx == 0) info[R + r] = (int)v;
+    else if (idx == 1) info[r] = (int)v;
+    else if (idx < 2 + mp) S[(long long)r * mp + (idx - 2)] = v;
+    else { const long long t = idx - 2 - mp; const long long a = t / mp, i = t - a * mp; Tt[a * ldt + (long long)r * mp + i] = v; }
+}
+
 static int do_setup(Handle* h, const double* y, const double* W, long long ldw, const double* E0, long long lde0, const double* E1,
                     long long lde1, const double* L, long long ldl, long long n, int c, int k0, int k1, long long mL,
-                    const double* rho_host, int R, cudaStream_t st) {
+                    const double* rho_host, int R, int r_first, int r_step, cudaStream_t st) {
     if (!y || !W || !E0 || !E1 || n <= 0 || c <= 0 || k0 <= 0 || k1 <= 0 || mL < 0 || R <= 0 || (mL > 0 && !L)) { set_error("crm_setup: bad arguments"); return CRM_ERR_INVALID; }
     if (n > 2000000000LL) { set_error("n too large"); return CRM_ERR_UNSUPPORTED; }
     if (c > 60) { set_error("at most 60 covariate columns are supported (got %d)", c); return CRM_ERR_UNSUPPORTED; }
     if (R > 64) { set_error("rho grid too long"); return CRM_ERR_UNSUPPORTED; }
+    if (r_step < 1 || r_first < 0 || r_first >= r_step) { set_error("crm_setup: bad grid-point selection %d mod %d", r_first, r_step); return CRM_ERR_INVALID; }
     if (k1 + mL > 30000) { set_error("background half-covariance has %lld columns; limit is 30000", (long long)(k1 + mL)); return CRM_ERR_UNSUPPORTED; }
     h->ready = false;
     h->donors_set = false;
@@ -689,60 +740,66 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     int* info_dev = h->devinfo.as<int>();
     int* rank_dev = h->devinfo.as<int>() + R;
     const int tall = n > m ? 1 : 0;
+    // grid points decomposed by this call: all of them, or every r_step-th one starting at r_first when the set-up is shared between
+    // the ranks of a multi-GPU scan (the others arrive through crm_import_basis before crm_setup_finish)
+    std::vector<int> sel;
+    for (int r = r_first; r < R; r += r_step) sel.push_back(r);
+    const int nsel = (int)sel.size();
+    CRM_CUDA(cudaMemsetAsync(info_dev, 0, (size_t)2 * R * 4, st));
     // All grid points go through the batched solver of eig.cuh (tridiagonalisation of every matrix at once on its own group of
     // SMs, multisection + inverse iteration + re-orthonormalisation, back-transformation): 33 ms instead of 122 ms for 11 problems
     // of size 1020 (profiles/r01_eig_bench.txt).  The sequential cusolverDnDsyevd calls remain as the fall-back when a size is out
     // of range or the residual / orthogonality check of a matrix fails, and as the reference point (CRM_EIG=cusolver).
     static const bool native = [] { const char* v = getenv("CRM_EIG"); return !(v && !strcmp(v, "cusolver")); }();
     bool native_done = false;
-    if (native && m >= 2 && m <= 4096 && R <= 64) {
-        std::vector<int> n_of(R), a0_of(R);
+    if (native && m >= 2 && m <= 4096 && R <= 64 && nsel > 0) {
+        std::vector<int> n_of(nsel), a0_of(nsel);
         bool ok = true;
-        for (int r = 0; r < R; r++) {
+        for (int j = 0; j < nsel; j++) {
+            const int r = sel[j];
             int a0 = 0, ms = m;
             if (mL > 0 && h->rho[r] == 1.0) { a0 = 0; ms = k1; }
             else if (mL > 0 && h->rho[r] == 0.0) { a0 = k1; ms = (int)mL; }
-            n_of[r] = ms; a0_of[r] = a0;
+            n_of[j] = ms; a0_of[j] = a0;
             if (ms < 2) ok = false;
         }
         if (ok) {
             if (!e.blas && cublasCreate(&e.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CRM_ERR_SOLVER; }
             size_t ws_bytes = 0;
-            CRM_CHECK(eig_workspace_bytes(m, R, &ws_bytes));
-            CRM_CHECK(e.mat.reserve((size_t)R * m * m * 8)); CRM_CHECK(e.vec.reserve((size_t)R * m * m * 8)); CRM_CHECK(e.val.reserve((size_t)R * m * 8));
-            CRM_CHECK(e.ws.reserve(ws_bytes)); CRM_CHECK(e.quality.reserve((size_t)R * 8 + (size_t)2 * R * 4));
+            CRM_CHECK(eig_workspace_bytes(m, nsel, &ws_bytes));
+            CRM_CHECK(e.mat.reserve((size_t)nsel * m * m * 8)); CRM_CHECK(e.vec.reserve((size_t)nsel * m * m * 8)); CRM_CHECK(e.val.reserve((size_t)nsel * m * 8));
+            CRM_CHECK(e.ws.reserve(ws_bytes)); CRM_CHECK(e.quality.reserve((size_t)nsel * 8 + (size_t)2 * nsel * 4));
             int lib_lwork = 0;
             CRM_CHECK(eig_lib_lwork(e.solver, m, &lib_lwork));
             CRM_CHECK(e.work.reserve((size_t)std::max(lib_lwork, lwork) * 8));
-            for (int r = 0; r < R; r++) {
-                scale_gram_kernel<<<blocks_for((long long)n_of[r] * n_of[r], 256), 256, 0, st>>>(h->gram.as<double>(), ldH, a0_of[r], n_of[r], k1, h->rho[r], e.mat.as<double>() + (size_t)r * m * m);
+            for (int j = 0; j < nsel; j++) {
+                scale_gram_kernel<<<blocks_for((long long)n_of[j] * n_of[j], 256), 256, 0, st>>>(h->gram.as<double>(), ldH, a0_of[j], n_of[j], k1, h->rho[sel[j]], e.mat.as<double>() + (size_t)j * m * m);
                 CRM_CUDA(cudaGetLastError()); count_launch();
             }
-            int* lib_info = reinterpret_cast<int*>(e.quality.as<double>() + R);
-            CRM_CUDA(cudaMemsetAsync(lib_info, 0, (size_t)2 * R * 4, st));
-            CRM_CHECK(eig_batched(e.solver, e.blas, e.mat.as<double>(), n_of.data(), m, R, e.val.as<double>(), e.vec.as<double>(), e.quality.as<double>(), e.ws.ptr,
+            int* lib_info = reinterpret_cast<int*>(e.quality.as<double>() + nsel);
+            CRM_CUDA(cudaMemsetAsync(lib_info, 0, (size_t)2 * nsel * 4, st));
+            CRM_CHECK(eig_batched(e.solver, e.blas, e.mat.as<double>(), n_of.data(), m, nsel, e.val.as<double>(), e.vec.as<double>(), e.quality.as<double>(), e.ws.ptr,
                                   e.work.as<double>(), std::max(lib_lwork, lwork), lib_info, st));
-            std::vector<double> q(R); std::vector<int> li(2 * R);
-            CRM_CUDA(cudaMemcpyAsync(q.data(), e.quality.ptr, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
-            CRM_CUDA(cudaMemcpyAsync(li.data(), lib_info, (size_t)2 * R * 4, cudaMemcpyDeviceToHost, st));
+            std::vector<double> q(nsel); std::vector<int> li(2 * nsel);
+            CRM_CUDA(cudaMemcpyAsync(q.data(), e.quality.ptr, (size_t)nsel * 8, cudaMemcpyDeviceToHost, st));
+            CRM_CUDA(cudaMemcpyAsync(li.data(), lib_info, (size_t)2 * nsel * 4, cudaMemcpyDeviceToHost, st));
             CRM_CUDA(cudaStreamSynchronize(st));
             native_done = true;
-            for (int r = 0; r < R; r++) if (!(q[r] < 1e-11) || li[r] != 0 || li[R + r] != 0) native_done = false;
+            for (int j = 0; j < nsel; j++) if (!(q[j] < 1e-11) || li[j] != 0 || li[nsel + j] != 0) native_done = false;
             static const bool verbose = [] { const char* v = getenv("CRM_TRACE"); return v && atoi(v) != 0; }();
-            if (verbose) { fprintf(stderr, "[crm trace] native eigensolver: %s; residuals", native_done ? "accepted" : "rejected"); for (int r = 0; r < R; r++) fprintf(stderr, " %.1e", q[r]); fprintf(stderr, "\n"); }
+            if (verbose) { fprintf(stderr, "[crm trace] native eigensolver: %s; residuals", native_done ? "accepted" : "rejected"); for (int j = 0; j < nsel; j++) fprintf(stderr, " %.1e", q[j]); fprintf(stderr, "\n"); }
             if (native_done) {
-                CRM_CUDA(cudaMemsetAsync(info_dev, 0, (size_t)R * 4, st));
-                for (int r = 0; r < R; r++) {
+                for (int j = 0; j < nsel; j++) {
                     build_basis_kernel<<<std::min(1024u, blocks_for((long long)m * mp, 256)), 256, 0, st>>>(
-                        e.vec.as<double>() + (size_t)r * m * m, e.val.as<double>() + (size_t)r * m, m, mp, a0_of[r], n_of[r], k1, h->rho[r], tall,
-                        h->S.as<double>() + (long long)r * mp, h->Tt.as<double>(), (long long)R * mp, r, rank_dev);
+                        e.vec.as<double>() + (size_t)j * m * m, e.val.as<double>() + (size_t)j * m, m, mp, a0_of[j], n_of[j], k1, h->rho[sel[j]], tall,
+                        h->S.as<double>() + (long long)sel[j] * mp, h->Tt.as<double>(), (long long)R * mp, sel[j], rank_dev);
                     CRM_CUDA(cudaGetLastError()); count_launch();
                 }
             }
         }
     }
     if (!native_done) {
-        for (int r = 0; r < R; r++) {
+        for (int r : sel) {
             // rho = 1 / rho = 0 zero one diagonal block of D: only the surviving block is decomposed
             int a0 = 0, ms = m;
             if (mL > 0 && h->rho[r] == 1.0) { a0 = 0; ms = k1; }
@@ -761,27 +818,12 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         }
     }
     tr.mark("eigendecompositions");
-    rotate_null_kernel<<<blocks_for((long long)R * mp, 128), 128, 0, st>>>(h->Tt.as<double>(), (long long)R * mp, h->gram.as<double>(), ldH, m,
-                                                                         mp, R, c, h->yr.as<double>(), h->Wr.as<double>());
-    CRM_CUDA(cudaGetLastError()); count_launch();
-    CRM_CHECK(h->YW.reserve((size_t)R * (1 + c) * mp * 8));
-    CRM_CHECK(h->ywgram.reserve((size_t)(1 + c) * (1 + c) * 8));
-    build_yw_kernel<<<blocks_for(std::max<long long>((long long)R * (1 + c) * mp, (long long)(1 + c) * (1 + c)), 256), 256, 0, st>>>(
-        h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
-    CRM_CUDA(cudaGetLastError()); count_launch();
-    std::vector<int> info(2 * R, 0);
-    CRM_CUDA(cudaMemcpyAsync(info.data(), h->devinfo.as<int>(), (size_t)(2 * R) * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CRM_CUDA(cudaStreamSynchronize(st));
-    h->max_rank = 0;
-    for (int r = 0; r < R; r++) {
-        if (info[r] != 0) { set_error("cusolverDnDsyevd did not converge for grid point %d (devInfo=%d)", r, info[r]); return CRM_ERR_SOLVER; }
-        h->max_rank = std::max(h->max_rank, info[R + r]);
+    tr.report("set-up (operands, Gram, eigendecompositions)");
+    if (r_step > 1) {                       // the caller exchanges the grid points between ranks, then calls crm_setup_finish
+        CRM_CUDA(cudaStreamSynchronize(st));       // the pooled solver buffers go back with the lock
+        return CRM_OK;
     }
-    h->ready = true;
-    tr.mark("rotate null");
-    tr.report("set-up");
-    if (trace_on()) fprintf(stderr, "[crm trace] host %.1f ms: set-up returns\n", host_ms());
-    return CRM_OK;
+    return finish_setup(h, st);
 }
 
 // New phenotype for the same cells, contexts, covariates and background (scans of many genes over one data set): only the
@@ -1597,7 +1639,48 @@ int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t ldw, con
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
-    return do_setup(&h->impl, y, W, ldw, E0, lde0, E1, lde1, L, ldl, n, c, k0, k1, mL, rho_host, R, (cudaStream_t)stream);
+    return do_setup(&h->impl, y, W, ldw, E0, lde0, E1, lde1, L, ldl, n, c, k0, k1, mL, rho_host, R, 0, 1, (cudaStream_t)stream);
+}
+
+int crm_setup_partial(crm_handle_t h, const double* y, const double* W, int64_t ldw, const double* E0, int64_t lde0, const double* E1,
+                      int64_t lde1, const double* L, int64_t ldl, int64_t n, int c, int k0, int k1, int64_t mL, const double* rho_host, int R,
+                      int r_first, int r_step, void* stream) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    return do_setup(&h->impl, y, W, ldw, E0, lde0, E1, lde1, L, ldl, n, c, k0, k1, mL, rho_host, R, r_first, r_step, (cudaStream_t)stream);
+}
+
+int64_t crm_basis_record_size(crm_handle_t h) {
+    if (!h || h->impl.m <= 0) return 0;
+    return 2 + (int64_t)h->impl.mp + (int64_t)h->impl.m * h->impl.mp;
+}
+
+int crm_export_basis(crm_handle_t h, int r, double* out, void* stream) {
+    if (!h || !out || r < 0 || r >= h->impl.R) { set_error("crm_export_basis: bad arguments"); return CRM_ERR_INVALID; }
+    Handle& H = h->impl;
+    CRM_CUDA(cudaSetDevice(H.device));
+    const long long total = 2 + (long long)H.mp + (long long)H.m * H.mp;
+    pack_basis_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(H.S.as<double>(), H.Tt.as<double>(), (long long)H.R * H.mp, H.devinfo.as<int>(), H.R, r, H.m, H.mp, out);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
+int crm_import_basis(crm_handle_t h, int r, const double* in, void* stream) {
+    if (!h || !in || r < 0 || r >= h->impl.R) { set_error("crm_import_basis: bad arguments"); return CRM_ERR_INVALID; }
+    Handle& H = h->impl;
+    CRM_CUDA(cudaSetDevice(H.device));
+    const long long total = 2 + (long long)H.mp + (long long)H.m * H.mp;
+    unpack_basis_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, H.R, r, H.m, H.mp, H.S.as<double>(), H.Tt.as<double>(), (long long)H.R * H.mp, H.devinfo.as<int>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
+int crm_setup_finish(crm_handle_t h, void* stream) {
+    if (!h || h->impl.m <= 0) { set_error("crm_setup_finish: crm_setup_partial has not run"); return CRM_ERR_STATE; }
+    CRM_CUDA(cudaSetDevice(h->impl.device));
+    AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    return finish_setup(&h->impl, (cudaStream_t)stream);
 }
 
 int crm_stage_genotypes(crm_handle_t h, const double* G_host, int64_t ldg, int64_t rows, int64_t p, void* stream) {
@@ -1612,6 +1695,11 @@ int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dtype, int
 }
 
 int crm_host_threads(void) { return host_threads(); }
+
+int crm_fp64_tensor_peak(double* tflops, void* stream) {
+    if (!tflops) { set_error("crm_fp64_tensor_peak: null output"); return CRM_ERR_INVALID; }
+    return measure_fp64_tensor_peak(tflops, (cudaStream_t)stream);
+}
 
 int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream) {
     if (!h || !h->impl.ready || !E0) { set_error("crm_set_test_contexts: handle not set up"); return CRM_ERR_STATE; }

@@ -162,4 +162,53 @@ int launch_gemm(int mode, const GemmOperands& op, int K, int m_begin, int m_coun
     return gemm_mt_choice() == 8 ? launch_gemm_mode<GEMM_PLAIN, 8>(op, a, stream) : launch_gemm_mode<GEMM_PLAIN, 4>(op, a, stream);
 }
 
+// FP64 tensor-core issue-rate probe: register-resident chains of mma.sync m8n8k4 (SASS DMMA.8x8x4), 8 independent accumulator pairs
+// per warp, 8 warps per CTA, 2 CTAs per SM -- the denominator of the fp64 rotation's roofline, measured on the device it runs on.
+__global__ void __launch_bounds__(256) crm_dmma_rate_kernel(double* out, int iters, double seed) {
+    const int lane = threadIdx.x & 31;
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    double a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = seed + lane * 1e-3 + i;
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = seed - lane * 1e-3 - i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma884(acc[i][0], acc[i][1], a[i], b[i & 3]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int measure_fp64_tensor_peak(double* tflops, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    CRM_CUDA(cudaGetDevice(&dev));
+    CRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    CRM_CUDA(cudaMallocAsync((void**)&out, (size_t)sms * 2 * 256 * sizeof(double), st));
+    const int iters = 20000, grid = sms * 2;
+    cudaEvent_t e0, e1;
+    CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {          // first repetition = warm-up
+        CRM_CUDA(cudaEventRecord(e0, st));
+        crm_dmma_rate_kernel<<<grid, 256, 0, st>>>(out, iters, 1.0);
+        CRM_CUDA(cudaGetLastError()); count_launch();
+        CRM_CUDA(cudaEventRecord(e1, st));
+        CRM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CRM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CRM_CUDA(cudaFreeAsync(out, st));
+    const double flop = (double)grid * 8.0 * iters * 8.0 * (2.0 * 8 * 8 * 4);
+    *tflops = flop / ((double)best * 1e-3) * 1e-12;
+    return CRM_OK;
+}
+
 }  // namespace crm

@@ -20,6 +20,9 @@ constexpr int GEMM_TILE_N = 128;
 int launch_gemm(int mode, const GemmOperands& op, int K, int m_begin, int m_count, int n_begin, int n_count,
                 double* out, long long ldc, int kexp, cudaStream_t stream);
 
+// FP64 tensor-core (DMMA) issue-rate peak of the current device in TFLOP/s, measured with a register-resident probe kernel (~5 ms)
+int measure_fp64_tensor_peak(double* tflops, cudaStream_t stream);
+
 // next launch_gemm calls on this thread may choose the K split by grid size (operands without a SNP dimension)
 void gemm_set_free_split(bool on);
 

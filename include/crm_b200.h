@@ -51,6 +51,22 @@ CRM_API int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t 
               const double* E1, int64_t lde1, const double* L, int64_t ldl, int64_t n, int c, int k0, int k1,
               int64_t mL, const double* rho_host, int R, void* stream);
 
+/*
+ * Set-up shared between the ranks of a multi-GPU scan (one process per GPU).  Every rank builds the operands and the Gram of
+ * the half-basis, but decomposes only the grid points r = r_first, r_first + r_step, ... (r_first = rank, r_step = world size);
+ * crm_export_basis packs a decomposed grid point into a record of crm_basis_record_size() doubles ([kept rank, solver info, S0 (mp),
+ * T_rho (m x mp)], device memory), the caller all-gathers the records (NCCL over NVLink) and hands the other ranks' grid points to
+ * crm_import_basis; crm_setup_finish completes the model.  Every rank ends up with the same bits in every grid point, so the sharded scan
+ * returns exactly the per-SNP results of the single-GPU call that uses this basis.
+ */
+CRM_API int crm_setup_partial(crm_handle_t h, const double* y, const double* W, int64_t ldw, const double* E0, int64_t lde0,
+                              const double* E1, int64_t lde1, const double* L, int64_t ldl, int64_t n, int c, int k0, int k1,
+                              int64_t mL, const double* rho_host, int R, int r_first, int r_step, void* stream);
+CRM_API int64_t crm_basis_record_size(crm_handle_t h);
+CRM_API int crm_export_basis(crm_handle_t h, int r, double* out, void* stream);
+CRM_API int crm_import_basis(crm_handle_t h, int r, const double* in, void* stream);
+CRM_API int crm_setup_finish(crm_handle_t h, void* stream);
+
 /* Start the host-to-device transfer of a host-resident genotype matrix (rows x p doubles, leading dimension ldg; pinned memory
  * for an asynchronous copy) ahead of the scan: returns at once, the copy runs in column chunks on the handle's copy stream.  May be
  * called right after crm_create, so that the transfer overlaps crm_setup; the next crm_scan_* call with g_on_host = 1 and the same
@@ -74,6 +90,9 @@ enum { CRM_G_F64 = 0, CRM_G_I8 = 1, CRM_G_U8 = 2, CRM_G_I16 = 3, CRM_G_I32 = 4, 
  * that consumes it returns (or the handle is destroyed). */
 CRM_API int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dtype, int64_t ldg, int64_t rows, int64_t p,
                                       int64_t basis_cols_hint, void* stream);
+/* FP64 tensor-core (DMMA) peak of the current device in TFLOP/s, measured with a register-resident mma.sync.m8n8k4.f64 probe
+ * (a few milliseconds; synchronises the stream): the roofline denominator of the float64 rotation (bench.py). */
+CRM_API int crm_fp64_tensor_peak(double* tflops, void* stream);
 /* Worker threads of the host feeder. */
 CRM_API int crm_host_threads(void);
 
