@@ -218,9 +218,7 @@ class CellRegMap:
             _lib.call("crm_setup", *setup_args, _stream())
         dims = (ctypes.c_int64 * 8)()
         _lib.call("crm_get_dims", self._handle, dims)
-        self._dims = {"n": dims[0], "c": dims[1], "k0": dims[2], "m": dims[3], "R": dims[4], "mp": dims[5], "max_rank": dims[6],
-                      "pre_expanded_basis": bool(dims[7])}
-        PROFILE["pre_expanded_basis"] = bool(dims[7])
+        self._dims = {"n": dims[0], "c": dims[1], "k0": dims[2], "m": dims[3], "R": dims[4], "mp": dims[5], "max_rank": dims[6]}
 
     def _shared_setup(self, setup_args, R, group):
         """Set-up shared between the ranks of `group`: rank r decomposes the grid points r, r + world, ...; one all-gather of the packed
@@ -233,8 +231,9 @@ class CellRegMap:
         mine = torch.zeros((slots, rec), dtype=torch.float64, device=self._device)
         for j, r in enumerate(range(rank, R, world)):
             _lib.call("crm_export_basis", self._handle, r, _ptr(mine[j]), _stream())
-        everything = torch.empty((world, slots, rec), dtype=torch.float64, device=self._device)
+        everything = torch.empty((world * slots, rec), dtype=torch.float64, device=self._device)
         dist.all_gather_into_tensor(everything, mine, group=group)
+        everything = everything.view(world, slots, rec)
         for other in range(world):
             if other == rank:
                 continue
@@ -254,6 +253,12 @@ class CellRegMap:
     @property
     def n_samples(self):
         return int(self._y.shape[0])
+
+    def _pre_expanded_basis(self):
+        """True / False once a float64 rotation of this model has chosen its route, None before (tests, bench labels)."""
+        dims = (ctypes.c_int64 * 8)()
+        _lib.call("crm_get_dims", self._handle, dims)
+        return None if dims[7] < 0 else bool(dims[7])
 
     def set_phenotype(self, y):
         """Extension (not in the reference API): replace the phenotype of this model, keeping cells, contexts, covariates
@@ -353,6 +358,10 @@ class CellRegMap:
             if idx_E is not None:
                 _lib.call("crm_set_test_contexts", self._handle, _ptr(self._E0), self._E0.stride(0), _stream())
         if PROFILE["on"]:
+            dims = (ctypes.c_int64 * 8)()
+            _lib.call("crm_get_dims", self._handle, dims)
+            if dims[7] >= 0:
+                PROFILE["pre_expanded_basis"] = bool(dims[7])
             ms, fl, nl = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
             _lib.call("crm_profile", self._handle, 0, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(nl))
             PROFILE["rot_ms"] += ms.value

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "launch.cuh"
 #include "feeder.hpp"
+#include "trace.cuh"
 
 namespace crm {
 
@@ -42,29 +43,6 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
     } while (0)
 
 static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
-
-// CRM_TRACE=1: per-phase device times (CUDA events on the launching stream) printed to stderr at the end of a call
-static double host_ms() { static const auto t0 = std::chrono::steady_clock::now(); return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
-static bool trace_on() { static const bool on = [] { const char* v = getenv("CRM_TRACE"); return v && atoi(v) != 0; }(); return on; }
-struct PhaseTrace {
-    bool on;
-    cudaStream_t st;
-    std::vector<std::pair<const char*, cudaEvent_t>> marks;
-    explicit PhaseTrace(cudaStream_t s) : st(s) { static const bool env = [] { const char* v = getenv("CRM_TRACE"); return v && atoi(v) != 0; }(); on = env; mark("begin"); }
-    void mark(const char* name) {
-        if (!on) return;
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.emplace_back(name, e);
-    }
-    void report(const char* what) {
-        if (!on) return;
-        cudaStreamSynchronize(st);
-        fprintf(stderr, "[crm trace] %s:", what);
-        for (size_t i = 1; i < marks.size(); i++) { float ms = 0.f; cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second); fprintf(stderr, " %s %.2f ms |", marks[i].first, ms); }
-        fprintf(stderr, "\n");
-        for (auto& m : marks) cudaEventDestroy(m.second);
-        marks.clear();
-    }
-};
 
 // Grow-only device buffer.  Allocation is stream-ordered on the stream of the ABI call in flight (AllocScope, set by every entry
 // point that takes a stream): memory is obtained and returned in the same order as the kernels that use it, so a buffer that grows
@@ -105,6 +83,14 @@ static size_t pool_cached_bytes(int device) {
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used) return (size_t)(reserved - used);
     return 0;
 }
+// stream-ordered scratch of the kernel launchers (split-K partial sums ...): from the same private pool -- the device's default pool
+// releases its memory at every synchronisation (release threshold 0), which turns each such allocation into a trip to the OS
+cudaError_t pool_alloc_async(void** ptr, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool = device_pool(dev);
+    return pool ? cudaMallocFromPoolAsync(ptr, bytes, pool, st) : cudaMallocAsync(ptr, bytes, st);
+}
 struct DevBuf {
     void* ptr = nullptr;
     size_t cap = 0;
@@ -125,7 +111,15 @@ struct DevBuf {
 
 // Creating a cuSOLVER handle costs tens of milliseconds, so one context per device lives in a process-wide pool and is
 // reused by every model object (set-up calls are serialised by the pool mutex).
-struct EigCtx { cusolverDnHandle_t solver = nullptr; cublasHandle_t blas = nullptr; DevBuf mat, val, work, vec, ws, quality; std::vector<char> host_work; };
+struct EigCtx { cusolverDnHandle_t solver = nullptr; cublasHandle_t blas = nullptr; DevBuf mat, val, work, vec, ws, quality, blas_ws; std::vector<char> host_work; };
+// cuBLAS handle of the set-up with an explicit workspace from the private pool (no allocation inside the library calls)
+static int ensure_blas(EigCtx& e) {
+    if (e.blas) return CRM_OK;
+    if (cublasCreate(&e.blas) != CUBLAS_STATUS_SUCCESS) { e.blas = nullptr; set_error("cublasCreate failed"); return CRM_ERR_SOLVER; }
+    const size_t bytes = (size_t)64 << 20;
+    if (e.blas_ws.reserve(bytes) == CRM_OK) cublasSetWorkspace(e.blas, e.blas_ws.ptr, bytes);
+    return CRM_OK;
+}
 struct EigPool { std::mutex mu; std::vector<EigCtx> ctx; };
 static EigPool g_eig_pool[16];
 
@@ -147,7 +141,7 @@ struct Handle {
     bool donors_set = false;
     DevBuf HxE_D, A2_D, dperm, doff;
     DevBuf HxE;           // optional n x (kexp * ldH) pre-expanded basis [Hx | Hx.E0_1 | ... | Hx.E0_k] (see launch_rotation)
-    bool use_hxe = false, hxe_built = false;
+    bool use_hxe = false, hxe_built = false, hxe_decided = false;
     // exact int8 split of the rotation for integer dosages (ozaki.cuh): digit planes of HxE, built by the first rotation that uses them
     int rotation_mode = 0;        // 0 auto (int8 split when the genotype block is integer), 1 fp64 DMMA only, 2 int8 split required
     bool oz_built = false, oz_built_a2 = false;
@@ -550,6 +544,26 @@ static int check_block_finite(Handle* h, const GBlock& blk, cudaStream_t st) {
     return CRM_OK;
 }
 
+// Pre-expanded basis of the fp64 route when it fits comfortably (CRM_NO_HXE=1 forces the on-the-fly route).  Decided by the first
+// float64 rotation of a model, not by the set-up: the memory query costs milliseconds and integer dosages never get here.
+static int decide_hxe(Handle* h) {
+    if (h->hxe_decided) return CRM_OK;
+    size_t free_b = 0, total_b = 0;
+    CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    free_b += pool_cached_bytes(h->device);     // memory cached in the allocation pool is reusable as well
+    const char* env = getenv("CRM_NO_HXE");
+    const char* envb = getenv("CRM_HXE_BLOCKS");       // tests: force streaming in groups of this many context blocks
+    const double budget = 0.45 * (double)(free_b + h->HxE.cap);
+    const double block_bytes = (double)h->n * h->ldH * 8.0;
+    int blocks = (int)std::min<double>(h->kexp, std::floor(budget / block_bytes));
+    if (envb && atoi(envb) > 0) blocks = std::min(blocks, atoi(envb));
+    h->use_hxe = !(env && atoi(env) != 0) && blocks >= 1 && (double)blocks * h->ldH < 2.0e9;
+    h->hxe_blocks = h->use_hxe ? blocks : 0;
+    if (!h->use_hxe) h->HxE.release();
+    h->hxe_decided = true;
+    return CRM_OK;
+}
+
 static int launch_rotation(Handle* h, GBlock& blk, double* C, cudaStream_t st) {
     const Handle::GenoSpace& gs = *h->gs;
     const long long ldE = (long long)h->kexp * h->ldH, B = blk.b;
@@ -570,6 +584,7 @@ static int launch_rotation(Handle* h, GBlock& blk, double* C, cudaStream_t st) {
     CRM_CHECK(block_f64(h, blk, st));
     if (h->rotation_mode == 1) CRM_CHECK(check_block_finite(h, blk, st));     // (the int8 conversion kernel reported it otherwise)
     op.B = blk.G; op.ldb = blk.ld; op.b_cols = blk.cols; op.B2 = blk.G; op.ldb2 = blk.ld; op.b2_cols = blk.cols;
+    CRM_CHECK(decide_hxe(h));
     if (h->use_hxe) {
         const int nb = h->hxe_blocks;
         CRM_CHECK(h->HxE.reserve((size_t)h->n * nb * h->ldH * 8));
@@ -687,22 +702,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     if (mL > 0) CRM_CUDA(cudaMemcpy2DAsync(Hx + k1, (size_t)ldH * 8, L, (size_t)ldl * 8, (size_t)mL * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
     CRM_CUDA(cudaMemcpy2DAsync(Hx + m, (size_t)ldH * 8, y, 8, 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
     CRM_CUDA(cudaMemcpy2DAsync(Hx + m + 1, (size_t)ldH * 8, W, (size_t)ldw * 8, (size_t)c * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
-    {   // pre-expanded basis when it fits comfortably (CRM_NO_HXE=1 forces the on-the-fly route)
-        const size_t bytes = (size_t)n * h->kexp * ldH * 8;
-        size_t free_b = 0, total_b = 0;
-        CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        free_b += pool_cached_bytes(h->device);     // memory cached in the allocation pool is reusable as well
-        const char* env = getenv("CRM_NO_HXE");
-        const char* envb = getenv("CRM_HXE_BLOCKS");       // tests: force streaming in groups of this many context blocks
-        const double budget = 0.45 * (double)(free_b + h->HxE.cap);
-        const double block_bytes = (double)n * ldH * 8.0;
-        int blocks = (int)std::min<double>(h->kexp, std::floor(budget / block_bytes));
-        if (envb && atoi(envb) > 0) blocks = std::min(blocks, atoi(envb));
-        h->use_hxe = !(env && atoi(env) != 0) && blocks >= 1 && (double)blocks * ldH < 2.0e9;
-        h->hxe_blocks = h->use_hxe ? blocks : 0;
-        (void)bytes;
-        if (!h->use_hxe) h->HxE.release();
-    }
+    h->hxe_decided = false;     // the fp64 route decides about its pre-expanded basis when it first runs (decide_hxe)
     {
         const char* rm = getenv("CRM_ROTATION");      // "dmma": fp64 tensor cores only; "int8": exact int8 split required; default auto
         h->rotation_mode = (rm && !strcmp(rm, "dmma")) ? 1 : (rm && !strcmp(rm, "int8")) ? 2 : 0;
@@ -764,7 +764,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
             if (ms < 2) ok = false;
         }
         if (ok) {
-            if (!e.blas && cublasCreate(&e.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CRM_ERR_SOLVER; }
+            CRM_CHECK(ensure_blas(e));
             size_t ws_bytes = 0;
             CRM_CHECK(eig_workspace_bytes(m, nsel, &ws_bytes));
             CRM_CHECK(e.mat.reserve((size_t)nsel * m * m * 8)); CRM_CHECK(e.vec.reserve((size_t)nsel * m * m * 8)); CRM_CHECK(e.val.reserve((size_t)nsel * m * 8));
@@ -778,8 +778,10 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
             }
             int* lib_info = reinterpret_cast<int*>(e.quality.as<double>() + nsel);
             CRM_CUDA(cudaMemsetAsync(lib_info, 0, (size_t)2 * nsel * 4, st));
+            tr.mark("scaled grams");
             CRM_CHECK(eig_batched(e.solver, e.blas, e.mat.as<double>(), n_of.data(), m, nsel, e.val.as<double>(), e.vec.as<double>(), e.quality.as<double>(), e.ws.ptr,
-                                  e.work.as<double>(), std::max(lib_lwork, lwork), lib_info, st));
+                                  e.work.as<double>(), std::max(lib_lwork, lwork), lib_info, st, R, sel.data()));
+            tr.mark("batched eigensolver");
             std::vector<double> q(nsel); std::vector<int> li(2 * nsel);
             CRM_CUDA(cudaMemcpyAsync(q.data(), e.quality.ptr, (size_t)nsel * 8, cudaMemcpyDeviceToHost, st));
             CRM_CUDA(cudaMemcpyAsync(li.data(), lib_info, (size_t)2 * nsel * 4, cudaMemcpyDeviceToHost, st));
@@ -1774,7 +1776,7 @@ int crm_profile_int8(crm_handle_t h, double* gemm_ms, double* gemm_ops, int64_t*
 
 int crm_get_dims(crm_handle_t h, int64_t* d) {
     if (!h || !h->impl.ready || !d) { set_error("crm_get_dims: handle not set up"); return CRM_ERR_STATE; }
-    d[0] = h->impl.n; d[1] = h->impl.c; d[2] = h->impl.k0; d[3] = h->impl.m; d[4] = h->impl.R; d[5] = h->impl.mp; d[6] = h->impl.max_rank; d[7] = h->impl.use_hxe ? 1 : 0;
+    d[0] = h->impl.n; d[1] = h->impl.c; d[2] = h->impl.k0; d[3] = h->impl.m; d[4] = h->impl.R; d[5] = h->impl.mp; d[6] = h->impl.max_rank; d[7] = h->impl.hxe_decided ? (h->impl.use_hxe ? 1 : 0) : -1;
     return CRM_OK;
 }
 
@@ -1834,7 +1836,7 @@ int crm_eigh_batched(const double* A, int n, int batch, double* W, double* V, do
     if (pool.ctx.empty()) pool.ctx.resize(1);
     EigCtx& e = pool.ctx[0];
     if (!e.solver) CRM_SOLVER(cusolverDnCreate(&e.solver));
-    if (!e.blas && cublasCreate(&e.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CRM_ERR_SOLVER; }
+    CRM_CHECK(ensure_blas(e));
     size_t ws_bytes = 0;
     CRM_CHECK(eig_workspace_bytes(n, batch, &ws_bytes));
     DevBuf mat, ws, quality, work;

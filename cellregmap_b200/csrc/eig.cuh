@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
     }
 }
 
-struct EigSizes { int nmax, batch; int n_of[SY_MAX_BATCH]; };
+struct EigSizes { int nmax, batch; int n_of[SY_MAX_BATCH]; int id_of[SY_MAX_BATCH]; };   // id_of: identity of a matrix beyond its position in this batch (seeds)
 
 // ---- eigenvalues of symmetric tridiagonal matrices by multisection on Sturm counts ----
 constexpr int BS_LANES = 4;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(128) crm_tridiag_invit_kernel(const double* d_
         U0[IDX(n - 1)] = dd; U1[IDX(n - 1)] = 0.0; U2[IDX(n - 1)] = 0.0;
         (void)du2;
     }
-    for (int i = 0; i < n; i++) X[IDX(i)] = invit_rand((unsigned)t, (unsigned)i, (unsigned)b);
+    for (int i = 0; i < n; i++) X[IDX(i)] = invit_rand((unsigned)t, (unsigned)i, (unsigned)sz.id_of[b]);
     constexpr int PF = 8;      // steps whose operands are fetched together: the recurrences are latency chains, the loads are not
     for (int it = 0; it < iters; it++) {
         // forward: apply the row operations of the factorisation to the right-hand side

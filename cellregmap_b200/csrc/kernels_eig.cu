@@ -8,6 +8,7 @@
 
 #include "eig.cuh"
 #include "launch.cuh"
+#include "trace.cuh"
 
 namespace crm {
 
@@ -88,7 +89,7 @@ int eig_workspace_bytes(int n, int batch, size_t* bytes) {
 // largest residual |T z - lambda z|_inf / |T| over the vectors (NaN/inf when the Cholesky-QR step broke down).
 // ws: eig_workspace_bytes(n, batch) bytes; lib_work: at least lib_lwork doubles (max of potrf / ormtr needs, queried by the caller).
 int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n, int batch, double* W, double* V, double* quality, void* ws, double* lib_work,
-                int lib_lwork, int* info_dev, cudaStream_t st) {
+                int lib_lwork, int* info_dev, cudaStream_t st, int group_batch, const int* ids) {
     cusolverDnHandle_t solver = (cusolverDnHandle_t)solver_v;
     cublasHandle_t blas = (cublasHandle_t)blas_v;
     if (n < 2 || n > SY_MAX_N || batch < 1 || batch > SY_MAX_BATCH) { set_error("eig_batched: n = %d outside [2, %d] or batch = %d outside [1, %d]", n, SY_MAX_N, batch, SY_MAX_BATCH); return CRM_ERR_UNSUPPORTED; }
@@ -96,6 +97,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
     sz.nmax = n; sz.batch = batch;
     for (int b = 0; b < batch; b++) {
         sz.n_of[b] = n_of ? n_of[b] : n;
+        sz.id_of[b] = ids ? ids[b] : b;
         if (sz.n_of[b] < 2 || sz.n_of[b] > n) { set_error("eig_batched: matrix %d has size %d outside [2, %d]", b, sz.n_of[b], n); return CRM_ERR_INVALID; }
     }
     const size_t nn = (size_t)n * n;
@@ -115,6 +117,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
     CRM_CUDA(cudaMemsetAsync(bar, 0, (size_t)batch * 8, st));
     CRM_CUDA(cudaMemsetAsync(quality, 0, (size_t)batch * 8, st));
     CRM_CUDA(cudaMemsetAsync(emax, 0, (size_t)batch * 8, st));
+    PhaseTrace tr(st);
     // 1. tridiagonalisation: every group of SY_GROUP CTAs must be resident -> cooperative launch
     {
         static bool attr = false;
@@ -122,19 +125,25 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
         static int sms = 0;
         if (!sms) { int dev = 0; CRM_CUDA(cudaGetDevice(&dev)); CRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
         SytrdArgs sa{};
-        sa.group = std::max(1, std::min(SY_MAX_GROUP, sms / batch));
+        // CTAs per matrix.  The partial sums of a column step are combined in group order, so a matrix's result depends on the group size:
+        // when this batch is a share of a larger one (set-up shared between ranks) the group size of the whole batch is used, and every
+        // rank count yields the bits of the single-GPU decomposition.
+        sa.group = std::max(1, std::min(SY_MAX_GROUP, sms / std::max(batch, group_batch)));
         for (int b = 0; b < batch; b++) sa.n_of[b] = sz.n_of[b];
         sa.A = A; sa.nmax = n; sa.batch = batch; sa.d = d; sa.e = e; sa.tau = tau; sa.xbuf = xbuf; sa.pbuf = pbuf; sa.part = part; sa.bar = bar;
         void* params[] = {&sa};
         CRM_CUDA(cudaLaunchCooperativeKernel((const void*)crm_sytrd_kernel, dim3((unsigned)(batch * sa.group)), dim3(SY_THREADS), params, (size_t)5 * (n + 1) * 8, st));
         count_launch();
     }
+    tr.mark("sytrd");
     // 2. eigenvalues
     crm_tridiag_bisect_kernel<<<dim3((unsigned)(((long long)n * BS_LANES + 255) / 256), (unsigned)batch), 256, (size_t)2 * n * 8, st>>>(d, e, sz, W, tnorm);
     CRM_CUDA(cudaGetLastError()); count_launch();
+    tr.mark("bisect");
     // 3. eigenvectors of the tridiagonal matrices
     crm_tridiag_invit_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)batch), 128, 0, st>>>(d, e, W, tnorm, sz, work, V, 3);
     CRM_CUDA(cudaGetLastError()); count_launch();
+    tr.mark("invit");
     // 4. Cholesky-QR, twice: Z <- Z R^-1 with R'R = Z'Z (orthonormal bases inside clusters of close eigenvalues)
     CRM_BLAS(cublasSetStream(blas, st));
     CRM_SOLVER_(cusolverDnSetStream(solver, st));
@@ -179,6 +188,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
         }
     }
     for (int b = 0; b < batch; b++) if (todo[b]) CRM_CUDA(cudaMemsetAsync(quality + b, 0x7f, 8, st));      // did not settle in four rounds
+    tr.mark("re-orthonormalisation");
     // residuals of the tridiagonal eigenpairs (before the back-transformation, O(n) per vector)
     eig_residual_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)batch), 128, 0, st>>>(d, e, V, tnorm, sz, rq, (unsigned long long*)quality);
     CRM_CUDA(cudaGetLastError()); count_launch();
@@ -189,6 +199,8 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
         CRM_SOLVER_(cusolverDnDormtr(solver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, nb, nb, A + (size_t)b * nn, nb, tau + (size_t)b * n, V + (size_t)b * nn, nb,
                                      lib_work, lib_lwork, info_dev + batch + b));
     }
+    tr.mark("residuals + back-transformation");
+    tr.report("batched eigensolver");
     return CRM_OK;
 }
 

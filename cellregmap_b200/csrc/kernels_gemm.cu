@@ -129,7 +129,7 @@ int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream)
             splits = (args.K + chunk - 1) / chunk;
             args.k_splits = splits; args.k_chunk = chunk;
             args.partial_stride = (long long)args.n_count * args.m_count;
-            if (splits > 1) CRM_CUDA(cudaMallocAsync((void**)&args.partial, (size_t)splits * args.partial_stride * sizeof(double), stream));
+            if (splits > 1) CRM_CUDA(pool_alloc_async((void**)&args.partial, (size_t)splits * args.partial_stride * sizeof(double), stream));
         }
     }
     dim3 grid((unsigned)ctas, (unsigned)args.k_splits, 1);
@@ -189,7 +189,7 @@ int measure_fp64_tensor_peak(double* tflops, cudaStream_t st) {
     CRM_CUDA(cudaGetDevice(&dev));
     CRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     double* out = nullptr;
-    CRM_CUDA(cudaMallocAsync((void**)&out, (size_t)sms * 2 * 256 * sizeof(double), st));
+    CRM_CUDA(pool_alloc_async((void**)&out, (size_t)sms * 2 * 256 * sizeof(double), st));
     const int iters = 20000, grid = sms * 2;
     cudaEvent_t e0, e1;
     CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));

@@ -20,6 +20,9 @@ constexpr int GEMM_TILE_N = 128;
 int launch_gemm(int mode, const GemmOperands& op, int K, int m_begin, int m_count, int n_begin, int n_count,
                 double* out, long long ldc, int kexp, cudaStream_t stream);
 
+// stream-ordered scratch from the library's private memory pool (abi.cu); release with cudaFreeAsync
+cudaError_t pool_alloc_async(void** ptr, size_t bytes, cudaStream_t st);
+
 // FP64 tensor-core (DMMA) issue-rate peak of the current device in TFLOP/s, measured with a register-resident probe kernel (~5 ms)
 int measure_fp64_tensor_peak(double* tflops, cudaStream_t stream);
 
@@ -67,6 +70,8 @@ int oz_int8_gemm(const int8_t* A8, long long Mrows, const int8_t* Gt8, long long
 int eig_workspace_bytes(int n, int batch, size_t* bytes);
 int eig_lib_lwork(void* solver, int n, int* lwork);
 int eig_batched(void* solver, void* blas, double* A, const int* n_of, int n, int batch, double* W, double* V, double* quality, void* ws, double* lib_work, int lib_lwork,
-                int* info_dev, cudaStream_t st);
+                int* info_dev, cudaStream_t st, int group_batch = 0, const int* ids = nullptr);
+// group_batch: size of the batch this one is a share of (0: itself); ids: position of each matrix in that batch (seeds of the start vectors).
+// With both given, a matrix is decomposed to the same bits whichever share of the batch it is solved in.
 
 }  // namespace crm

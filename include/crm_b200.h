@@ -117,7 +117,8 @@ CRM_API int crm_update_phenotype(crm_handle_t h, const double* y, void* stream);
 CRM_API int crm_set_donors(crm_handle_t h, const int32_t* perm, const int32_t* offsets, int64_t d, void* stream);
 
 /* Sizes fixed by crm_setup: [0]=n [1]=c [2]=k0 [3]=m (columns of H) [4]=R [5]=padded m [6]=max kept rank
- * [7]=1 when the pre-expanded basis [Hx | Hx.E0_j] is resident (rotation runs as a plain contraction). */
+ * [7]=1 when the pre-expanded basis [Hx | Hx.E0_j] of the float64 route is resident (rotation runs as a plain contraction), 0 when it
+ * is not, -1 before the first float64 rotation of the model has decided. */
 CRM_API int crm_get_dims(crm_handle_t h, int64_t* dims8);
 /* Copies S0 of grid point r (padded to dims[5], zeros beyond the kept rank) into out (device). */
 CRM_API int crm_get_spectrum(crm_handle_t h, int r, double* out, void* stream);

@@ -6,7 +6,7 @@ third-party packages that are neither vendored under /root/reference nor install
 `install()` registers stand-in modules for exactly the names the reference imports, backed by the restatements of this
 package (lmm_port, sugar_port, chiscore_port); `load_reference()` then imports the unmodified reference package:
 
-  * from `oracle/_ref/cellregmap/*.pyc`, byte-compiled by `oracle/build_ref.py` from the sources where they lie under
+  * from `oracle/_ref/cellregmap/*.bin` (byte code), compiled by `oracle/build_ref.py` from the sources where they lie under
     /root/reference (compiled outputs only -- no reference source is copied; oracle/_ref is git-ignored and travels to
     the GPU box like any other built checker), or
   * from /root/reference itself when that directory exists (this container).
@@ -93,7 +93,44 @@ def is_shimmed():
 
 
 def available():
-    return os.path.isdir(os.path.join(REF_SOURCE, "cellregmap")) or os.path.exists(os.path.join(REF_BUILD, "cellregmap", "__init__.pyc"))
+    return os.path.isdir(os.path.join(REF_SOURCE, "cellregmap")) or os.path.exists(os.path.join(REF_BUILD, "cellregmap", "__init__.bin"))
+
+
+def _load_compiled(root):
+    """Import the byte-compiled package oracle/_ref/cellregmap (files *.bin = .pyc content) without any source."""
+    import importlib.machinery
+    import importlib.util
+    pkg_dir = os.path.join(root, "cellregmap")
+
+    def load(name, fname, is_pkg=False):
+        loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(pkg_dir, fname))
+        spec = importlib.util.spec_from_loader(name, loader, is_package=is_pkg)
+        mod = importlib.util.module_from_spec(spec)
+        if is_pkg:
+            mod.__path__ = [pkg_dir]
+        sys.modules[name] = mod
+        try:
+            loader.exec_module(mod)
+        except BaseException:
+            sys.modules.pop(name, None)
+            raise
+        return mod
+
+    # submodules first (the package's __init__ imports from them), in dependency order
+    pkg = types.ModuleType("cellregmap")
+    pkg.__path__ = [pkg_dir]
+    pkg.__package__ = "cellregmap"
+    sys.modules["cellregmap"] = pkg
+    try:
+        for sub in ("_types", "_math", "_cellregmap", "_simulate"):
+            setattr(pkg, sub, load("cellregmap." + sub, sub + ".bin"))
+        init = importlib.machinery.SourcelessFileLoader("cellregmap", os.path.join(pkg_dir, "__init__.bin"))
+        exec(init.get_code("cellregmap"), pkg.__dict__)
+    except BaseException:
+        for name in [n for n in sys.modules if n == "cellregmap" or n.startswith("cellregmap.")]:
+            sys.modules.pop(name, None)
+        raise
+    return pkg
 
 
 def load_reference(qs_method="svd", prefer_source=True):
@@ -105,18 +142,21 @@ def load_reference(qs_method="svd", prefer_source=True):
         return cached
     if prefer_source and os.path.isdir(os.path.join(REF_SOURCE, "cellregmap")):
         root = REF_SOURCE
-    elif os.path.exists(os.path.join(REF_BUILD, "cellregmap", "__init__.pyc")):
+    elif os.path.exists(os.path.join(REF_BUILD, "cellregmap", "__init__.bin")):
         root = REF_BUILD
     else:
         return None
-    sys.path.insert(0, root)
-    try:
-        sys.dont_write_bytecode, saved = True, sys.dont_write_bytecode     # /root/reference is read-only
-        mod = importlib.import_module("cellregmap")
-        importlib.import_module("cellregmap._simulate")
-    finally:
-        sys.dont_write_bytecode = saved
-        sys.path.remove(root)
+    if root == REF_BUILD:
+        mod = _load_compiled(root)
+    else:
+        sys.path.insert(0, root)
+        try:
+            sys.dont_write_bytecode, saved = True, sys.dont_write_bytecode     # /root/reference is read-only
+            mod = importlib.import_module("cellregmap")
+            importlib.import_module("cellregmap._simulate")
+        finally:
+            sys.dont_write_bytecode = saved
+            sys.path.remove(root)
     mod.__oracle_loaded__ = True
     mod.__oracle_root__ = root
     return mod

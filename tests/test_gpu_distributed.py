@@ -54,5 +54,6 @@ def test_sharded_scan_with_shared_setup(cuda_device, world):
     for rank in range(world):
         for name, got in results[rank].items():
             # every rank returns the full result; SNP sharding changes no bit of a SNP's arithmetic, and neither does sharing the set-up
-            # (a grid point's decomposition does not depend on which other grid points are decomposed with it)
+            # (a grid point's decomposition does not depend on which other grid points are decomposed with it: the batched solver
+            # keeps the CTA-group size of the whole grid)
             np.testing.assert_array_equal(got, want, err_msg=f"rank {rank} {name}")

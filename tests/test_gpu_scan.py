@@ -269,12 +269,13 @@ def test_rotation_routes_agree(cuda_device, monkeypatch):
     d = make_data(n=900, donors=60, k=7, p=130, q=5, seed=17)
     monkeypatch.setenv("CRM_ROTATION", "dmma")      # integer dosages would otherwise take the int8 split
     model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
-    assert model._dims["pre_expanded_basis"]
+    assert model._pre_expanded_basis() is None          # decided by the first float64 rotation
     pv_a, info_a = model.scan_interaction(d.G)
+    assert model._pre_expanded_basis() is True
     monkeypatch.setenv("CRM_NO_HXE", "1")
     model_b = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
-    assert not model_b._dims["pre_expanded_basis"]
     pv_b, info_b = model_b.scan_interaction(d.G)
+    assert model_b._pre_expanded_basis() is False
     np.testing.assert_array_equal(info_a["rho1"], info_b["rho1"])
     assert np.max(np.abs(np.log10(pv_a) - np.log10(pv_b))) <= 1e-8
     for key in ("e2", "g2", "eps2"):
