@@ -148,6 +148,10 @@ struct Handle {
     DevBuf A8, a8expo, Gt8, G2t8, D32, ozflags, A28, a28expo;   // A28: digit planes of A2 = [1 | E0 | pairs] for the g^2 Grams
     bool oz_block_valid = false;   // Gt8 / G2t8 hold the int8 image of the genotype block of the rotation just done
     int oz_block_gmax = 0;
+    // affine-integer genotype columns g = a d + b (ozaki.cuh): Gt8 holds d; aff = [a | b | tolerance] per column of the block;
+    // colsum / colsum2 = column sums of [Hx | Hx.E0_j] and of A2 (per gene, built on demand)
+    bool oz_block_affine = false, colsum_valid = false;
+    DevBuf aff, affscratch, colsum, colsum2, sq1;
     double prof_oz_gemm_ops = 0.0; std::vector<cudaEvent_t> prof_oz_events;
     int hxe_blocks = 0;   // context blocks j held by HxE at a time: kexp = whole basis resident, fewer = streamed in groups
     DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
@@ -178,7 +182,7 @@ struct Handle {
         DevBuf* all[] = {&A8, &a8expo, &Gt8, &G2t8, &D32, &ozflags, &A28, &a28expo, &HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
-                         &gtchunk[0], &gtchunk[1], &gstage, &g8dev[0], &g8dev[1], &gwide, &gwide2, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
+                         &gtchunk[0], &gtchunk[1], &gstage, &g8dev[0], &g8dev[1], &gwide, &gwide2, &aff, &affscratch, &colsum, &colsum2, &sq1, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -423,6 +427,7 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
     h->hxe_built = false;    // the pre-expanded basis is (re)built by the first cell-level rotation that needs it
     h->oz_built = false;
     h->oz_built_a2 = false;
+    h->colsum_valid = false;
     h->cells.K = h->n; h->cells.HxE = nullptr; h->cells.ldE = (long long)h->kexp * h->ldH;   // cells.HxE unused: see launch_rotation
     h->cells.Hx = h->Hx.as<double>(); h->cells.ldHx = h->ldH; h->cells.A2 = h->A2.as<double>(); h->cells.ld2 = h->ld2;
     if (h->donors_set) CRM_CHECK(aggregate_donors(h, st));
@@ -469,6 +474,28 @@ static int int8_split_contract(Handle* h, const int8_t* P8, long long Mp, long l
     return oz_launch_combine(h->D32.as<int>(), Mp, Bp, expo, Mtot, B, C, ldc, st);
 }
 
+// column sums of the expanded basis, colsum[j * ldH + a] = sum_i Eext[i][j] Hx[i][a], and of A2: the images of a constant genotype
+// column, which map contractions of the integer part d of an affine column g = a d + b back to contractions of g
+static int ensure_column_sums(Handle* h, cudaStream_t st) {
+    if (h->colsum_valid) return CRM_OK;
+    CRM_CHECK(h->colsum.reserve((size_t)h->kexp * h->ldH * 8));
+    CRM_CHECK(h->colsum2.reserve((size_t)h->ld2 * 8));
+    CRM_CUDA(cudaMemsetAsync(h->colsum.ptr, 0, (size_t)h->kexp * h->ldH * 8, st));
+    GemmOperands op{};
+    op.A = h->Hx.as<double>(); op.lda = h->ldH; op.a_cols = h->Mx;
+    op.B = h->Eext.as<double>(); op.ldb = h->epitch; op.b_cols = h->epitch; op.B2 = op.B; op.ldb2 = op.ldb; op.b2_cols = op.b_cols;
+    gemm_set_free_split(true);
+    int status = launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, h->Mx, 0, h->kexp, h->colsum.as<double>(), h->ldH, 1, st);
+    GemmOperands o2{};
+    o2.A = h->A2.as<double>(); o2.lda = h->ld2; o2.a_cols = h->M2;
+    o2.B = h->Eext.as<double>(); o2.ldb = h->epitch; o2.b_cols = h->epitch; o2.B2 = o2.B; o2.ldb2 = o2.ldb; o2.b2_cols = o2.b_cols;
+    if (status == CRM_OK) status = launch_gemm(GEMM_PLAIN, o2, (int)h->n, 0, h->M2, 0, 1, h->colsum2.as<double>(), h->ld2, 1, st);     // Eext column 0 = ones
+    gemm_set_free_split(false);
+    CRM_CHECK(status);
+    h->colsum_valid = true;
+    return CRM_OK;
+}
+
 static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStream_t st, int* used) {
     *used = 0;
     const long long B = blk.b;
@@ -491,6 +518,7 @@ static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStre
     CRM_CHECK(h->G2t8.reserve((size_t)Bp * Kp));
     CRM_CHECK(h->ozflags.reserve(64));
     int flags[4] = {0, 0, 0, 0};
+    bool affine = false;
     if (blk.G8 && blk.gmax >= 0) {
         // int8 dosages whose range the host already knows (converted by the feeder): no flag read-back, no host synchronisation
         if ((double)Kp * 64.0 * (double)std::max(blk.gmax, 1) >= 2147483648.0) return CRM_OK;
@@ -502,7 +530,20 @@ static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStre
         CRM_CUDA(cudaMemcpyAsync(flags, h->ozflags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
         CRM_CUDA(cudaStreamSynchronize(st));
         if (flags[2] != 0) { set_error("There are non-finite values in the genotype matrix (SNP columns %lld..%lld).", blk.s0, blk.s0 + B - 1); return CRM_ERR_NONFINITE; }
-        if (flags[0] != 0) return CRM_OK;                                              // not integer dosages
+        if (flags[0] != 0) {
+            // not integer dosages: every column an affine image a d + b of small integers (standardised / centred dosages)?
+            static const bool affine_on = [] { const char* v = getenv("CRM_AFFINE"); return !(v && atoi(v) == 0); }();
+            if (!affine_on || !blk.G) return CRM_OK;
+            const long long lda = round_up(B, 2);
+            CRM_CHECK(h->aff.reserve((size_t)3 * lda * 8));
+            CRM_CHECK(h->affscratch.reserve(oz_affine_scratch_bytes(B)));
+            CRM_CHECK(oz_launch_affine_genotypes(blk.G, blk.ld, n, B, h->affscratch.ptr, h->aff.as<double>(), lda, h->Gt8.as<int8_t>(), h->G2t8.as<int8_t>(), Bp, Kp,
+                                                 h->ozflags.as<int>(), st));
+            CRM_CUDA(cudaMemcpyAsync(flags, h->ozflags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
+            CRM_CUDA(cudaStreamSynchronize(st));
+            if (flags[0] != 0) return CRM_OK;                                          // real-valued genotypes: the fp64 route
+            affine = true;
+        }
         if ((double)Kp * 64.0 * (double)std::max(flags[1], 1) >= 2147483648.0) return CRM_OK;   // int32 accumulation could overflow
     }
     tr.mark("genotypes->int8");
@@ -524,9 +565,15 @@ static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStre
     CRM_CHECK(int8_split_contract(h, h->A8.as<int8_t>(), Mp, Mtot, h->a8expo.as<int>(), h->Gt8.as<int8_t>(), Bp, B, Kp, C, Mtot, st));
     if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_oz_events.back(), st));
     tr.mark("int8 contraction");
+    if (affine) {
+        CRM_CHECK(ensure_column_sums(h, st));
+        CRM_CHECK(oz_launch_affine_fix(C, Mtot, B, Mtot, h->aff.as<double>(), round_up(B, 2), h->colsum.as<double>(), st));
+        tr.mark("affine map");
+    }
     tr.report("int8 rotation");
     h->oz_block_valid = true;
     h->oz_block_gmax = flags[1];
+    h->oz_block_affine = affine;
     *used = 1;
     return CRM_OK;
 }
@@ -854,6 +901,7 @@ static int do_update_phenotype(Handle* h, const double* y, cudaStream_t st) {
         h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
     h->oz_built = false;     // the digit planes of the y column (and its exponent) change with the phenotype: rebuilt on demand
+    h->colsum_valid = false;
     if (h->use_hxe && h->hxe_built && h->hxe_blocks == h->kexp) {
         refresh_y_hxe_kernel<<<blocks_for(h->n * h->kexp, 256), 256, 0, st>>>(Hx, ldH, m, h->Eext.as<double>(), h->epitch, h->kexp, h->n, h->HxE.as<double>());
         CRM_CUDA(cudaGetLastError()); count_launch();
@@ -1236,6 +1284,11 @@ static int interaction_batch(Handle* h, GBlock blk, double* out_pv, double* out_
             h->oz_built_a2 = true;
         }
         CRM_CHECK(int8_split_contract(h, h->A28.as<int8_t>(), M2p, h->M2, h->a28expo.as<int>(), h->G2t8.as<int8_t>(), Bp, B, Kp, sq, h->ld2, st));
+        if (h->oz_block_affine) {       // g = a d + b: Grams of g^2 from those of d^2 (above) and of d
+            CRM_CHECK(h->sq1.reserve((size_t)B * h->ld2 * 8));
+            CRM_CHECK(int8_split_contract(h, h->A28.as<int8_t>(), M2p, h->M2, h->a28expo.as<int>(), h->Gt8.as<int8_t>(), Bp, B, Kp, h->sq1.as<double>(), h->ld2, st));
+            CRM_CHECK(oz_launch_affine_fix_square(sq, h->sq1.as<double>(), h->ld2, B, h->M2, h->aff.as<double>(), round_up(B, 2), h->colsum2.as<double>(), st));
+        }
     } else {
         CRM_CHECK(block_f64(h, blk, st));
         GemmOperands op{};
@@ -1697,6 +1750,15 @@ int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dtype, int
 }
 
 int crm_host_threads(void) { return host_threads(); }
+
+int crm_host_narrow(const void* src_host, int dtype, int64_t ld, int64_t rows, int64_t cols, int8_t* dst_host, int64_t ldd, int32_t* bad, int32_t* gmax) {
+    if (!src_host || !dst_host || rows < 0 || cols < 0 || ld < cols || ldd < cols || host_dtype_size(dtype) == 0) { set_error("crm_host_narrow: bad arguments"); return CRM_ERR_INVALID; }
+    int b = 0, g = 0;
+    host_parallel_narrow(src_host, dtype, ld, rows, 0, cols, dst_host, ldd, &b, &g);
+    if (bad) *bad = b;
+    if (gmax) *gmax = g;
+    return CRM_OK;
+}
 
 int crm_fp64_tensor_peak(double* tflops, void* stream) {
     if (!tflops) { set_error("crm_fp64_tensor_peak: null output"); return CRM_ERR_INVALID; }

@@ -1,6 +1,9 @@
 // Host-side genotype feeder (feeder.hpp): worker pool, pinned slot cache, narrowing loops.  Plain C++ (g++), no device code.
 #include "feeder.hpp"
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <sched.h>
 #include <stdlib.h>
 #include <string.h>
@@ -76,8 +79,46 @@ static inline void narrow_row_int(const T* s, int8_t* d, long long b, int& bad, 
     bad |= lb; gmax = lm > gmax ? lm : gmax;
 }
 
-CRM_CLONES static NarrowFlags narrow_f64(const double* src, long long ld, long long r0, long long r1, long long c0, long long b, int8_t* dst, long long ldd) {
+#if defined(__x86_64__)
+// float64 -> int8, 16 entries per iteration: truncating conversion, exactness by converting back (NaN and out-of-range entries convert to
+// INT_MIN and fail the comparison), range by the running maximum of |q|.  The auto-vectoriser leaves the scalar loop alone; this is twice
+// as fast per thread and the conversion of 8 GB of dosages is what the end-to-end scan waits for.
+__attribute__((target("avx2"))) static void narrow_row_f64_avx2(const double* s, int8_t* d, long long b, int& bad, int& gmax) {
+    __m256d ok = _mm256_castsi256_pd(_mm256_set1_epi32(-1));
+    __m128i mx = _mm_setzero_si128();
+    long long j = 0;
+    for (; j + 16 <= b; j += 16) {
+        const __m256d v0 = _mm256_loadu_pd(s + j), v1 = _mm256_loadu_pd(s + j + 4), v2 = _mm256_loadu_pd(s + j + 8), v3 = _mm256_loadu_pd(s + j + 12);
+        const __m128i q0 = _mm256_cvttpd_epi32(v0), q1 = _mm256_cvttpd_epi32(v1), q2 = _mm256_cvttpd_epi32(v2), q3 = _mm256_cvttpd_epi32(v3);
+        ok = _mm256_and_pd(ok, _mm256_and_pd(_mm256_and_pd(_mm256_cmp_pd(_mm256_cvtepi32_pd(q0), v0, _CMP_EQ_OQ), _mm256_cmp_pd(_mm256_cvtepi32_pd(q1), v1, _CMP_EQ_OQ)),
+                                              _mm256_and_pd(_mm256_cmp_pd(_mm256_cvtepi32_pd(q2), v2, _CMP_EQ_OQ), _mm256_cmp_pd(_mm256_cvtepi32_pd(q3), v3, _CMP_EQ_OQ))));
+        mx = _mm_max_epu32(mx, _mm_max_epu32(_mm_max_epu32(_mm_abs_epi32(q0), _mm_abs_epi32(q1)), _mm_max_epu32(_mm_abs_epi32(q2), _mm_abs_epi32(q3))));
+        const __m128i p01 = _mm_packs_epi32(q0, q1), p23 = _mm_packs_epi32(q2, q3);
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(d + j), _mm_packs_epi16(p01, p23));
+    }
+    int lb = _mm256_movemask_pd(ok) != 0xF;
+    alignas(16) unsigned m4[4];
+    _mm_store_si128(reinterpret_cast<__m128i*>(m4), mx);
+    unsigned lm = 0;
+    for (int u = 0; u < 4; u++) lm = m4[u] > lm ? m4[u] : lm;
+    int tb = 0, tm = 0;
+    narrow_row_float<double>(s + j, d + j, b - j, tb, tm);
+    lb |= tb;
+    lm = (unsigned)tm > lm ? (unsigned)tm : lm;
+    if (lm > 127u) { lb = 1; lm = 127u; }
+    bad |= lb; gmax = (int)lm > gmax ? (int)lm : gmax;
+}
+#endif
+
+static NarrowFlags narrow_f64(const double* src, long long ld, long long r0, long long r1, long long c0, long long b, int8_t* dst, long long ldd) {
     NarrowFlags f{0, 0};
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) {
+        for (long long i = r0; i < r1; i++) narrow_row_f64_avx2(src + i * ld + c0, dst + i * ldd, b, f.bad, f.gmax);
+        return f;
+    }
+#endif
     for (long long i = r0; i < r1; i++) narrow_row_float<double>(src + i * ld + c0, dst + i * ldd, b, f.bad, f.gmax);
     return f;
 }
@@ -283,6 +324,21 @@ void host_parallel_widen(const void* src, int dtype, long long ld, long long row
             default: break;
         }
     });
+}
+
+void host_parallel_narrow(const void* src, int dtype, long long ld, long long rows, long long c0, long long cols, int8_t* dst, long long ldd, int* bad, int* gmax) {
+    const int threads = host_threads();
+    const long long chunk = std::max<long long>(64, (rows + 4 * threads - 1) / (4 * threads));
+    const long long units = (rows + chunk - 1) / chunk;
+    std::atomic<int> any_bad{0}, top{0};
+    parallel_for(units, [&](long long u) {
+        const NarrowFlags f = narrow_any(src, dtype, ld, u * chunk, std::min(rows, (u + 1) * chunk), c0, cols, dst, ldd);
+        if (f.bad) any_bad.store(1);
+        int cur = top.load();
+        while (f.gmax > cur && !top.compare_exchange_weak(cur, f.gmax)) {}
+    });
+    if (bad) *bad = any_bad.load();
+    if (gmax) *gmax = top.load();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -56,4 +56,7 @@ void feeder_cancel(FeedJob& job);
 // synchronous helper: copy rows x cols elements of any host dtype into a float64 pinned/pageable destination with the pool
 void host_parallel_widen(const void* src, int dtype, long long ld, long long rows, long long c0, long long cols, double* dst, long long ldd);
 
+// synchronous helper: the feeder's conversion of rows x cols elements (columns c0.. of a matrix of leading dimension ld) to int8
+void host_parallel_narrow(const void* src, int dtype, long long ld, long long rows, long long c0, long long cols, int8_t* dst, long long ldd, int* bad, int* gmax);
+
 }  // namespace crm

@@ -76,6 +76,34 @@ int oz_launch_finite_check(const double* G, long long ldg, long long n, long lon
     return CRM_OK;
 }
 
+// affine-integer columns (ozaki.cuh): statistics -> lattice (a, b, tolerance) per column -> int8 image of d; scratch = chunks * B OzColStat
+size_t oz_affine_scratch_bytes(long long B) { return (size_t)OZ_AFFINE_CHUNKS * (size_t)B * sizeof(OzColStat); }
+int oz_launch_affine_genotypes(const double* G, long long ldg, long long n, long long B, void* scratch, double* aff, long long lda, int8_t* Gt8, int8_t* G2t8,
+                               long long Bp, long long Kp, int* flags, cudaStream_t st) {
+    const int chunks = (int)std::max<long long>(1, std::min<long long>(OZ_AFFINE_CHUNKS, n / 256));
+    const long long rows_per_chunk = (n + chunks - 1) / chunks;
+    OzColStat* partial = static_cast<OzColStat*>(scratch);
+    oz_colstat_kernel<<<dim3((unsigned)((B + 31) / 32), (unsigned)chunks), 256, 0, st>>>(G, ldg, n, B, rows_per_chunk, partial);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    oz_colstat_merge_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(partial, chunks, B, aff, lda);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    CRM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
+    dim3 grid((unsigned)((Kp + OZ_ROWS - 1) / OZ_ROWS), (unsigned)((Bp + OZ_TILE - 1) / OZ_TILE), 1);
+    oz_affine_genotype_kernel<<<grid, 256, 0, st>>>(G, ldg, n, B, aff, lda, Gt8, G2t8, Bp, Kp, flags);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+int oz_launch_affine_fix(double* C, long long ldc, long long B, long long cols, const double* aff, long long lda, const double* colsum, cudaStream_t st) {
+    oz_affine_fix_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)B), 256, 0, st>>>(C, ldc, B, cols, aff, lda, colsum);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+int oz_launch_affine_fix_square(double* sq, const double* lin, long long ld, long long B, int cols, const double* aff, long long lda, const double* colsum2, cudaStream_t st) {
+    oz_affine_fix_square_kernel<<<dim3((unsigned)((cols + 127) / 128), (unsigned)B), 128, 0, st>>>(sq, lin, ld, B, cols, aff, lda, colsum2);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+
 int oz_launch_combine(const int* D, long long Mp, long long ldd, const int* expo, long long Mtot, long long B, double* C, long long ldc, cudaStream_t st) {
     dim3 grid((unsigned)((B + OZ_TILE - 1) / OZ_TILE), (unsigned)((Mtot + OZ_TILE - 1) / OZ_TILE), 1), block(OZ_TILE, 8, 1);
     oz_combine_kernel<<<grid, block, 0, st>>>(D, Mp, ldd, expo, Mtot, B, C, ldc);

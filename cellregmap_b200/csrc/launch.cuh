@@ -58,6 +58,13 @@ int oz_launch_genotypes(const double* G, long long ldg, long long n, long long B
 int oz_launch_transpose_i8(const int8_t* G8, long long ld8, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st);
 int oz_launch_widen_i8(const int8_t* G8, long long ld8, long long n, long long B, double* out, long long ldo, cudaStream_t st);
 int oz_launch_finite_check(const double* G, long long ldg, long long n, long long B, int* flags, cudaStream_t st);
+// affine-integer genotype columns g = a d + b (ozaki.cuh): detection + int8 image of d, and the maps back from contractions of d
+constexpr int OZ_AFFINE_CHUNKS = 128;
+size_t oz_affine_scratch_bytes(long long B);
+int oz_launch_affine_genotypes(const double* G, long long ldg, long long n, long long B, void* scratch, double* aff, long long lda, int8_t* Gt8, int8_t* G2t8,
+                               long long Bp, long long Kp, int* flags, cudaStream_t st);
+int oz_launch_affine_fix(double* C, long long ldc, long long B, long long cols, const double* aff, long long lda, const double* colsum, cudaStream_t st);
+int oz_launch_affine_fix_square(double* sq, const double* lin, long long ld, long long B, int cols, const double* aff, long long lda, const double* colsum2, cudaStream_t st);
 int oz_launch_matrix_planes(const double* X, long long ldx, int cols, long long n, int* expo, int8_t* P8, long long Mp, long long Kp, cudaStream_t st);
 int oz_launch_combine(const int* D, long long Mp, long long ldd, const int* expo, long long Mtot, long long B, double* C, long long ldc, cudaStream_t st);
 // the same contraction + recombination in one hand-written tcgen05 kernel (oz_mma.cuh): C[s][col], bit-identical

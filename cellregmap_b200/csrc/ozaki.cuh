@@ -232,6 +232,114 @@ __global__ void oz_finite_check_kernel(const double* G, long long ldg, long long
     if ((threadIdx.x & 31) == 0 && bad) atomicOr(&flags[2], 1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Affine-integer genotype columns: g = a d + b with small non-negative integers d (standardised dosages -- the reference's own
+// simulator hands column_normalize(G) to the scan, cellregmap/_simulate.py:50-54,339 -- centred dosages, dosages / 2 ...).  The
+// contraction is linear in g, so it runs on d with the exact int8 split and is mapped back with the column sums of the basis:
+//     sum_i X[i][col] g_i = a sum_i X[i][col] d_i + b sum_i X[i][col].
+// Detection per column: the two smallest distinct values give b and a, every entry must then sit on the lattice b + a {0..127}
+// within a few ulps of the column's magnitude (what the rounding of (d - mean) / sd leaves).
+// ---------------------------------------------------------------------------------------------------------------------------
+struct OzColStat { double m1, m2, mx; };      // smallest, second smallest distinct (+inf: none), largest
+__device__ __forceinline__ void oz_stat_push(OzColStat& s, double v) {
+    if (v < s.m1) { s.m2 = s.m1; s.m1 = v; }
+    else if (v > s.m1 && v < s.m2) s.m2 = v;
+    if (v > s.mx) s.mx = v;
+}
+__device__ __forceinline__ void oz_stat_merge(OzColStat& s, const OzColStat& o) {
+    oz_stat_push(s, o.m1);
+    if (o.m2 < s.m2 && o.m2 > s.m1) s.m2 = o.m2;
+    if (o.mx > s.mx) s.mx = o.mx;
+}
+// partial[chunk][s]: statistics of the rows of one chunk; grid (column tiles of 32, row chunks), 32 x 8 threads
+__global__ void __launch_bounds__(256) oz_colstat_kernel(const double* G, long long ldg, long long n, long long B, long long rows_per_chunk, OzColStat* partial) {
+    __shared__ OzColStat sh[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long s = (long long)blockIdx.x * 32 + tx;
+    const long long i0 = (long long)blockIdx.y * rows_per_chunk, i1 = min(n, i0 + rows_per_chunk);
+    OzColStat st{INFINITY, INFINITY, -INFINITY};
+    if (s < B) for (long long i = i0 + ty; i < i1; i += 8) oz_stat_push(st, G[i * ldg + s]);
+    sh[ty][tx] = st;
+    __syncthreads();
+    if (ty == 0 && s < B) {
+        for (int r = 1; r < 8; r++) oz_stat_merge(st, sh[r][tx]);
+        partial[(long long)blockIdx.y * B + s] = st;
+    }
+}
+// aff[0][s] = a (lattice step), aff[1][s] = b (origin), aff[2][s] = tolerance
+__global__ void oz_colstat_merge_kernel(const OzColStat* partial, int chunks, long long B, double* aff, long long lda) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B) return;
+    OzColStat st = partial[s];
+    for (int c = 1; c < chunks; c++) oz_stat_merge(st, partial[(long long)c * B + s]);
+    const double step = (st.m2 < INFINITY) ? st.m2 - st.m1 : 1.0;          // constant column: d = 0 everywhere
+    aff[s] = step;
+    aff[lda + s] = st.m1;
+    aff[2 * lda + s] = 8.0 * 2.220446049250313e-16 * fmax(fabs(st.m1), fabs(st.mx));
+}
+// Gt8[s][i] = d, G2t8[s][i] = d^2 with d = rint((G[i][s] - b_s) / a_s); flags[0] |= 1 when some entry is off the lattice (or not
+// finite, or d > 127); flags[1] = max d.  Same tiling as oz_genotype_kernel.
+__global__ void __launch_bounds__(256) oz_affine_genotype_kernel(const double* G, long long ldg, long long n, long long B, const double* aff, long long lda, int8_t* Gt8,
+                                                                 int8_t* G2t8, long long Bp, long long Kp, int* flags) {
+    __shared__ double tile[OZ_ROWS][OZ_TILE + 1];
+    __shared__ int s_bad, s_max;
+    const long long i0 = (long long)blockIdx.x * OZ_ROWS;
+    const long long s0 = (long long)blockIdx.y * OZ_TILE;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_bad = 0; s_max = 0; }
+    __syncthreads();
+    int bad = 0, gmax = 0;
+    const long long sc = s0 + tx;
+    const double a = sc < B ? aff[sc] : 1.0, b = sc < B ? aff[lda + sc] : 0.0, tol = sc < B ? aff[2 * lda + sc] : 0.0;
+    for (int r = ty; r < OZ_ROWS; r += 8) {
+        const long long i = i0 + r;
+        double d = 0.0;
+        if (i < n && sc < B) {
+            const double v = G[i * ldg + sc];
+            d = rint((v - b) / a);
+            if (!(fabs(v - fma(a, d, b)) <= tol) || !(d >= 0.0 && d <= 127.0)) { bad = 1; d = 0.0; } else gmax = max(gmax, (int)d);
+        }
+        tile[r][tx] = d;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if (tx == 0) { if (bad) atomicOr(&s_bad, 1); atomicMax(&s_max, gmax); }
+    __syncthreads();
+    for (int r = ty; r < OZ_TILE; r += 8) {
+        const long long s = s0 + r, i = i0 + 4 * tx;
+        if (s < Bp && i < Kp) {
+            char4 q, q2;
+            signed char* qa = reinterpret_cast<signed char*>(&q);
+            signed char* qb = reinterpret_cast<signed char*>(&q2);
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int gv = (int)tile[4 * tx + u][r]; qa[u] = (signed char)gv; qb[u] = (signed char)(gv * gv); }
+            *reinterpret_cast<char4*>(Gt8 + s * Kp + i) = q;
+            if (G2t8) *reinterpret_cast<char4*>(G2t8 + s * Kp + i) = q2;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (s_bad) atomicOr(&flags[0], 1);
+        if (s_max > *reinterpret_cast<volatile int*>(&flags[1])) atomicMax(&flags[1], s_max);
+    }
+}
+// C[s][col] <- a_s C[s][col] + b_s colsum[col]      (rotation of g = a d + b from the rotation of d)
+__global__ void oz_affine_fix_kernel(double* C, long long ldc, long long B, long long cols, const double* aff, long long lda, const double* colsum) {
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long s = blockIdx.y;
+    if (col >= cols || s >= B) return;
+    const double a = aff[s], b = aff[lda + s];
+    C[s * ldc + col] = fma(a, C[s * ldc + col], b * colsum[col]);
+}
+// sq[s][c] <- a^2 sq[s][c] + 2 a b lin[s][c] + b^2 colsum2[c]      (Grams of g^2 from those of d^2 and d)
+__global__ void oz_affine_fix_square_kernel(double* sq, const double* lin, long long ld, long long B, int cols, const double* aff, long long lda, const double* colsum2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long s = blockIdx.y;
+    if (c >= cols || s >= B) return;
+    const double a = aff[s], b = aff[lda + s];
+    sq[s * ld + c] = a * a * sq[s * ld + c] + 2.0 * a * b * lin[s * ld + c] + b * b * colsum2[c];
+}
+
 // C[s][col] = 2^(e_col + 1) sum_t 2^(-7 (t + 1)) D[t * Mp + col][s]   (D int32, row stride ldd; C fp64, row stride ldc)
 __global__ void oz_combine_kernel(const int* D, long long Mp, long long ldd, const int* expo, long long Mtot, long long B, double* C, long long ldc) {
     __shared__ double tile[OZ_TILE][OZ_TILE + 1];

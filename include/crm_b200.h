@@ -95,6 +95,11 @@ CRM_API int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dt
 CRM_API int crm_fp64_tensor_peak(double* tflops, void* stream);
 /* Worker threads of the host feeder. */
 CRM_API int crm_host_threads(void);
+/* The feeder's conversion on its own (host memory in, host memory out, no device involved): rows x cols elements of type `dtype`
+ * (leading dimension ld) -> int8 (leading dimension ldd bytes); *bad = 1 when some entry is not an integer in [-127, 127] (such
+ * entries are written as saturated / arbitrary values), *gmax = largest |entry| among the valid ones. */
+CRM_API int crm_host_narrow(const void* src_host, int dtype, int64_t ld, int64_t rows, int64_t cols, int8_t* dst_host, int64_t ldd,
+                            int32_t* bad, int32_t* gmax);
 
 /* Replaces the tested-context matrix E0 (row-permuted contexts: idx_E of scan_interaction, _cellregmap.py:398-401). */
 CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream);

@@ -566,3 +566,80 @@ def test_scan_and_predict_on_a_side_stream(cuda_device, monkeypatch):
     np.testing.assert_array_equal(bx1, bx0)
     np.testing.assert_array_equal(got_std, _scan_bits(model, torch.from_numpy(d.G / 3.0).cuda()))
     del m2
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# affine-integer genotype columns (standardised / centred dosages): int8 route on the integer part, mapped back
+# ------------------------------------------------------------------------------------------------------------------
+def _int8_launches(fn):
+    from cellregmap_b200 import _cellregmap as api
+    api.PROFILE.update(on=True, rot_ms=0.0, rot_flops=0.0, rot_launches=0, int8_ms=0.0, int8_ops=0.0, int8_launches=0)
+    try:
+        out = fn()
+    finally:
+        api.PROFILE["on"] = False
+    return out, api.PROFILE["int8_launches"]
+
+
+@pytest.mark.parametrize("transform", ["standardised", "centred", "halved", "constant column"])
+def test_affine_genotypes_take_the_int8_route(cuda_device, monkeypatch, transform):
+    """g = a d + b per column (the reference's simulator passes column_normalize(G), _simulate.py:50-54,339): same results as the
+    float64 tensor-core route and as the oracle, through the int8 contraction."""
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    from oracle import crm_port
+    d = make_data(n=900, donors=60, k=6, p=70, q=5, seed=31)
+    G = d.G.copy()
+    if transform == "standardised":
+        G = (G - G.mean(0)) / G.std(0)
+    elif transform == "centred":
+        G = G - G.mean(0)
+    elif transform == "halved":
+        G = G / 2.0 + 0.25
+    else:
+        G = (G - G.mean(0)) / G.std(0)
+        G[:, 7] = 0.731            # monomorphic after the map: d = 0 everywhere
+    G = np.ascontiguousarray(G)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    for Gin in (torch.from_numpy(G).cuda(), G):            # device-resident, and pageable host memory (feeder gives up, float64 blocks)
+        if transform == "constant column":
+            with pytest.raises(RuntimeError, match="No eigenvalue"):        # monomorphic SNP: g.E0 spans nothing (reference: chiscore raises)
+                model.scan_interaction(Gin)
+            continue
+        (pv, info), launches = _int8_launches(lambda: model.scan_interaction(Gin))
+        assert launches > 0, "the affine columns did not take the int8 contraction"
+        monkeypatch.setenv("CRM_AFFINE", "0")
+        (pv64, info64), launches64 = _int8_launches(lambda: model.scan_interaction(Gin))
+        monkeypatch.delenv("CRM_AFFINE")
+        assert launches64 == 0
+        np.testing.assert_array_equal(info["rho1"], info64["rho1"])
+        assert np.max(np.abs(np.log10(pv) - np.log10(pv64))) <= 1e-5
+        for key in ("e2", "g2", "eps2"):
+            np.testing.assert_allclose(info[key], info64[key], rtol=5e-6, atol=1e-12)
+    if transform != "constant column":
+        ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, G, W=d.W, hK=d.hK)
+        np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+        assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= DLOG10_P
+        np.testing.assert_array_equal(np.argsort(pv, kind="stable"), np.argsort(ref_pv, kind="stable"))
+
+
+def test_affine_detection_rejects_real_valued_columns(cuda_device):
+    """One entry off the lattice (or imputed real-valued dosages) sends the block to the float64 route: bits of CRM_AFFINE=0."""
+    import os
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    d = make_data(n=600, donors=50, k=5, p=40, q=4, seed=32)
+    G = (d.G - d.G.mean(0)) / d.G.std(0)
+    G[123, 17] += 1e-9
+    Gi = d.G + np.random.default_rng(0).uniform(-0.2, 0.2, d.G.shape)       # imputed-like dosages
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    for Gx in (G, Gi):
+        Gd = torch.from_numpy(np.ascontiguousarray(Gx)).cuda()
+        (pv, _), launches = _int8_launches(lambda: model.scan_interaction(Gd))
+        assert launches == 0
+        os.environ["CRM_AFFINE"] = "0"
+        try:
+            pv0, _ = model.scan_interaction(Gd)
+        finally:
+            del os.environ["CRM_AFFINE"]
+        np.testing.assert_array_equal(pv, pv0)
