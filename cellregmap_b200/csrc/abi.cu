@@ -532,7 +532,8 @@ static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStre
         if (flags[2] != 0) { set_error("There are non-finite values in the genotype matrix (SNP columns %lld..%lld).", blk.s0, blk.s0 + B - 1); return CRM_ERR_NONFINITE; }
         if (flags[0] != 0) {
             // not integer dosages: every column an affine image a d + b of small integers (standardised / centred dosages)?
-            static const bool affine_on = [] { const char* v = getenv("CRM_AFFINE"); return !(v && atoi(v) == 0); }();
+            const char* aff_env = getenv("CRM_AFFINE");          // CRM_AFFINE=0: float64 route for every non-integer block (tests, A/B)
+            const bool affine_on = !(aff_env && atoi(aff_env) == 0);
             if (!affine_on || !blk.G) return CRM_OK;
             const long long lda = round_up(B, 2);
             CRM_CHECK(h->aff.reserve((size_t)3 * lda * 8));
@@ -1182,7 +1183,9 @@ static int for_each_block(Handle* h, const GSource& src, const GSource* src2, lo
             CRM_CUDA(cudaEventRecord(h->ev_done[1], st));
             for (long long ib = 0; ib < nb && status == CRM_OK; ib++) {
                 int bad = 0, gmax = 0;
+                const double t_wait = host_ms();
                 feeder_wait_block(*job, ib, &bad, &gmax);
+                if (trace_on()) fprintf(stderr, "[crm trace] host %.1f ms: feeder block %lld of %lld ready after waiting %.1f ms (bad=%d, max |g|=%d)\n", host_ms(), ib, nb, host_ms() - t_wait, bad, gmax);
                 if (bad) break;                                                      // not integer dosages: the rest goes over as float64
                 const int dslot = (int)(ib & 1);
                 const long long s0 = job->starts[ib], bw = job->starts[ib + 1] - s0;

@@ -113,7 +113,7 @@ __attribute__((target("avx2"))) static void narrow_row_f64_avx2(const double* s,
 static NarrowFlags narrow_f64(const double* src, long long ld, long long r0, long long r1, long long c0, long long b, int8_t* dst, long long ldd) {
     NarrowFlags f{0, 0};
 #if defined(__x86_64__)
-    static const bool avx2 = __builtin_cpu_supports("avx2");
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !(getenv("CRM_NARROW_SCALAR") && atoi(getenv("CRM_NARROW_SCALAR")) != 0);
     if (avx2) {
         for (long long i = r0; i < r1; i++) narrow_row_f64_avx2(src + i * ld + c0, dst + i * ldd, b, f.bad, f.gmax);
         return f;
