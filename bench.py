@@ -227,7 +227,7 @@ def default_cpu_sample(a):
     """SNPs for roughly 10-30 s of CPU work on a 16-core host (measured per-SNP costs of the reference path)."""
     if a.cpu_sample_snps > 0:
         return min(a.cpu_sample_snps, a.snps)
-    per_config = {1: 100, 2: 60, 3: 8, 4: 16, 5: 1}
+    per_config = {1: 100, 2: 400, 3: 40, 4: 100, 5: 2}
     return max(1, min(per_config[a.config], a.snps))
 
 
@@ -396,6 +396,9 @@ def run_b200_arm(a):
         """`at_least` untimed steps, then more (untimed, bounded) until three consecutive steps agree within 5 %: the first models of a
         process grow the library's memory pool and the cuBLAS/cuSOLVER workspaces, which takes a varying number of steps to settle."""
         recent = []
+        if os.environ.get("CRM_BENCH_FIXED_WARMUP") == "1":     # profiler runs: exactly the requested number of steps
+            at_most_extra = 0
+        i = -1
         for i in range(at_least + at_most_extra):
             torch.cuda.synchronize(); t0 = time.time()
             fn()

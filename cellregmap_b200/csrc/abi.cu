@@ -496,21 +496,39 @@ static int ensure_column_sums(Handle* h, cudaStream_t st) {
     return CRM_OK;
 }
 
+// room for the digit planes of [Hx | Hx.E0_j]?  (cudaMemGetInfo costs milliseconds: only asked for large requests); extra = further
+// bytes the caller needs next to them
+static int planes_fit(Handle* h, double extra, bool* fits) {
+    const long long Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(h->n, 16);
+    const size_t a8_bytes = (size_t)OZAKI_SLICES * Mp * Kp;
+    *fits = true;
+    if (h->oz_built || h->A8.cap >= a8_bytes) return CRM_OK;
+    static size_t total_mem[16] = {0};
+    if (!total_mem[h->device]) { size_t f = 0; CRM_CUDA(cudaMemGetInfo(&f, &total_mem[h->device])); }
+    const double need = (double)a8_bytes + extra;
+    if (need > 0.2 * (double)total_mem[h->device]) {
+        size_t free_b = 0, total_b = 0;
+        CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += pool_cached_bytes(h->device);
+        if (need > 0.5 * (double)free_b) *fits = false;
+    }
+    return CRM_OK;
+}
+// exponents + digit planes of [Hx | Hx.E0_j] on stream `on` (buffers reserved by the caller's stream order)
+static int build_planes(Handle* h, cudaStream_t on) {
+    const long long n = h->n, Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(n, 16);
+    CRM_CHECK(oz_launch_exponents(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, n, h->a8expo.as<int>(), on));
+    return oz_launch_slices(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, 0, h->kexp, n, h->a8expo.as<int>(), h->A8.as<int8_t>(), Mp, Kp, on);
+}
 static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStream_t st, int* used) {
     *used = 0;
     const long long B = blk.b;
     const long long n = h->n, Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
     const size_t a8_bytes = (size_t)OZAKI_SLICES * Mp * Kp;
-    if (!h->oz_built && h->A8.cap < a8_bytes) {      // room for the digit planes?  (cudaMemGetInfo costs milliseconds: only asked for large requests)
-        static size_t total_mem[16] = {0};
-        if (!total_mem[h->device]) { size_t f = 0; CRM_CUDA(cudaMemGetInfo(&f, &total_mem[h->device])); }
-        const double need = (double)a8_bytes + (int8_route_library() ? (double)OZAKI_SLICES * Mp * Bp * 4.0 : 0.0);
-        if (need > 0.2 * (double)total_mem[h->device]) {
-            size_t free_b = 0, total_b = 0;
-            CRM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            free_b += pool_cached_bytes(h->device);
-            if (need > 0.5 * (double)free_b) return CRM_OK;
-        }
+    {
+        bool fits = true;
+        CRM_CHECK(planes_fit(h, int8_route_library() ? (double)OZAKI_SLICES * Mp * Bp * 4.0 : 0.0, &fits));
+        if (!fits) return CRM_OK;
     }
     PhaseTrace tr(st);
     h->oz_block_valid = false;
@@ -551,8 +569,7 @@ static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStre
     if (!h->oz_built) {
         if (h->A8.reserve(a8_bytes) != CRM_OK) return CRM_OK;      // no room after all: the fp64 route takes over
         CRM_CHECK(h->a8expo.reserve((size_t)Mtot * sizeof(int)));
-        CRM_CHECK(oz_launch_exponents(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, n, h->a8expo.as<int>(), st));
-        CRM_CHECK(oz_launch_slices(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, 0, h->kexp, n, h->a8expo.as<int>(), h->A8.as<int8_t>(), Mp, Kp, st));
+        CRM_CHECK(build_planes(h, st));
         h->oz_built = true;
         tr.mark("digit planes");
     }
@@ -715,6 +732,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     if (k1 + mL > 30000) { set_error("background half-covariance has %lld columns; limit is 30000", (long long)(k1 + mL)); return CRM_ERR_UNSUPPORTED; }
     h->ready = false;
     h->donors_set = false;
+    h->oz_built = false; h->oz_built_a2 = false;
     h->n = n; h->c = c; h->k0 = k0; h->k1 = k1; h->mL = mL; h->R = R;
     h->m = (int)(k1 + mL);
     h->mp = (int)round_up(h->m, 2);

@@ -47,6 +47,12 @@ __global__ void oz_column_exponent_kernel(const double* Hx, int ldH, const doubl
 
 constexpr int OZ_ROWS = 128;               // cells per block of the slicing kernel (4 per thread -> char4 stores)
 
+// Shared-memory tile of OZ_ROWS cells x OZ_TILE columns used to turn row-major reads (lanes along columns) into K-major writes (each
+// thread 4 consecutive cells of one column).  Row r of the tile is stored at slot (r % 4) * 32 + r / 4: the four cells 4 tx + u of
+// lane tx then sit 32 slots apart and a warp's read of one u touches 32 consecutive slots of one column -- with a pitch of 33 doubles
+// that is conflict-free, where the identity mapping is an 8-way bank conflict (ncu: 429 M conflicts per launch, profiles/r02_ncu_oz_slice_kernel.txt).
+__device__ __forceinline__ int oz_tile_slot(int r) { return ((r & 3) << 5) | (r >> 2); }
+
 // digit planes, K-major: A8[t][col][i] (plane stride = Mp * Kp, row stride = Kp, Kp a multiple of 4)
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* Hx, int ldH, const double* Eext, int epitch, int j0, int nj, long long n, const int* expo,
                                                        int8_t* A8, long long Mp, long long Kp) {
@@ -54,11 +60,19 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* Hx, int ldH
     const long long i0 = (long long)blockIdx.x * OZ_ROWS;
     const int a0 = blockIdx.y * OZ_TILE;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    // this thread's 16 entries of the Hx tile stay in registers for all context blocks j (the basis is read once, not 1 + k times)
+    double hx[OZ_ROWS / 8];
+#pragma unroll
+    for (int q = 0; q < OZ_ROWS / 8; q++) {
+        const long long i = i0 + ty + 8 * q; const int a = a0 + tx;
+        hx[q] = (i < n && a < ldH) ? Hx[i * ldH + a] : 0.0;
+    }
     for (int jj = 0; jj < nj; jj++) {
         const int j = j0 + jj;
-        for (int r = ty; r < OZ_ROWS; r += 8) {                   // read: rows i, columns a (coalesced along a)
-            const long long i = i0 + r; const int a = a0 + tx;
-            tile[r][tx] = (i < n && a < ldH) ? Eext[i * epitch + j] * Hx[i * ldH + a] : 0.0;
+#pragma unroll
+        for (int q = 0; q < OZ_ROWS / 8; q++) {                   // rows i, columns a (coalesced along a); Eext[i][j] is a warp-wide broadcast
+            const int r = ty + 8 * q; const long long i = i0 + r;
+            tile[oz_tile_slot(r)][tx] = (i < n) ? Eext[i * epitch + j] * hx[q] : 0.0;
         }
         __syncthreads();
         for (int r = ty; r < OZ_TILE; r += 8) {                   // write: rows a, 4 consecutive cells per thread
@@ -69,7 +83,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* Hx, int ldH
                 const double scale = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(1.0, -(e + 1));     // exact power of two
                 double x[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) x[u] = tile[4 * tx + u][r] * scale;               // |x| < 1/2
+                for (int u = 0; u < 4; u++) x[u] = tile[(u << 5) | tx][r] * scale;           // cell 4 tx + u; |x| < 1/2
 #pragma unroll
                 for (int t = 0; t < OZ_SLICES; t++) {
                     char4 q;
@@ -101,7 +115,7 @@ __global__ void __launch_bounds__(256) oz_matrix_slice_kernel(const double* X, l
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int r = ty; r < OZ_ROWS; r += 8) {
         const long long i = i0 + r; const int a = a0 + tx;
-        tile[r][tx] = (i < n && a < cols) ? X[i * ldx + a] : 0.0;
+        tile[oz_tile_slot(r)][tx] = (i < n && a < cols) ? X[i * ldx + a] : 0.0;
     }
     __syncthreads();
     for (int r = ty; r < OZ_TILE; r += 8) {
@@ -111,7 +125,7 @@ __global__ void __launch_bounds__(256) oz_matrix_slice_kernel(const double* X, l
             const double scale = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(1.0, -(e + 1));
             double x[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) x[u] = tile[4 * tx + u][r] * scale;
+            for (int u = 0; u < 4; u++) x[u] = tile[(u << 5) | tx][r] * scale;
 #pragma unroll
             for (int t = 0; t < OZ_SLICES; t++) {
                 char4 q;
@@ -144,7 +158,7 @@ __global__ void __launch_bounds__(256) oz_genotype_kernel(const double* G, long 
             v = G[i * ldg + s];
             if (!(v == rint(v)) || fabs(v) > 127.0) { bad = 1; if (!isfinite(v)) bad = 3; } else gmax = max(gmax, (int)fabs(v));
         }
-        tile[r][tx] = v;
+        tile[oz_tile_slot(r)][tx] = v;
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
 #pragma unroll
@@ -158,7 +172,7 @@ __global__ void __launch_bounds__(256) oz_genotype_kernel(const double* G, long 
             signed char* a = reinterpret_cast<signed char*>(&q);
             signed char* b = reinterpret_cast<signed char*>(&q2);
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const int gv = (int)tile[4 * tx + u][r]; a[u] = (signed char)gv; b[u] = (signed char)(gv * gv); }
+            for (int u = 0; u < 4; u++) { const int gv = (int)tile[(u << 5) | tx][r]; a[u] = (signed char)gv; b[u] = (signed char)(gv * gv); }
             *reinterpret_cast<char4*>(Gt8 + s * Kp + i) = q;
             if (G2t8) *reinterpret_cast<char4*>(G2t8 + s * Kp + i) = q2;
         }
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(256) oz_affine_genotype_kernel(const double* G
             d = rint((v - b) / a);
             if (!(fabs(v - fma(a, d, b)) <= tol) || !(d >= 0.0 && d <= 127.0)) { bad = 1; d = 0.0; } else gmax = max(gmax, (int)d);
         }
-        tile[r][tx] = d;
+        tile[oz_tile_slot(r)][tx] = d;
     }
     bad = __any_sync(0xffffffffu, bad);
 #pragma unroll
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(256) oz_affine_genotype_kernel(const double* G
             signed char* qa = reinterpret_cast<signed char*>(&q);
             signed char* qb = reinterpret_cast<signed char*>(&q2);
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const int gv = (int)tile[4 * tx + u][r]; qa[u] = (signed char)gv; qb[u] = (signed char)(gv * gv); }
+            for (int u = 0; u < 4; u++) { const int gv = (int)tile[(u << 5) | tx][r]; qa[u] = (signed char)gv; qb[u] = (signed char)(gv * gv); }
             *reinterpret_cast<char4*>(Gt8 + s * Kp + i) = q;
             if (G2t8) *reinterpret_cast<char4*>(G2t8 + s * Kp + i) = q2;
         }

@@ -249,4 +249,192 @@ __global__ void __launch_bounds__(SCORE_THREADS) crm_score_kernel(const ScoreArg
     if (lane == 0) { a.Q[s] = qs; a.nlam[s] = nl; a.flags[s] = (pcnt == 0 || nl == 0) ? 1 : 0; }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Warp-per-SNP version of the kernel above for NZ <= 8 NB columns (NB = 3 covers one covariate + 20 contexts): the weighted Gram
+// runs on the FP64 tensor cores (mma.sync m8n8k4: lane (g, t) feeds row 4 s + t of the columns 8 b + g of Z, the NB (NB + 1) / 2
+// lower block pairs accumulate in registers), the small algebra and both Jacobi eigensolvers stay inside the warp.  The CTA-per-SNP
+// kernel spends most of its life with one warp in the 20 x 20 Jacobi while seven have exited (ncu: 17 % of the warp slots active,
+// FP64 pipe 7 %, profiles/r02_ncu_score_fit.txt); here every warp of a CTA owns a SNP from start to end.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int SCOREW_WARPS = 4;
+constexpr int SCOREW_WCHUNK = 128;       // rows whose weights are staged per pass
+
+__host__ __device__ inline size_t scorew_warp_doubles(int NZ, int P, int k) {
+    return (size_t)NZ * NZ + SCOREW_WCHUNK + (size_t)k * k + 2 * (size_t)P * (1 + k) + 2 * (size_t)k + 2 * (size_t)P * P + 2;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(SCOREW_WARPS * 32) crm_score_warp_kernel(const ScoreArgs a) {
+    extern __shared__ __align__(16) double ssm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pos = blockIdx.x * SCOREW_WARPS + warp;
+    if (pos >= a.p) return;
+    const int s = a.perm[pos];
+    const int rho = a.rho_idx[s];
+    const int P = a.c + 1, C = a.c;
+    const int k = a.k, NZ = 1 + P + k, mp = a.mp, m = a.m;
+    const double v0 = a.v0[s], v1 = a.v1[s];
+    double* G = ssm + (size_t)warp * scorew_warp_doubles(NZ, P, k);
+    double* wch = G + NZ * NZ;
+    double* Mm = wch + SCOREW_WCHUNK;
+    double* sol = Mm + k * k;
+    double* tv = sol + P * (1 + k);
+    double* Aw = tv + 2 * k;
+    double* Vw = Aw + P * P;
+    double* yw = Vw + P * P;
+    const double* S = a.S + (long long)rho * mp;
+    const double* yr = a.yr + (long long)rho * mp;
+    const double* Wr = a.Wr + (long long)rho * C * mp;
+    const double* gr = a.gr + (long long)s * a.gr_ld + (long long)rho * mp;
+    const double* GEr = a.GEr + (long long)pos * k * mp;
+
+    // ---- 1. rotated weighted Gram  RG = sum_i w_i Zr_i Zr_i'  on the tensor cores ----
+    const int g = lane >> 2, t = lane & 3;
+    const double* colp[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int col = 8 * b + g;
+        colp[b] = (col == 0) ? yr : (col <= C) ? Wr + (long long)(col - 1) * mp : (col == P) ? gr : (col < NZ) ? GEr + (long long)(col - 1 - P) * mp : nullptr;
+    }
+    double acc[NB * (NB + 1) / 2][2];
+#pragma unroll
+    for (int e = 0; e < NB * (NB + 1) / 2; e++) { acc[e][0] = 0.0; acc[e][1] = 0.0; }
+    for (int i0 = 0; i0 < m; i0 += SCOREW_WCHUNK) {
+        for (int ii = lane; ii < SCOREW_WCHUNK; ii += 32) {
+            const int i = i0 + ii;
+            double w = 0.0;
+            if (i < m) { const double vs = v0 * S[i]; w = vs / (vs + v1); }
+            wch[ii] = w;
+        }
+        __syncwarp();
+        const int steps = min(SCOREW_WCHUNK, m - i0 + 3) / 4;
+#pragma unroll 4
+        for (int st = 0; st < steps; st++) {
+            const int i = i0 + 4 * st + t;
+            const bool ok = i < m;
+            const double w = wch[4 * st + t];
+            double z[NB], wz[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) { z[b] = (ok && colp[b]) ? colp[b][i] : 0.0; wz[b] = w * z[b]; }
+            int e = 0;
+#pragma unroll
+            for (int bi = 0; bi < NB; bi++)
+#pragma unroll
+                for (int bj = 0; bj <= bi; bj++, e++) dmma884(acc[e][0], acc[e][1], wz[bi], z[bj]);
+        }
+        __syncwarp();
+    }
+    {
+        int e = 0;
+#pragma unroll
+        for (int bi = 0; bi < NB; bi++)
+#pragma unroll
+            for (int bj = 0; bj <= bi; bj++, e++) {
+                const int r = 8 * bi + g, c0 = 8 * bj + 2 * t;
+                if (r < NZ) {
+                    if (c0 < NZ) { G[r * NZ + c0] = acc[e][0]; G[c0 * NZ + r] = acc[e][0]; }
+                    if (c0 + 1 < NZ) { G[r * NZ + c0 + 1] = acc[e][1]; G[(c0 + 1) * NZ + r] = acc[e][1]; }
+                }
+            }
+    }
+    __syncwarp();
+    // ---- 2. K0^-1 Gram: (Z'Z - RG) / v1 ----
+    const double* row0 = a.rot + (long long)s * a.kexp * a.rot_ld;   // row of g
+    const double* sq = a.sq + (long long)s * a.sq_ld;
+    const int npairs = NZ * (NZ + 1) / 2;
+    for (int e = lane; e < npairs; e += 32) {
+        int ia = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (ia * (ia + 1) / 2 > e) ia--;
+        while ((ia + 1) * (ia + 2) / 2 <= e) ia++;
+        const int ib = e - ia * (ia + 1) / 2;      // ia >= ib ; columns: 0 = y, 1..C = W, P = g, P+1.. = GE_j
+        double zz;
+        if (ia == 0) zz = a.stats[0];
+        else if (ia <= C) zz = (ib == 0) ? a.stats[ia] : a.stats[1 + C + (ia - 1) * C + (ib - 1)];
+        else if (ia == P) zz = (ib == 0) ? row0[a.col_y] : (ib <= C ? row0[a.col_W + ib - 1] : sq[0]);
+        else {
+            const int j = ia - P - 1;
+            const double* rowj = row0 + (long long)(1 + j) * a.rot_ld;
+            if (ib == 0) zz = rowj[a.col_y];
+            else if (ib <= C) zz = rowj[a.col_W + ib - 1];
+            else if (ib == P) zz = sq[1 + j];
+            else zz = sq[1 + k + pair_index(j, ib - P - 1)];
+        }
+        const double v = (zz - G[ia * NZ + ib]) / v1;
+        G[ia * NZ + ib] = v; G[ib * NZ + ia] = v;
+    }
+    __syncwarp();
+    // ---- 3. A^+ [X'Ky | X'K GE]: pseudo-inverse of the P x P block (Jacobi, lstsq(rcond=None) cut-off, reference _math.py:33-37) ----
+    for (int e = lane; e < P * P; e += 32) { const int i = e / P, j = e - i * P; Aw[e] = G[(1 + i) * NZ + (1 + j)]; }
+    __syncwarp();
+    warp_jacobi_vec(Aw, Vw, P, lane);
+    {
+        double lmax = 0.0;
+        for (int r = 0; r < P; r++) lmax = fmax(lmax, fabs(Aw[r * P + r]));
+        const double cut = CRM_EPS_TINY * P * lmax;
+        for (int e = lane; e < P * (1 + k); e += 32) {
+            const int r = e / (1 + k), j = e - r * (1 + k);
+            const int col = (j == 0) ? 0 : P + j;
+            const double l = Aw[r * P + r];
+            double v = 0.0;
+            if (fabs(l) > cut && fabs(l) > 0.0) {
+                for (int tt = 0; tt < P; tt++) v += Vw[tt * P + r] * G[(1 + tt) * NZ + col];
+                v /= l;
+            }
+            yw[e] = v;
+        }
+        __syncwarp();
+        for (int e = lane; e < P * (1 + k); e += 32) {
+            const int i = e / (1 + k), j = e - i * (1 + k);
+            double v = 0.0;
+            for (int r = 0; r < P; r++) v += Vw[i * P + r] * yw[r * (1 + k) + j];
+            sol[e] = v;
+        }
+    }
+    __syncwarp();
+    for (int j = lane; j < k; j += 32) {
+        double tj = G[(P + 1 + j) * NZ + 0];
+        for (int i = 0; i < P; i++) tj -= G[(P + 1 + j) * NZ + (1 + i)] * sol[i * (1 + k) + 0];
+        tv[j] = tj;
+    }
+    for (int e = lane; e < k * k; e += 32) {
+        const int j = e / k, l = e - j * k;
+        double v = G[(P + 1 + j) * NZ + (P + 1 + l)];
+        for (int i = 0; i < P; i++) v -= G[(P + 1 + j) * NZ + (1 + i)] * sol[i * (1 + k) + 1 + l];
+        Mm[e] = 0.5 * v;
+    }
+    __syncwarp();
+    for (int e = lane; e < k * k; e += 32) {   // symmetrise away the round-off asymmetry
+        const int j = e / k, l = e - j * k;
+        if (j < l) { const double v = 0.5 * (Mm[j * k + l] + Mm[l * k + j]); Mm[j * k + l] = v; Mm[l * k + j] = v; }
+    }
+    __syncwarp();
+    if (a.Mout) for (int e = lane; e < k * k; e += 32) a.Mout[(long long)s * k * k + e] = Mm[e];
+    // ---- 4. Q, eigenvalues of M by cyclic Jacobi, filter ----
+    double qs = 0.0;
+    for (int j = lane; j < k; j += 32) qs += tv[j] * tv[j];
+    qs = 0.5 * warp_sum(qs);
+    __syncwarp();
+    warp_jacobi_vec(Mm, nullptr, k, lane);
+    for (int j = lane; j < k; j += 32) {
+        const double lj = Mm[j * k + j];
+        int rank = 0;
+        for (int l = 0; l < k; l++) { const double ll = Mm[l * k + l]; if (ll > lj || (ll == lj && l < j)) rank++; }
+        sol[rank] = lj;
+    }
+    __syncwarp();
+    double psum = 0.0; int pcnt = 0;
+    for (int j = lane; j < k; j += 32) { if (sol[j] >= 0.0) { psum += sol[j]; pcnt++; } }
+    psum = warp_sum(psum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pcnt += __shfl_xor_sync(0xffffffffu, pcnt, o);
+    int nl = 0;
+    if (pcnt > 0) {
+        const double thr = (psum / pcnt) / 100000.0;
+        for (int j = 0; j < k; j++) if (sol[j] > thr) nl++;
+    }
+    for (int j = lane; j < k; j += 32) a.lam[(long long)s * a.lam_ld + j] = sol[j];
+    if (lane == 0) { a.Q[s] = qs; a.nlam[s] = nl; a.flags[s] = (pcnt == 0 || nl == 0) ? 1 : 0; }
+}
+
 }  // namespace crm

@@ -446,9 +446,10 @@ def test_int8_split_rotation_matches_fp64_rotation(cuda_device, monkeypatch):
     ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, d.G[:, :40], W=d.W, hK=d.hK)
     np.testing.assert_array_equal(out_i["rho1"][:40].cpu().numpy(), ref_info["rho1"])
     assert np.max(np.abs(np.log10(out_i["pv"][:40].cpu().numpy()) - np.log10(ref_pv))) <= DLOG10_P
-    # auto mode: non-integer genotypes silently use the fp64 route and agree with it
+    # auto mode: real-valued genotypes (imputed-like dosages: neither integers nor an affine image of integers) silently use the
+    # fp64 route and agree with it
     monkeypatch.delenv("CRM_ROTATION")
-    Gf = d.G + 0.25
+    Gf = d.G + np.random.default_rng(3).uniform(-0.2, 0.2, d.G.shape)
     m_a = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
     pv_a, _ = m_a.scan_interaction(Gf)
     pv_f, _ = m_d.scan_interaction(Gf)
