@@ -1012,22 +1012,15 @@ static int stage_host_block(Handle* h, const double* G, long long ldg, const dou
     return CRM_OK;
 }
 
-// Column blocks of the feeder: a whole number of 256-SNP tiles of the int8 contraction, chosen so that (SNP tiles x basis tiles) fills
-// the 148 SMs in whole waves (basis_cols = columns of the expanded basis, 0 when unknown); a short matrix is one block.
+// Column blocks of the feeder: equal blocks of whole 256-SNP tiles of the int8 contraction, at most 3072 columns each.  Narrow enough
+// that the first block is converted while the set-up runs (25 ms for 100k x 2560 float64 on 16 threads), wide enough that the
+// per-block costs of the scan (launch chain, host synchronisation for the rho groups, the small g^2 contraction) stay a few per cent;
+// measured at bench size: 1792 -> 243 ms, 2560 -> 225 ms, 5120 -> 257 ms per call (profiles/e2e_blocks_ab.py).
 static long long feeder_block_cols(long long p, long long basis_cols) {
+    (void)basis_cols;
     if (const char* env = getenv("CRM_FEEDER_BLOCK")) { if (atoll(env) > 0) return std::min<long long>(p, atoll(env)); }     // tests: many small blocks
-    long long best_t = 8;
-    if (basis_cols > 0) {
-        const long long mt = (basis_cols + 127) / 128;
-        double best = -1.0;
-        for (long long t = 6; t <= 16; t++) {
-            const long long tiles = t * mt, waves = (tiles + 147) / 148;
-            const double eff = (double)tiles / (double)(waves * 148);
-            if (eff > best + 0.004) { best = eff; best_t = t; }
-        }
-    }
-    const long long block = 256 * best_t;
-    return (p <= block + block / 4) ? p : block;
+    const long long nblocks = (p + 3071) / 3072;
+    return std::min(p, round_up((p + nblocks - 1) / nblocks, 256));
 }
 
 static void drop_feed(Handle* h) {
