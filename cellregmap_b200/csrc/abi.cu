@@ -1012,14 +1012,17 @@ static int stage_host_block(Handle* h, const double* G, long long ldg, const dou
     return CRM_OK;
 }
 
-// Column blocks of the feeder: equal blocks of whole 256-SNP tiles of the int8 contraction, at most 3072 columns each.  Narrow enough
+// Column blocks of the feeder: equal blocks of whole 256-SNP tiles of the int8 contraction, at most 3072 columns each (2560 with 16 threads).  Narrow enough
 // that the first block is converted while the set-up runs (25 ms for 100k x 2560 float64 on 16 threads), wide enough that the
 // per-block costs of the scan (launch chain, host synchronisation for the rho groups, the small g^2 contraction) stay a few per cent;
 // measured at bench size: 1792 -> 243 ms, 2560 -> 225 ms, 5120 -> 257 ms per call (profiles/e2e_blocks_ab.py).
 static long long feeder_block_cols(long long p, long long basis_cols) {
     (void)basis_cols;
     if (const char* env = getenv("CRM_FEEDER_BLOCK")) { if (atoll(env) > 0) return std::min<long long>(p, atoll(env)); }     // tests: many small blocks
-    const long long nblocks = (p + 3071) / 3072;
+    // few host threads (several ranks sharing the cores of a box): narrower blocks, so that a block is converted in ~25 ms whatever the
+    // thread count (5 GB/s of float64 per thread) and the scan of block i hides the conversion of block i + 1
+    const long long cap = std::min<long long>(3072, std::max<long long>(512, round_up(160LL * host_threads(), 256)));
+    const long long nblocks = (p + cap - 1) / cap;
     return std::min(p, round_up((p + nblocks - 1) / nblocks, 256));
 }
 
