@@ -780,9 +780,9 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     op.A = Hx; op.lda = ldH; op.a_cols = Mx;
     op.B = Hx; op.ldb = ldH; op.b_cols = Mx;
     op.B2 = Hx; op.ldb2 = ldH; op.b2_cols = Mx;
-    gemm_set_free_split(true);
+    gemm_set_free_split(true); gemm_set_symmetric(true);
     const int gram_status = launch_gemm(GEMM_PLAIN, op, (int)n, 0, Mx, 0, Mx, h->gram.as<double>(), ldH, 1, st);
-    gemm_set_free_split(false);
+    gemm_set_free_split(false); gemm_set_symmetric(false);
     CRM_CHECK(gram_status);
     extract_stats_kernel<<<1, 1024, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();

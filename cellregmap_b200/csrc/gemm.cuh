@@ -46,6 +46,8 @@ struct GemmArgs {
     int k_chunk;            //      its partial tile to partial + z * partial_stride (packed, ld = m_count), summed afterwards
     double* partial;
     long long partial_stride;
+    int sym;                // 1: A and B are the same matrix (Gram): only tiles with m_tile >= n_tile are computed (k_splits > 1 only; the
+                            //    reduction mirrors them)
 };
 constexpr int GEMM_RASTER_N = 8;
 
@@ -68,7 +70,13 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // Rasterisation: consecutive block indices walk GEMM_RASTER_N n-tiles for one m-tile, then the next m-tile, so the
     // ~148 CTAs in flight share each A panel among up to 8 of them and each B panel among ~18 (L2 reuse both ways).
     int m_tile, n_tile;
-    {
+    if (args.sym) {         // lower triangle of the tile grid, row by row
+        const int L = blockIdx.x;
+        int r = (int)((sqrtf(8.0f * (float)L + 1.0f) - 1.0f) * 0.5f);
+        while (r * (r + 1) / 2 > L) r--;
+        while ((r + 1) * (r + 2) / 2 <= L) r++;
+        m_tile = r; n_tile = L - r * (r + 1) / 2;
+    } else {
         const int L = blockIdx.x, per_group = GEMM_RASTER_N * args.m_tiles;
         const int group = L / per_group, within = L - group * per_group;
         const int gn = min(GEMM_RASTER_N, args.n_tiles - group * GEMM_RASTER_N);
@@ -193,13 +201,16 @@ crm_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
-// out[n][m] = sum over the K chunks of partial[z][n][m], in chunk order (deterministic)
-__global__ void crm_gemm_reduce_kernel(const double* partial, long long stride, int splits, int n_count, int m_count, double* out, long long ldc) {
+// out[n][m] = sum over the K chunks of partial[z][n][m], in chunk order (deterministic); sym: entries of tiles above the diagonal of
+// the tile grid are taken from their mirror image (only the lower tiles were computed)
+__global__ void crm_gemm_reduce_kernel(const double* partial, long long stride, int splits, int n_count, int m_count, double* out, long long ldc, int sym) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)n_count * m_count) return;
     const long long n = idx / m_count; const int m = (int)(idx - n * m_count);
+    long long src = idx;
+    if (sym && (m / GEMM_BM) < (int)(n / GEMM_BN)) src = (long long)m * m_count + n;
     double s = 0.0;
-    for (int z = 0; z < splits; z++) s += partial[(long long)z * stride + idx];
+    for (int z = 0; z < splits; z++) s += partial[(long long)z * stride + src];
     out[n * ldc + m] = s;
 }
 

@@ -66,8 +66,9 @@ static int gemm_mt_choice() {
     return mt;
 }
 
-static thread_local bool g_free_split = false;
+static thread_local bool g_free_split = false, g_symmetric = false;
 void gemm_set_free_split(bool on) { g_free_split = on; }
+void gemm_set_symmetric(bool on) { g_symmetric = on; }
 
 template <int MODE, int MT>
 int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream) {
@@ -104,7 +105,10 @@ int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream)
     args.m_tiles = (m_span + GEMM_BM - 1) / GEMM_BM;
     args.n_tiles = (n_span + GEMM_BN - 1) / GEMM_BN;
     if (args.m_tiles == 0 || args.n_tiles == 0) return CRM_OK;
-    const long long ctas = (long long)args.m_tiles * args.n_tiles;
+    // Gram of one matrix with itself (set-up): the tiles above the diagonal are mirror images
+    const bool sym = g_symmetric && g_free_split && MODE == GEMM_PLAIN && op.A == op.B && op.lda == op.ldb && args.m_begin == 0 && args.n_begin == 0 &&
+                     args.m_count == args.n_count && args.m_tiles == args.n_tiles && args.m_tiles > 1 && GEMM_BM == GEMM_BN;
+    const long long ctas = sym ? (long long)args.m_tiles * (args.m_tiles + 1) / 2 : (long long)args.m_tiles * args.n_tiles;
     if (ctas > 2000000000LL) { set_error("GEMM of %d x %d tiles is too large for one launch", args.m_tiles, args.n_tiles); return CRM_ERR_UNSUPPORTED; }
     // Narrow outputs over a long contraction leave most SMs idle: cut K into chunks (partials summed in chunk order).
     // The chunking depends only on (m_tiles, K) -- never on the number of SNP columns -- so that a SNP's arithmetic is the
@@ -116,7 +120,7 @@ int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream)
         int splits = 1;
         if (g_free_split && ctas < 2 * 148) {
             double best = 0.0;
-            for (int z = 1; z <= max_splits; z++) {     // wave efficiency of ctas * z blocks on 148 SMs
+            for (int z = sym ? 2 : 1; z <= max_splits; z++) {     // wave efficiency of ctas * z blocks on 148 SMs (sym needs the reduction pass)
                 const long long blocks = ctas * z, waves = (blocks + 147) / 148;
                 const double eff = (double)blocks / (double)(waves * 148);
                 if (eff > best + 1e-9) { best = eff; splits = z; }
@@ -132,13 +136,14 @@ int launch_gemm_mode(const GemmOperands& op, GemmArgs args, cudaStream_t stream)
             if (splits > 1) CRM_CUDA(pool_alloc_async((void**)&args.partial, (size_t)splits * args.partial_stride * sizeof(double), stream));
         }
     }
-    dim3 grid((unsigned)ctas, (unsigned)args.k_splits, 1);
+    args.sym = (sym && args.k_splits > 1) ? 1 : 0;
+    dim3 grid((unsigned)(args.sym ? ctas : (long long)args.m_tiles * args.n_tiles), (unsigned)args.k_splits, 1);
     crm_gemm_kernel<MODE, MT><<<grid, gemm_threads(MT), smem, stream>>>(tmA, tmB, tmB2, args);
     CRM_CUDA(cudaGetLastError()); count_launch();
     if (args.k_splits > 1) {
         const long long total = (long long)args.n_count * args.m_count;
         crm_gemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(args.partial, args.partial_stride, args.k_splits, args.n_count, args.m_count,
-                                                                                 args.out, args.ldc);
+                                                                                 args.out, args.ldc, args.sym);
         CRM_CUDA(cudaGetLastError()); count_launch();
         CRM_CUDA(cudaFreeAsync(args.partial, stream));
     }

@@ -85,6 +85,28 @@ int oz_launch_mma(const int8_t* A8, long long Mp, long long Mtot, const int* exp
         return CRM_OK;
     }
     const long long units = (long long)a.m_tiles * a.n_tiles;
+    // Few tiles over a long contraction (the g^2 Grams: 2 column tiles): one CTA per tile would walk all of K alone (2 ms whatever
+    // the batch width) -> cut K into chunks, one unit per (tile, chunk), integer partial sums added in global memory.
+    static const bool splitk_on = [] { const char* v = getenv("CRM_OZ_SPLITK"); return !(v && atoi(v) == 0); }();
+    if (splitk_on && units * 2 <= sms && a.kblocks >= 32) {
+        static bool attr3 = false;
+        if (!attr3) { CRM_CUDA(cudaFuncSetAttribute(oz_mma_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZM_SMEM_BYTES)); attr3 = true; }
+        int ks = (int)std::min<long long>(sms / units, a.kblocks / 16);
+        a.kchunk = (a.kblocks + ks - 1) / ks;
+        ks = (a.kblocks + a.kchunk - 1) / a.kchunk;
+        a.ksplit = ks;
+        a.Bp32 = B;
+        const size_t bytes = (size_t)OZ_SLICES * (size_t)B * (size_t)Mp * sizeof(int);
+        CRM_CUDA(pool_alloc_async((void**)&a.D32, bytes, st));
+        CRM_CUDA(cudaMemsetAsync(a.D32, 0, bytes, st));
+        const unsigned gridk = (unsigned)std::min<long long>(units * ks, sms);
+        oz_mma_splitk_kernel<<<gridk, OZM_THREADS, OZM_SMEM_BYTES, st>>>(tmA, tmB, a);
+        CRM_CUDA(cudaGetLastError()); count_launch();
+        oz_combine_planes_kernel<<<dim3((unsigned)((Mtot + 127) / 128), (unsigned)std::min<long long>(B, 65535)), 128, 0, st>>>(a.D32, a.Bp32, Mp, expo, Mtot, B, C, ldc);
+        CRM_CUDA(cudaGetLastError()); count_launch();
+        CRM_CUDA(cudaFreeAsync(a.D32, st));
+        return CRM_OK;
+    }
     const unsigned grid = (unsigned)std::min<long long>(units, sms);
     oz_mma_kernel<<<grid, OZM_THREADS, OZM_SMEM_BYTES, st>>>(tmA, tmB, a);
     CRM_CUDA(cudaGetLastError()); count_launch();

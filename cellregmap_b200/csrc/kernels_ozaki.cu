@@ -94,12 +94,12 @@ int oz_launch_affine_genotypes(const double* G, long long ldg, long long n, long
     return CRM_OK;
 }
 int oz_launch_affine_fix(double* C, long long ldc, long long B, long long cols, const double* aff, long long lda, const double* colsum, cudaStream_t st) {
-    oz_affine_fix_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)B), 256, 0, st>>>(C, ldc, B, cols, aff, lda, colsum);
+    oz_affine_fix_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)std::min<long long>(B, 65535)), 256, 0, st>>>(C, ldc, B, cols, aff, lda, colsum);
     CRM_CUDA(cudaGetLastError()); count_launch();
     return CRM_OK;
 }
 int oz_launch_affine_fix_square(double* sq, const double* lin, long long ld, long long B, int cols, const double* aff, long long lda, const double* colsum2, cudaStream_t st) {
-    oz_affine_fix_square_kernel<<<dim3((unsigned)((cols + 127) / 128), (unsigned)B), 128, 0, st>>>(sq, lin, ld, B, cols, aff, lda, colsum2);
+    oz_affine_fix_square_kernel<<<dim3((unsigned)((cols + 127) / 128), (unsigned)std::min<long long>(B, 65535)), 128, 0, st>>>(sq, lin, ld, B, cols, aff, lda, colsum2);
     CRM_CUDA(cudaGetLastError()); count_launch();
     return CRM_OK;
 }

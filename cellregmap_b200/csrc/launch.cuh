@@ -28,6 +28,8 @@ int measure_fp64_tensor_peak(double* tflops, cudaStream_t stream);
 
 // next launch_gemm calls on this thread may choose the K split by grid size (operands without a SNP dimension)
 void gemm_set_free_split(bool on);
+// with free split: next launch_gemm calls on this thread whose two operands are the same matrix compute only the lower tile triangle
+void gemm_set_symmetric(bool on);
 
 int launch_fit_with_g(const FitArgs& fa, cudaStream_t st);   // design [W g], P = c + 1 in 1..8
 int launch_fit_null(const FitArgs& fa, cudaStream_t st);     // design W,     P = c     in 1..7

@@ -37,6 +37,10 @@ struct OzMmaArgs {
     int kblocks, m_tiles, n_tiles, ngroup;
     const int* expo;
     double* C;
+    // split-K variant (few tiles, long contraction): unit = (tile, K chunk); the int32 partial sums of every plane are added into
+    // D32[plane][s][col] (exact: integer addition commutes) and recombined by oz_combine_planes_kernel
+    int ksplit, kchunk;     // chunks per tile, K blocks per chunk
+    int* D32; long long Bp32;
 };
 
 // ---- tcgen05 wrappers (PTX ISA: tcgen05.alloc / mma / commit / ld / fence) ----
@@ -111,7 +115,8 @@ __device__ __forceinline__ OzTile oz_unit_tile(const OzMmaArgs& a, int u) {
     return t;
 }
 
-__global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzMmaArgs a) {
+template <bool SPLITK>
+__device__ __forceinline__ void oz_mma_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const OzMmaArgs& a) {
     extern __shared__ uint8_t oz_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OZM_STAGES * OZM_STAGE_BYTES);
@@ -121,7 +126,8 @@ __global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_con
     uint64_t* tmem_empty = tmem_full + 1;          // epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int units = a.m_tiles * a.n_tiles;
+    const int ks = SPLITK ? a.ksplit : 1;
+    const int units = a.m_tiles * a.n_tiles * ks;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
@@ -140,10 +146,11 @@ __global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_con
         if (lane == 0) {                            // ===== TMA producer =====
             uint32_t it = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const OzTile t = oz_unit_tile(a, u);
+                const OzTile t = oz_unit_tile(a, u / ks);
+                const int kb0 = SPLITK ? (u % ks) * a.kchunk : 0, kb1 = SPLITK ? min(a.kblocks, kb0 + a.kchunk) : a.kblocks;
                 for (int pass = 0; pass < 4; pass++) {
                     const int row1 = (int)((long long)(7 - 2 * pass) * a.Mp) + t.m0, row2 = (int)((long long)(6 - 2 * pass) * a.Mp) + t.m0;
-                    for (int kb = 0; kb < a.kblocks; kb++, it++) {
+                    for (int kb = kb0; kb < kb1; kb++, it++) {
                         const uint32_t s = it % OZM_STAGES, ph = (it / OZM_STAGES) & 1u;
                         mbar_wait_backoff(&empty[s], ph ^ 1u);
                         uint8_t* st = smem + s * OZM_STAGE_BYTES;
@@ -159,12 +166,13 @@ __global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_con
         if (lane == 0) {                            // ===== MMA issue =====
             uint32_t it = 0, acc_it = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const OzTile t = oz_unit_tile(a, u);
+                const OzTile t = oz_unit_tile(a, u / ks);
+                const int kb0 = SPLITK ? (u % ks) * a.kchunk : 0, kb1 = SPLITK ? min(a.kblocks, kb0 + a.kchunk) : a.kblocks;
                 const uint32_t idesc = oz_instr_desc(OZM_BM, t.ncols);
                 for (int pass = 0; pass < 4; pass++, acc_it++) {
                     mbar_wait(tmem_empty, (acc_it & 1u) ^ 1u);
                     tc_fence_after();
-                    for (int kb = 0; kb < a.kblocks; kb++, it++) {
+                    for (int kb = kb0; kb < kb1; kb++, it++) {
                         const uint32_t s = it % OZM_STAGES, ph = (it / OZM_STAGES) & 1u;
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_con
 #pragma unroll
                         for (int k4 = 0; k4 < OZM_BK / OZM_UK; k4++) {
                             const uint64_t adv = (uint64_t)(k4 * OZM_UK >> 4);       // start-address field advances in 16-byte units
-                            const uint32_t acc = (kb | k4) != 0;
+                            const uint32_t acc = ((kb - kb0) | k4) != 0;
                             tc_mma_i8(tmem_base, d1 + adv, db + adv, idesc, acc);
                             tc_mma_i8(tmem_base + OZM_BN, d2 + adv, db + adv, idesc, acc);
                         }
@@ -187,10 +195,10 @@ __global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_con
         const int q = warp & 3;
         uint32_t acc_it = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const OzTile t = oz_unit_tile(a, u);
+            const OzTile t = oz_unit_tile(a, u / ks);
             const long long col = (long long)t.m0 + 32 * q + lane;
             const bool col_ok = col < a.Mtot;
-            const int e = col_ok ? a.expo[col] : OZ_EXP_EMPTY;
+            const int e = (col_ok && !SPLITK) ? a.expo[col] : OZ_EXP_EMPTY;
             for (int pass = 0; pass < 4; pass++, acc_it++) {
                 mbar_wait(tmem_full, acc_it & 1u);
                 tc_fence_after();
@@ -202,7 +210,16 @@ __global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_con
                     tc_ld32(tlane + ch * 32, hi);
                     tc_ld32(tlane + OZM_BN + ch * 32, lo);
                     tc_wait_ld();
-                    if (col_ok) {
+                    if (SPLITK) {
+                        if (col_ok) {        // lanes = consecutive columns: coalesced integer reductions into D32[plane][s][col]
+                            int* dhi = a.D32 + ((long long)(7 - 2 * pass) * a.Bp32 + s_first) * a.Mp + col;
+                            int* dlo = a.D32 + ((long long)(6 - 2 * pass) * a.Bp32 + s_first) * a.Mp + col;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (s_first + j < a.B) { atomicAdd(dhi + (long long)j * a.Mp, (int)hi[j]); atomicAdd(dlo + (long long)j * a.Mp, (int)lo[j]); }
+                            }
+                        }
+                    } else if (col_ok) {
                         double* cp = a.C + s_first * a.ldc + col;
                         double acc[32];
 #pragma unroll
@@ -224,6 +241,26 @@ __global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tc_dealloc(tmem_base, 512);
+}
+
+__global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzMmaArgs a) {
+    oz_mma_body<false>(tmA, tmB, a);
+}
+// few output tiles over a long contraction (the g^2 Grams: 232 columns): the K range is cut into chunks, one unit per (tile, chunk)
+__global__ void __launch_bounds__(OZM_THREADS, 1) oz_mma_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzMmaArgs a) {
+    oz_mma_body<true>(tmA, tmB, a);
+}
+// C[s][col] = 2^(e_col + 1) sum_t 2^(-7 (t + 1)) D32[t][s][col]: the Horner order of the fused epilogue, so the result is bit-identical
+__global__ void oz_combine_planes_kernel(const int* D32, long long Bp32, long long Mp, const int* expo, long long Mtot, long long B, double* C, long long ldc) {
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= Mtot) return;
+    const int e = expo[col];
+    for (long long s = blockIdx.y; s < B; s += gridDim.y) {
+        double acc = 0.0;
+#pragma unroll
+        for (int t = OZ_SLICES - 1; t >= 0; t--) acc = (acc + (double)D32[((long long)t * Bp32 + s) * Mp + col]) * 0.0078125;
+        C[s * ldc + col] = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(acc, e + 1);
+    }
 }
 
 

@@ -340,18 +340,20 @@ __global__ void __launch_bounds__(256) oz_affine_genotype_kernel(const double* G
 // C[s][col] <- a_s C[s][col] + b_s colsum[col]      (rotation of g = a d + b from the rotation of d)
 __global__ void oz_affine_fix_kernel(double* C, long long ldc, long long B, long long cols, const double* aff, long long lda, const double* colsum) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long s = blockIdx.y;
-    if (col >= cols || s >= B) return;
-    const double a = aff[s], b = aff[lda + s];
-    C[s * ldc + col] = fma(a, C[s * ldc + col], b * colsum[col]);
+    if (col >= cols) return;
+    for (long long s = blockIdx.y; s < B; s += gridDim.y) {
+        const double a = aff[s], b = aff[lda + s];
+        C[s * ldc + col] = fma(a, C[s * ldc + col], b * colsum[col]);
+    }
 }
 // sq[s][c] <- a^2 sq[s][c] + 2 a b lin[s][c] + b^2 colsum2[c]      (Grams of g^2 from those of d^2 and d)
 __global__ void oz_affine_fix_square_kernel(double* sq, const double* lin, long long ld, long long B, int cols, const double* aff, long long lda, const double* colsum2) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const long long s = blockIdx.y;
-    if (c >= cols || s >= B) return;
-    const double a = aff[s], b = aff[lda + s];
-    sq[s * ld + c] = a * a * sq[s * ld + c] + 2.0 * a * b * lin[s * ld + c] + b * b * colsum2[c];
+    if (c >= cols) return;
+    for (long long s = blockIdx.y; s < B; s += gridDim.y) {
+        const double a = aff[s], b = aff[lda + s];
+        sq[s * ld + c] = a * a * sq[s * ld + c] + 2.0 * a * b * lin[s * ld + c] + b * b * colsum2[c];
+    }
 }
 
 // C[s][col] = 2^(e_col + 1) sum_t 2^(-7 (t + 1)) D[t * Mp + col][s]   (D int32, row stride ldd; C fp64, row stride ldc)
