@@ -178,14 +178,36 @@ struct Handle {
     std::shared_ptr<FeedJob> feed;
     const void* feed_src = nullptr; long long feed_ld = 0, feed_p = 0, feed_rows = 0; int feed_dtype = 0;
     DevBuf g8dev[2], gwide, gwide2;
-    void free_all() {
+    // buffers of a model object recycled from an earlier one (crm_destroy keeps them, see BufCache): work on them is ordered after this event
+    cudaEvent_t adopt_ev = nullptr;
+    template <class F> void for_each_buf(F&& fn) {
         DevBuf* all[] = {&A8, &a8expo, &Gt8, &G2t8, &D32, &ozflags, &A28, &a28expo, &HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
                          &gtchunk[0], &gtchunk[1], &gstage, &g8dev[0], &g8dev[1], &gwide, &gwide2, &aff, &affscratch, &colsum, &colsum2, &sq1, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
-        for (DevBuf* b : all) b->release();
+        for (DevBuf* b : all) fn(*b);
     }
+    void free_all() { for_each_buf([](DevBuf& b) { b.release(); }); }
 };
+
+// Device buffers of destroyed model objects, kept for the next crm_create on the same device.  A scan of many genes creates and drops one
+// model per gene; handing the (grow-only) buffers over instead of returning them to the memory pool means that a model of the same shape
+// allocates nothing at all -- pool allocations of the large operands (17 GB of digit planes) were measured to take 0.1-2.5 s every few
+// steps when the pool had split its blocks for smaller requests (profiles/r02_step_trace.txt).  At most two sets per device are kept;
+// crm_trim_pool releases them.
+struct BufCache { std::vector<DevBuf> bufs; cudaEvent_t ev = nullptr; };
+static std::mutex g_cache_mu;
+static std::vector<BufCache> g_cache[32];
+static const size_t BUF_CACHE_DEPTH = 2;
+
+// first use of recycled buffers on the stream of this call: order it after the last work of their previous owner
+static int adopt_buffers(Handle* h, cudaStream_t st) {
+    if (!h->adopt_ev) return CRM_OK;
+    CRM_CUDA(cudaStreamWaitEvent(st, h->adopt_ev, 0));
+    cudaEventDestroy(h->adopt_ev);
+    h->adopt_ev = nullptr;
+    return CRM_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // small set-up kernels
@@ -1665,6 +1687,16 @@ int crm_create(crm_handle_t* out, int device) {
     if (prop.major != 10) { set_error("libcrm_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor); return CRM_ERR_UNSUPPORTED; }
     crm_handle_s* h = new crm_handle_s();
     h->impl.device = device;
+    if (device < 32) {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        if (!g_cache[device].empty()) {
+            BufCache c = std::move(g_cache[device].back());
+            g_cache[device].pop_back();
+            size_t i = 0;
+            h->impl.for_each_buf([&](DevBuf& b) { if (i < c.bufs.size()) b = c.bufs[i]; i++; });
+            h->impl.adopt_ev = c.ev;
+        }
+    }
     *out = h;
     return CRM_OK;
 }
@@ -1684,7 +1716,23 @@ int crm_destroy(crm_handle_t h) {
     }
     {
         AllocScope alloc_scope(st);
-        h->impl.free_all();
+        if (h->impl.adopt_ev) { cudaStreamWaitEvent(st, h->impl.adopt_ev, 0); cudaEventDestroy(h->impl.adopt_ev); h->impl.adopt_ev = nullptr; }
+        static const bool recycle = [] { const char* v = getenv("CRM_NO_RECYCLE"); return !(v && atoi(v) != 0); }();
+        bool kept = false;
+        if (recycle && h->impl.device < 32) {
+            BufCache c;
+            if (cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming) == cudaSuccess && cudaEventRecord(c.ev, st) == cudaSuccess) {
+                std::lock_guard<std::mutex> lock(g_cache_mu);
+                if (g_cache[h->impl.device].size() < BUF_CACHE_DEPTH) {
+                    h->impl.for_each_buf([&](DevBuf& b) { c.bufs.push_back(b); b.ptr = nullptr; b.cap = 0; });
+                    g_cache[h->impl.device].push_back(std::move(c));
+                    kept = true;
+                }
+            }
+            if (!kept && c.ev) cudaEventDestroy(c.ev);
+            cudaGetLastError();
+        }
+        if (!kept) h->impl.free_all();
     }
     if (h->impl.copy_stream) {
         cudaStreamDestroy(h->impl.copy_stream);     // asynchronous: resources are released once the stream has drained
@@ -1700,6 +1748,17 @@ int crm_destroy(crm_handle_t h) {
 int crm_trim_pool(int device) {
     cudaMemPool_t pool = device_pool(device);
     if (!pool) { set_error("crm_trim_pool: no allocation pool for device %d", device); return CRM_ERR_INVALID; }
+    std::vector<BufCache> cached;
+    if (device >= 0 && device < 32) { std::lock_guard<std::mutex> lock(g_cache_mu); cached.swap(g_cache[device]); }
+    if (!cached.empty()) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        CRM_CUDA(cudaSetDevice(device));
+        CRM_CUDA(cudaDeviceSynchronize());
+        for (BufCache& c : cached) { for (DevBuf& b : c.bufs) b.release(); if (c.ev) cudaEventDestroy(c.ev); }
+        CRM_CUDA(cudaDeviceSynchronize());
+        cudaSetDevice(prev);
+    }
     CRM_CUDA(cudaMemPoolTrimTo(pool, 0));
     release_pinned_slots();
     return CRM_OK;
@@ -1711,6 +1770,7 @@ int crm_setup(crm_handle_t h, const double* y, const double* W, int64_t ldw, con
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     return do_setup(&h->impl, y, W, ldw, E0, lde0, E1, lde1, L, ldl, n, c, k0, k1, mL, rho_host, R, 0, 1, (cudaStream_t)stream);
 }
 
@@ -1720,6 +1780,7 @@ int crm_setup_partial(crm_handle_t h, const double* y, const double* W, int64_t 
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     return do_setup(&h->impl, y, W, ldw, E0, lde0, E1, lde1, L, ldl, n, c, k0, k1, mL, rho_host, R, r_first, r_step, (cudaStream_t)stream);
 }
 
@@ -1752,6 +1813,7 @@ int crm_setup_finish(crm_handle_t h, void* stream) {
     if (!h || h->impl.m <= 0) { set_error("crm_setup_finish: crm_setup_partial has not run"); return CRM_ERR_STATE; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     return finish_setup(&h->impl, (cudaStream_t)stream);
 }
 
@@ -1763,6 +1825,7 @@ int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dtype, int
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     return do_stage_genotypes(&h->impl, G_host, dtype, ldg, rows, p, basis_cols_hint, (cudaStream_t)stream);
 }
 
@@ -1786,6 +1849,7 @@ int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* 
     if (!h || !h->impl.ready || !E0) { set_error("crm_set_test_contexts: handle not set up"); return CRM_ERR_STATE; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     return build_test_contexts(&h->impl, E0, lde0, (cudaStream_t)stream);
 }
 
@@ -1815,6 +1879,7 @@ int crm_update_phenotype(crm_handle_t h, const double* y, void* stream) {
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     return do_update_phenotype(&h->impl, y, (cudaStream_t)stream);
 }
 
@@ -1825,6 +1890,7 @@ int crm_set_donors(crm_handle_t h, const int32_t* perm, const int32_t* offsets, 
     CRM_CUDA(cudaSetDevice(H.device));
     cudaStream_t st = (cudaStream_t)stream;
     AllocScope alloc_scope(st); H.last_stream = st;
+    CRM_CHECK(adopt_buffers(&H, st));
     CRM_CHECK(H.dperm.reserve((size_t)H.n * 4));
     CRM_CHECK(H.doff.reserve((size_t)(d + 1) * 4));
     CRM_CUDA(cudaMemcpyAsync(H.dperm.ptr, perm, (size_t)H.n * 4, cudaMemcpyDeviceToDevice, st));
@@ -1871,6 +1937,7 @@ int crm_scan_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_t p
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     const GSource src{G, ldg, (g_on_host >> 4) & 15, g_on_host & 1}, tested{Gtest, ldgt, (g_on_host >> 4) & 15, g_on_host & 1};
     return do_scan_interaction(&h->impl, (g_on_host >> 1) & 1, src, p, Gtest ? &tested : nullptr, out_pv, out_rho1, out_e2, out_g2, out_eps2, diag, (cudaStream_t)stream);
 }
@@ -1880,6 +1947,7 @@ int crm_scan_association(crm_handle_t h, const double* G, int64_t ldg, int64_t p
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     const GSource src{G, ldg, (g_on_host >> 4) & 15, g_on_host & 1};
     return do_scan_association(&h->impl, (g_on_host >> 1) & 1, src, p, fast, out_pv, out_alt_lml, info4, out_null_lml, (cudaStream_t)stream);
 }
@@ -1889,6 +1957,7 @@ int crm_predict_interaction(crm_handle_t h, const double* G, int64_t ldg, int64_
     if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(h->impl.device));
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
+    CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     const GSource src{G, ldg, (g_on_host >> 4) & 15, g_on_host & 1};
     return do_predict(&h->impl, (g_on_host >> 1) & 1, src, p, maf, use_background, out_beta_g, out_beta_gxe, ldo, out_rho1, (cudaStream_t)stream);
 }
