@@ -771,6 +771,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     h->rho.assign(rho_host, rho_host + R);
     const int m = h->m, mp = h->mp, Mx = h->Mx, ldH = h->ldH;
 
+    SlowSection* sec = new SlowSection("set-up: reserve");
     CRM_CHECK(h->Hx.reserve((size_t)n * ldH * 8));
     CRM_CHECK(h->Eext.reserve((size_t)n * h->epitch * 8));
     CRM_CHECK(h->A2.reserve((size_t)n * h->ld2 * 8));
@@ -782,9 +783,11 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     CRM_CHECK(h->stats.reserve((size_t)(1 + c + c * c + R + 4) * 8));
     CRM_CHECK(h->devinfo.reserve((size_t)(2 * R + 8) * sizeof(int)));
 
+    delete sec;
     PhaseTrace tr(st);
     // Hx = [E1 | L | y | W]
     double* Hx = h->Hx.as<double>();
+    sec = new SlowSection("set-up: operand copies + test contexts");
     CRM_CUDA(cudaMemsetAsync(Hx, 0, (size_t)n * ldH * 8, st));
     CRM_CUDA(cudaMemcpy2DAsync(Hx, (size_t)ldH * 8, E1, (size_t)lde1 * 8, (size_t)k1 * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
     if (mL > 0) CRM_CUDA(cudaMemcpy2DAsync(Hx + k1, (size_t)ldH * 8, L, (size_t)ldl * 8, (size_t)mL * 8, (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -796,6 +799,8 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         h->rotation_mode = (rm && !strcmp(rm, "dmma")) ? 1 : (rm && !strcmp(rm, "int8")) ? 2 : 0;
     }
     CRM_CHECK(build_test_contexts(h, E0, lde0, st));
+    delete sec;
+    sec = new SlowSection("set-up: gram launch");
 
     // Gram of [H | y | W] by the K1 kernel (plain mode): H'H, H'y, H'W, y'y, W'y, W'W
     GemmOperands op{};
@@ -808,6 +813,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     CRM_CHECK(gram_status);
     extract_stats_kernel<<<1, 1024, 0, st>>>(h->gram.as<double>(), ldH, m, c, h->stats.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
+    delete sec;
     tr.mark("operands+gram");
 
     // per-rho eigendecomposition (cuSOLVER, one-off per gene) with one pooled cuSOLVER context per device.  Measured on
@@ -1678,13 +1684,26 @@ const char* crm_last_error(void) { return g_err; }
 
 int crm_create(crm_handle_t* out, int device) {
     if (!out) { set_error("crm_create: null output"); return CRM_ERR_INVALID; }
-    int count = 0;
-    CRM_CUDA(cudaGetDeviceCount(&count));
+    // one model object per gene: nothing here may be slow.  cudaGetDeviceProperties is (milliseconds, with stalls of 0.1-0.3 s every few
+    // calls, profiles/r02_step_trace.txt): the two attributes that matter are read once per device
+    static int count = -1;
+    static int cc_major[64], cc_minor[64];
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (count < 0) {
+            int c = 0;
+            CRM_CUDA(cudaGetDeviceCount(&c));
+            for (int d = 0; d < c && d < 64; d++) {
+                CRM_CUDA(cudaDeviceGetAttribute(&cc_major[d], cudaDevAttrComputeCapabilityMajor, d));
+                CRM_CUDA(cudaDeviceGetAttribute(&cc_minor[d], cudaDevAttrComputeCapabilityMinor, d));
+            }
+            count = std::min(c, 64);
+        }
+    }
     if (device < 0 || device >= count) { set_error("crm_create: device %d not available (%d visible)", device, count); return CRM_ERR_INVALID; }
     CRM_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CRM_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) { set_error("libcrm_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor); return CRM_ERR_UNSUPPORTED; }
+    if (cc_major[device] != 10) { set_error("libcrm_b200 is built for sm_100a only; device %d is sm_%d%d", device, cc_major[device], cc_minor[device]); return CRM_ERR_UNSUPPORTED; }
     crm_handle_s* h = new crm_handle_s();
     h->impl.device = device;
     if (device < 32) {

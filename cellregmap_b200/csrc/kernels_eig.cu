@@ -132,6 +132,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
         for (int b = 0; b < batch; b++) sa.n_of[b] = sz.n_of[b];
         sa.A = A; sa.nmax = n; sa.batch = batch; sa.d = d; sa.e = e; sa.tau = tau; sa.xbuf = xbuf; sa.pbuf = pbuf; sa.part = part; sa.bar = bar;
         void* params[] = {&sa};
+        SlowSection sec("eig: cooperative launch of sytrd");
         CRM_CUDA(cudaLaunchCooperativeKernel((const void*)crm_sytrd_kernel, dim3((unsigned)(batch * sa.group)), dim3(SY_THREADS), params, (size_t)5 * (n + 1) * 8, st));
         count_launch();
     }
@@ -161,6 +162,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
         for (int b = 0; b < batch; b++) {
             if (!todo[b]) continue;
             const int nb = sz.n_of[b];
+            SlowSection sec1("eig: one cublasDsyrk");
             CRM_BLAS(cublasDsyrk(blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, nb, nb, &one, V + (size_t)b * nn, nb, &zero, G + (size_t)b * nn, nb));
         }
         eig_gram_error_kernel<<<dim3(64, (unsigned)batch), 256, 0, st>>>(G, sz, (unsigned long long*)emax);
@@ -182,6 +184,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
             eig_first_order_rinv_kernel<<<64, 256, 0, st>>>(Gb, nb);
             CRM_CUDA(cudaGetLastError()); count_launch();
             double* tmp = work + (size_t)b * 5 * nn;         // out of place into the free inverse-iteration workspace, then back
+            SlowSection sec2("eig: one cublasDtrmm");
             CRM_BLAS(cublasDtrmm(blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, nb, nb, &one, Gb, nb, Z, nb, tmp, nb));
             CRM_CUDA(cudaMemcpyAsync(Z, tmp, (size_t)nb * nb * 8, cudaMemcpyDeviceToDevice, st));
             if (emax_h[b] < 1e-8) todo[b] = 0;               // error after the step ~ E^2 < 1e-16
@@ -196,6 +199,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
     CRM_SOLVER_(cusolverDnSetStream(solver, st));
     for (int b = 0; b < batch; b++) {
         const int nb = sz.n_of[b];
+        SlowSection sec3("eig: one cusolverDnDormtr");
         CRM_SOLVER_(cusolverDnDormtr(solver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, nb, nb, A + (size_t)b * nn, nb, tau + (size_t)b * n, V + (size_t)b * nn, nb,
                                      lib_work, lib_lwork, info_dev + batch + b));
     }

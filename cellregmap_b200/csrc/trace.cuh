@@ -35,4 +35,15 @@ struct PhaseTrace {
 };
 
 
+// CRM_TRACE=1: reports a host-side section that took longer than `limit_ms` (where does an occasional long step lose its time?)
+struct SlowSection {
+    const char* name; double t0, limit;
+    explicit SlowSection(const char* n, double limit_ms = 3.0) : name(n), t0(trace_on() ? host_ms() : 0.0), limit(limit_ms) {}
+    ~SlowSection() {
+        if (!trace_on()) return;
+        const double dt = host_ms() - t0;
+        if (dt > limit) fprintf(stderr, "[crm trace] host %.1f ms: SLOW host section '%s' took %.1f ms\n", host_ms(), name, dt);
+    }
+};
+
 }  // namespace crm
