@@ -331,10 +331,12 @@ __global__ void __launch_bounds__(SCOREW_WARPS * 32) crm_score_warp_kernel(const
         for (int bi = 0; bi < NB; bi++)
 #pragma unroll
             for (int bj = 0; bj <= bi; bj++, e++) {
+                // lower triangle only (row >= column), mirrored: in a diagonal block the entry (c, r) is also some other lane's (r', c'),
+                // computed with the roles of the two factors swapped -- one writer per location keeps the result deterministic
                 const int r = 8 * bi + g, c0 = 8 * bj + 2 * t;
                 if (r < NZ) {
-                    if (c0 < NZ) { G[r * NZ + c0] = acc[e][0]; G[c0 * NZ + r] = acc[e][0]; }
-                    if (c0 + 1 < NZ) { G[r * NZ + c0 + 1] = acc[e][1]; G[(c0 + 1) * NZ + r] = acc[e][1]; }
+                    if (c0 <= r) { G[r * NZ + c0] = acc[e][0]; G[c0 * NZ + r] = acc[e][0]; }
+                    if (c0 + 1 <= r) { G[r * NZ + c0 + 1] = acc[e][1]; G[(c0 + 1) * NZ + r] = acc[e][1]; }
                 }
             }
     }

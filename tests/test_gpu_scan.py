@@ -639,3 +639,32 @@ def test_affine_detection_rejects_real_valued_columns(cuda_device):
         finally:
             del os.environ["CRM_AFFINE"]
         np.testing.assert_array_equal(pv, pv0)
+
+
+def test_buffers_recycled_across_models_shapes_and_streams(cuda_device):
+    """crm_destroy hands a model's device buffers to the next crm_create (no allocator traffic in a per-gene loop): models of different
+    shapes, created and dropped on different streams, interleaved with a live one, give the results of fresh processes' models; crm_trim_pool
+    returns the kept memory."""
+    import torch
+    from cellregmap_b200 import _lib, run_interaction
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    cases = [make_data(n=500, donors=40, k=5, p=60, q=4, seed=71), make_data(n=900, donors=50, k=7, p=33, q=6, seed=72),
+             make_data(n=300, donors=30, k=3, p=90, q=2, seed=73)]
+    first = [run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK) for d in cases]          # sizes grow and shrink: buffers are grow-only
+    keep = _make_interaction_model(cases[0].y, cases[0].E, cases[0].W, None, None, cases[0].hK)      # a live model next to the recycled ones
+    side = torch.cuda.Stream()
+    for rnd in range(3):
+        for d, (pv0, info0) in zip(cases, first):
+            if rnd == 1:
+                with torch.cuda.stream(side):
+                    pv, info = run_interaction(d.y, d.E, torch.from_numpy(d.G).cuda(), W=d.W, hK=d.hK)
+                side.synchronize()
+            else:
+                pv, info = run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+            np.testing.assert_array_equal(pv, pv0)
+            np.testing.assert_array_equal(info["eps2"], info0["eps2"])
+        pv_k, _ = keep.scan_interaction(cases[0].G)
+        np.testing.assert_array_equal(pv_k, first[0][0])
+    _lib.call("crm_trim_pool", torch.cuda.current_device())
+    pv, _ = run_interaction(cases[1].y, cases[1].E, cases[1].G, W=cases[1].W, hK=cases[1].hK)
+    np.testing.assert_array_equal(pv, first[1][0])
