@@ -108,7 +108,12 @@ class _Genotypes:
             self.ptr, self.ld = G.data_ptr(), (G.stride(0) if G.shape[0] > 1 else G.shape[1])
             self.dtype = 1 if G.dtype == torch.int8 else 0
         else:
-            arr = G.detach().numpy() if isinstance(G, torch.Tensor) else np.asarray(G)
+            if isinstance(G, torch.Tensor):
+                if G.dtype in (torch.bfloat16, torch.float16) or G.is_complex():      # no numpy view / not a storage the feeder converts
+                    G = G.to(torch.float64)
+                arr = G.detach().numpy()
+            else:
+                arr = np.asarray(G)
             assert arr.ndim == 2, "G must be n x p"
             if arr.dtype not in _G_DTYPES or force_float64:
                 arr = np.asarray(arr, dtype=np.float64)

@@ -668,3 +668,53 @@ def test_buffers_recycled_across_models_shapes_and_streams(cuda_device):
     _lib.call("crm_trim_pool", torch.cuda.current_device())
     pv, _ = run_interaction(cases[1].y, cases[1].E, cases[1].G, W=cases[1].W, hK=cases[1].hK)
     np.testing.assert_array_equal(pv, first[1][0])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# edge shapes: empty, single, odd and ragged inputs
+# ------------------------------------------------------------------------------------------------------------------
+def test_empty_genotype_matrix(cuda_device):
+    """No SNP columns: the reference's loops run zero times and return empty arrays (association: the null model's info)."""
+    import torch
+    from cellregmap_b200 import estimate_betas, run_association, run_interaction
+    d = make_data(n=200, donors=20, k=3, p=4, q=2, seed=81)
+    for G0 in (np.zeros((200, 0)), torch.zeros((200, 0), dtype=torch.float64, device="cuda"), np.zeros((200, 0), dtype=np.int8)):
+        pv, info = run_interaction(d.y, d.E, G0, W=d.W, hK=d.hK)
+        assert pv.shape == (0,) and all(info[k].shape == (0,) for k in ("rho1", "e2", "g2", "eps2"))
+    pa, ia = run_association(d.y, d.W, d.E, np.zeros((200, 0)), hK=d.hK)
+    assert pa.shape == (0,) and ia["rho1"].shape == (1,)
+    bg, bx = estimate_betas(d.y, d.W, d.E, np.zeros((200, 0)), maf=np.zeros(0), hK=d.hK)
+    assert bg.shape == (0,) and bx.shape == (1, 200, 0)
+
+
+@pytest.mark.parametrize("n,k,q,p,c", [(301, 1, 1, 1, 1), (257, 2, 3, 129, 2), (64, 3, 2, 5, 1), (1025, 5, 1, 17, 1)])
+def test_odd_and_ragged_shapes(cuda_device, n, k, q, p, c):
+    """Odd numbers of cells / columns (TMA alignment, padded tiles), one context, one SNP: same results as the oracle, device and host genotypes."""
+    import torch
+    from cellregmap_b200 import run_association, run_interaction
+    from oracle import crm_port
+    d = make_data(n=n, donors=max(8, n // 12), k=k, p=p, q=q, seed=n + p, n_covariates=c, causal_persistent=(0,), causal_gxc=(0,))
+    ref_pv, ref_info = crm_port.run_interaction(d.y, d.E, d.G, W=d.W, hK=d.hK)
+    for G in (d.G, torch.from_numpy(d.G).cuda(), d.G.astype(np.int8)):
+        pv, info = run_interaction(d.y, d.E, G, W=d.W, hK=d.hK)
+        np.testing.assert_array_equal(info["rho1"], ref_info["rho1"])
+        assert np.max(np.abs(np.log10(pv) - np.log10(ref_pv))) <= DLOG10_P
+    ref_pa, _ = crm_port.run_association(d.y, d.W, d.E, d.G, hK=d.hK)
+    pa, _ = run_association(d.y, d.W, d.E, d.G, hK=d.hK)
+    big = ref_pa >= 1e-12
+    assert np.max(np.abs(np.log10(pa[big]) - np.log10(ref_pa[big]))) <= DLOG10_P
+
+
+def test_all_zero_tested_design_raises_like_chiscore(cuda_device):
+    """A SNP whose tested design g.E0 is identically zero has no positive eigenvalue: chiscore.davies_pvalue raises
+    RuntimeError("No eigenvalue is bigger than 0!!") inside the reference's loop; same exception here and in the oracle."""
+    from cellregmap_b200 import run_interaction
+    from oracle import crm_port
+    d = make_data(n=300, donors=30, k=4, p=12, q=3, seed=91)
+    G = d.G.copy()
+    G[:, 5] = 0.0
+    with pytest.raises(RuntimeError, match="No eigenvalue is bigger than 0"):
+        crm_port.run_interaction(d.y, d.E, G, W=d.W, hK=d.hK)
+    for Gin in (G, G.astype(np.int8)):
+        with pytest.raises(RuntimeError, match="No eigenvalue is bigger than 0"):
+            run_interaction(d.y, d.E, Gin, W=d.W, hK=d.hK)
