@@ -110,6 +110,22 @@ def test_config4_association_sample(cuda_device):
     assert np.max(np.abs(np.log10(pv[sample]) - np.log10(ref_pv))) <= DLOG10_P
 
 
+def test_config5_betas_sample(cuda_device):
+    """BASELINE configs[4] family: estimate_betas at n = 50k cells, k = 20 on two SNPs against the oracle (thin SVD of the
+    50k x 120 half-covariance per SNP and rho1, as the reference does at :166-171).  beta_G is a GLS coefficient at the fitted
+    delta: its sensitivity to where Brent stops (|d logit delta| <= 4e-6) is far below 1e-6; the GxC betas carry the factor
+    v0 * rho1 and follow the variance-component rule (rtol 1e-6 of the largest entry)."""
+    from cellregmap_b200 import estimate_betas
+    from oracle import crm_port
+    d = make_data(n=50000, donors=500, k=20, p=2, q=5, seed=23, causal_gxc=(0,), causal_persistent=(1,), v_gxc=0.01)
+    ref_bg, ref_bgxe = crm_port.estimate_betas(d.y, d.W, d.E, d.G, hK=d.hK)
+    bg, bgxe = estimate_betas(d.y, d.W, d.E, d.G, hK=d.hK)
+    assert bg.shape == (2,) and bgxe.shape == (1, 50000, 2)
+    assert np.abs(ref_bgxe[0, :, 0]).max() > 0                   # SNP 0 carries the simulated GxC effect: rho1 > 0 selected
+    np.testing.assert_allclose(bg, ref_bg, rtol=1e-6)
+    np.testing.assert_allclose(bgxe, ref_bgxe, rtol=0, atol=4e-6 * np.abs(ref_bgxe).max())
+
+
 def test_wide_background_basis(cuda_device):
     """m = k + k q = 2 404 columns in the half-covariance: the per-rho vectors no longer fit the fit kernel's shared memory
     (global-memory path) and the spectrum is long; checked against the oracle on a few SNPs."""

@@ -227,9 +227,10 @@ def test_estimate_betas(cuda_device, onehot):
     bg, bgxe = estimate_betas(d.y, d.W, E, d.G, hK=d.hK)
     assert bg.shape == ref_bg.shape == (12,)
     assert bgxe.shape == ref_bgxe.shape == (1, 400, 12)
-    np.testing.assert_allclose(bg, ref_bg, rtol=2e-5, atol=1e-8)
-    scale = np.abs(ref_bgxe).max()
-    np.testing.assert_allclose(bgxe, ref_bgxe, rtol=0, atol=2e-5 * scale)
+    # measured agreement on the B200: <= 2e-10 for beta_G, <= 2e-10 of the column maximum for the GxC betas
+    np.testing.assert_allclose(bg, ref_bg, rtol=1e-6, atol=1e-12)
+    scale = np.abs(ref_bgxe).max(axis=(0, 1))
+    np.testing.assert_allclose(bgxe, ref_bgxe, rtol=0, atol=1e-6 * scale + 1e-300)
     # explicit maf and device-resident genotypes
     import torch
     maf = crm_port.compute_maf(d.G)
