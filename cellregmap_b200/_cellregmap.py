@@ -51,26 +51,29 @@ def _stream():
 
 
 def _scaled_left_vectors(E):
-    """U S of the thin SVD of the tall matrix E with singular values >= sqrt(eps) (numpy_sugar.linalg.economic_svd), up to the sign
-    of each column.  Through the triangular factor: E = Q R, R = Ur S V' (k x k, on the host: one 3 KB read-back) and U S = E V.
+    """(U S, V) of the thin SVD of the tall matrix E with singular values >= sqrt(eps) (numpy_sugar.linalg.economic_svd), up to the
+    sign of each column; V (k x r, numpy) is the map U S = E V, None when E is wider than tall.  Through the triangular factor:
+    E = Q R, R = Ur S V' (k x k, on the host: one 3 KB read-back).
     torch.linalg.svd on the device runs an iterative cuSOLVER routine with dozens of small launches and host round trips per call
     (25-45 ms of an otherwise 210 ms run_interaction); the QR route is two launches, one tiny SVD and one thin GEMM."""
     if E.shape[0] < E.shape[1]:
         U, S, _ = torch.linalg.svd(E, full_matrices=False)
         keep = S >= EPS_SMALL
-        return U[:, keep] * S[keep]
+        return U[:, keep] * S[keep], None
     R = torch.linalg.qr(E, mode="r").R
     _, S, Vh = np.linalg.svd(R.cpu().numpy())
     keep = S >= EPS_SMALL
-    V = torch.from_numpy(np.ascontiguousarray(Vh[keep, :].T)).to(E.device)
-    return E @ V
+    Vnp = np.ascontiguousarray(Vh[keep, :].T)
+    return E @ torch.from_numpy(Vnp).to(E.device), Vnp
 
 
-def _L_concat(hK, E):
-    """[L_1 | ... | L_k] with L_i = diag(U_i S_i) hK  (reference get_L_values, :533-545), one device tensor."""
-    us = _scaled_left_vectors(E)
+def _L_concat(hK, E, with_map=False):
+    """[L_1 | ... | L_k] with L_i = diag(U_i S_i) hK  (reference get_L_values, :533-545), one device tensor; with_map: also the
+    k x r matrix V with U S = E V (crm_set_background_factors)."""
+    us, V = _scaled_left_vectors(E)
     n = hK.shape[0]
-    return (us[:, :, None] * hK[:, None, :]).reshape(n, us.shape[1] * hK.shape[1]).contiguous()
+    L = (us[:, :, None] * hK[:, None, :]).reshape(n, us.shape[1] * hK.shape[1]).contiguous()
+    return (L, V) if with_map else L
 
 
 def get_L_values(hK, E):
@@ -246,6 +249,15 @@ class CellRegMap:
                 _lib.call("crm_import_basis", self._handle, r, _ptr(everything[other, j]), _stream())
         _lib.call("crm_setup_finish", self._handle, _stream())
 
+    def _declare_background_factors(self, hK, V):
+        """Tells the library that Ls = get_L_values(hK, E) with U S = E V (crm_set_background_factors); verified there."""
+        self._background_factors = (hK, np.ascontiguousarray(V, dtype=np.float64))
+        hK, V = self._background_factors
+        ok = ctypes.c_int(0)
+        _lib.call("crm_set_background_factors", self._handle, _ptr(hK), hK.stride(0), int(hK.shape[1]),
+                  V.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(V.shape[1]), ctypes.byref(ok), _stream())
+        return bool(ok.value)
+
     def __del__(self):
         h = getattr(self, "_handle", None)
         if h is not None and h.value:
@@ -362,6 +374,8 @@ class CellRegMap:
         finally:
             if idx_E is not None:
                 _lib.call("crm_set_test_contexts", self._handle, _ptr(self._E0), self._E0.stride(0), _stream())
+                if getattr(self, "_background_factors", None) is not None:
+                    self._declare_background_factors(*self._background_factors)
         if PROFILE["on"]:
             dims = (ctypes.c_int64 * 8)()
             _lib.call("crm_get_dims", self._handle, dims)
@@ -459,9 +473,19 @@ def run_association_fast(y, W, E, G, hK=None, *, donor_index=None):
 def _make_interaction_model(y, E, W, E1, E2, hK, device=None, prefetch=None, group=None):
     dev = _device(device)
     E1 = E if E1 is None else E1
+    same_contexts = E2 is None or E2 is E
     E2 = E if E2 is None else E2
-    Ls = None if hK is None else _L_concat(_to_dev(hK, dev, two_d=True), _to_dev(E2, dev))
-    return CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev, _prefetch=prefetch, _group=group)
+    Ls, V, hK_dev = None, None, None
+    if hK is not None:
+        hK_dev = _to_dev(hK, dev, two_d=True)
+        Ls, V = _L_concat(hK_dev, _to_dev(E2, dev), with_map=True)
+    crm = CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev, _prefetch=prefetch, _group=group)
+    if V is not None and not same_contexts:
+        same_contexts = tuple(E2.shape) == tuple(E.shape) and bool(torch.equal(_to_dev(E2, dev), crm._E0))
+    if V is not None and same_contexts:
+        # the background was built from the tested contexts themselves: L.E_j products are symmetric triple products (see the header)
+        crm._declare_background_factors(hK_dev, V)
+    return crm
 
 
 def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None, *, donor_index=None):

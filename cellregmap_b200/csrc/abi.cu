@@ -153,6 +153,13 @@ struct Handle {
     bool oz_block_affine = false, colsum_valid = false;
     DevBuf aff, affscratch, colsum, colsum2, sq1;
     double prof_oz_gemm_ops = 0.0; std::vector<cudaEvent_t> prof_oz_events;
+    // Khatri-Rao structure of the background basis (crm_set_background_factors): L[:, i q + c] = (E0 M)[:, i] * hK[:, c], so that the
+    // products L.E0_j are combinations of the symmetric triple products hK_c.E0_l.E0_j -- the rotation contracts the compact set of
+    // distinct columns (kr_rows of them, layout in kr_layout) and kr_expand_kernel rebuilds the full C from it
+    bool kr = false, oz_built_kr = false;
+    int kr_q = 0, kr_r = 0;
+    long long kr_R1 = 0, kr_R2 = 0, kr_R3 = 0, kr_rows = 0;
+    DevBuf krK, krM, Cc;
     int hxe_blocks = 0;   // context blocks j held by HxE at a time: kexp = whole basis resident, fewer = streamed in groups
     DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
     // null-model state for the association scans
@@ -184,7 +191,7 @@ struct Handle {
         DevBuf* all[] = {&A8, &a8expo, &Gt8, &G2t8, &D32, &ozflags, &A28, &a28expo, &HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
-                         &gtchunk[0], &gtchunk[1], &gstage, &g8dev[0], &g8dev[1], &gwide, &gwide2, &aff, &affscratch, &colsum, &colsum2, &sq1, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram};
+                         &gtchunk[0], &gtchunk[1], &gstage, &g8dev[0], &g8dev[1], &gwide, &gwide2, &aff, &affscratch, &colsum, &colsum2, &sq1, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram, &krK, &krM, &Cc};
         for (DevBuf* b : all) fn(*b);
     }
     void free_all() { for_each_buf([](DevBuf& b) { b.release(); }); }
@@ -227,6 +234,66 @@ __global__ void build_hxe_kernel(const double* Hx, int ldH, const double* Eext, 
         for (int a = threadIdx.x; a < ldH; a += blockDim.x) {
             const double hv = hrow[a];
             for (int j = 0; j < nj; j++) orow[(long long)j * ldH + a] = erow[j] * hv;
+        }
+    }
+}
+// ---- Khatri-Rao structured background (Handle::kr) ----
+// Compact row layout of the rotation when L[:, i q + c] = (E0 M)[:, i] * hK[:, c]:
+//   [0, ldH)                      Hx[:, a]                               (block j = 0 of the full layout)
+//   R1 + (j-1) k1 + a             E1[:, a] * E0[:, j-1]                   j = 1..k0, a < k1
+//   R2 + (j-1) (1+c) + t          [y | W][:, t] * E0[:, j-1]              t < 1 + c
+//   R3 + pair(l, j) q + cc        hK[:, cc] * E0[:, l] * E0[:, j]         l <= j, pair = j (j + 1) / 2 + l  (the pair columns of A2)
+// Full layout (row = j ldH + a): block j >= 1, column k1 + i q + cc  =  sum_l M[l][i] * compact[R3 + pair(l, j-1) q + cc].
+// does the declared structure reproduce the L columns of Hx?  flag |= 1 on the first entry that does not
+__global__ void kr_check_kernel(const double* Hx, int ldH, int k1, const double* Eext, int epitch, int k0, const double* hK, int q, const double* M, int r,
+                                long long n, int* flag) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)r * q;
+    if (idx >= n * per) return;
+    const long long i = idx / per; const int col = (int)(idx - i * per); const int ii = col / q, cc = col - ii * q;
+    double us = 0.0, mag = 0.0;
+    for (int l = 0; l < k0; l++) { const double t = Eext[i * epitch + 1 + l] * M[l * r + ii]; us += t; mag += fabs(t); }
+    const double hk = hK[i * q + cc];
+    const double want = us * hk, got = Hx[i * ldH + k1 + col];
+    if (!(fabs(got - want) <= 1e-11 * mag * fabs(hk) + 1e-290)) atomicOr(flag, 1);
+}
+// full rotation output C[(s kexp + j)][a] from the compact one S[s][row] (one block per SNP; M in shared memory, k0 x rp)
+constexpr int KR_IT = 8;
+__global__ void __launch_bounds__(256) kr_expand_kernel(const double* __restrict__ S, long long lds, const double* __restrict__ M, int k0, int r, int q, int k1, int m,
+                                                        int c, int ldH, long long R1, long long R2, long long R3, long long B, double* __restrict__ C) {
+    extern __shared__ double Msh[];
+    const int rp = (r + KR_IT - 1) / KR_IT * KR_IT;
+    for (int t = threadIdx.x; t < k0 * rp; t += blockDim.x) { const int l = t / rp, i = t - l * rp; Msh[t] = i < r ? M[l * r + i] : 0.0; }
+    __syncthreads();
+    const int kexp = 1 + k0, small = k1 + (ldH - m);
+    for (long long s = blockIdx.x; s < B; s += gridDim.x) {
+        const double* Ss = S + s * lds;
+        double* Cs = C + s * (long long)kexp * ldH;
+        for (int a = threadIdx.x; a < ldH; a += blockDim.x) Cs[a] = Ss[a];
+        for (int t = threadIdx.x; t < k0 * small; t += blockDim.x) {
+            const int j = t / small, u = t - j * small;
+            double v; int a;
+            if (u < k1) { a = u; v = Ss[R1 + (long long)j * k1 + u]; }
+            else { const int w = u - k1; a = m + w; v = w < 1 + c ? Ss[R2 + (long long)j * (1 + c) + w] : 0.0; }
+            Cs[(long long)(1 + j) * ldH + a] = v;
+        }
+        for (int t = threadIdx.x; t < k0 * q; t += blockDim.x) {
+            const int j = t / q, cc = t - j * q;
+            double* out = Cs + (long long)(1 + j) * ldH + k1 + cc;
+            for (int i0 = 0; i0 < r; i0 += KR_IT) {
+                double acc[KR_IT];
+#pragma unroll
+                for (int u = 0; u < KR_IT; u++) acc[u] = 0.0;
+                for (int l = 0; l < k0; l++) {
+                    const int lo = min(l, j), hi = max(l, j);
+                    const double sv = Ss[R3 + (long long)(hi * (hi + 1) / 2 + lo) * q + cc];
+                    const double* mrow = Msh + l * rp + i0;
+#pragma unroll
+                    for (int u = 0; u < KR_IT; u++) acc[u] = fma(mrow[u], sv, acc[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < KR_IT; u++) if (i0 + u < r) out[(long long)(i0 + u) * q] = acc[u];
+            }
         }
     }
 }
@@ -447,6 +514,7 @@ static int build_test_contexts(Handle* h, const double* E0, long long lde0, cuda
     build_a2_kernel<<<blocks_for(h->n * h->ld2, 256), 256, 0, st>>>(E0, lde0, h->n, h->k0, h->A2.as<double>(), h->ld2);
     CRM_CUDA(cudaGetLastError()); count_launch();
     h->hxe_built = false;    // the pre-expanded basis is (re)built by the first cell-level rotation that needs it
+    h->kr = false;           // a declared structure of the background refers to the contexts it was declared with
     h->oz_built = false;
     h->oz_built_a2 = false;
     h->colsum_valid = false;
@@ -520,11 +588,28 @@ static int ensure_column_sums(Handle* h, cudaStream_t st) {
 
 // room for the digit planes of [Hx | Hx.E0_j]?  (cudaMemGetInfo costs milliseconds: only asked for large requests); extra = further
 // bytes the caller needs next to them
+static int kr_expand(Handle* h, const double* S, long long lds, long long B, double* C, cudaStream_t st) {
+    const int rp = (h->kr_r + KR_IT - 1) / KR_IT * KR_IT;
+    const size_t smem = (size_t)h->k0 * rp * sizeof(double);
+    if (smem > 48 * 1024) { set_error("structured background: %d x %d context map does not fit shared memory", h->k0, h->kr_r); return CRM_ERR_UNSUPPORTED; }
+    kr_expand_kernel<<<(unsigned)std::min<long long>(B, 148 * 64), 256, smem, st>>>(S, lds, h->krM.as<double>(), h->k0, h->kr_r, h->kr_q, h->k1, h->m, h->c, h->ldH,
+                                                                                   h->kr_R1, h->kr_R2, h->kr_R3, B, C);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+// CRM_KR=0 (read per call: tests, A/B) ignores a declared Khatri-Rao structure
+static bool kr_active(const Handle* h) {
+    if (!h->kr) return false;
+    const char* v = getenv("CRM_KR");
+    return !(v && atoi(v) == 0);
+}
+// rows of the K-major digit-plane operand: the full expanded basis, or the compact set of a structured background
+static long long plane_rows(const Handle* h) { return kr_active(h) ? h->kr_rows : (long long)h->kexp * h->ldH; }
 static int planes_fit(Handle* h, double extra, bool* fits) {
-    const long long Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(h->n, 16);
+    const long long Mtot = plane_rows(h), Mp = round_up(Mtot, 16), Kp = round_up(h->n, 16);
     const size_t a8_bytes = (size_t)OZAKI_SLICES * Mp * Kp;
     *fits = true;
-    if (h->oz_built || h->A8.cap >= a8_bytes) return CRM_OK;
+    if ((h->oz_built && h->oz_built_kr == kr_active(h)) || h->A8.cap >= a8_bytes) return CRM_OK;
     static size_t total_mem[16] = {0};
     if (!total_mem[h->device]) { size_t f = 0; CRM_CUDA(cudaMemGetInfo(&f, &total_mem[h->device])); }
     const double need = (double)a8_bytes + extra;
@@ -536,16 +621,33 @@ static int planes_fit(Handle* h, double extra, bool* fits) {
     }
     return CRM_OK;
 }
-// exponents + digit planes of [Hx | Hx.E0_j] on stream `on` (buffers reserved by the caller's stream order)
+// exponents + digit planes of [Hx | Hx.E0_j] (or of its compact form, kr_layout) on stream `on` (buffers reserved by the caller's stream order)
 static int build_planes(Handle* h, cudaStream_t on) {
-    const long long n = h->n, Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(n, 16);
-    CRM_CHECK(oz_launch_exponents(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, n, h->a8expo.as<int>(), on));
-    return oz_launch_slices(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, 0, h->kexp, n, h->a8expo.as<int>(), h->A8.as<int8_t>(), Mp, Kp, on);
+    const long long n = h->n, Mtot = plane_rows(h), Mp = round_up(Mtot, 16), Kp = round_up(n, 16);
+    int* expo = h->a8expo.as<int>();
+    int8_t* A8 = h->A8.as<int8_t>();
+    if (!kr_active(h)) {
+        CRM_CHECK(oz_launch_exponents(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, h->kexp, n, expo, on));
+        return oz_launch_slices(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, 0, h->kexp, n, expo, A8, Mp, Kp, on);
+    }
+    const double* Hx = h->Hx.as<double>(); const double* Ee = h->Eext.as<double>(); const double* A2 = h->A2.as<double>(); const double* hK = h->krK.as<double>();
+    const int ldH = h->ldH, k0 = h->k0, k1 = h->k1, yw = 1 + h->c, q = h->kr_q, npair = k0 * (k0 + 1) / 2;
+    CRM_CHECK(oz_launch_fill_exponents(expo, Mtot, on));
+    CRM_CHECK(oz_launch_product_exponents(Hx, ldH, ldH, Ee, h->epitch, 0, 1, n, expo, 0, ldH, on));
+    CRM_CHECK(oz_launch_product_exponents(Hx, ldH, k1, Ee, h->epitch, 1, k0, n, expo, h->kr_R1, k1, on));
+    CRM_CHECK(oz_launch_product_exponents(Hx + h->m, ldH, yw, Ee, h->epitch, 1, k0, n, expo, h->kr_R2, yw, on));
+    CRM_CHECK(oz_launch_product_exponents(hK, q, q, A2, h->ld2, 1 + k0, npair, n, expo, h->kr_R3, q, on));
+    CRM_CHECK(oz_launch_product_slices(Hx, ldH, ldH, Ee, h->epitch, 0, 1, n, expo, A8, Mp, Kp, 0, ldH, on));
+    CRM_CHECK(oz_launch_product_slices(Hx, ldH, k1, Ee, h->epitch, 1, k0, n, expo, A8, Mp, Kp, h->kr_R1, k1, on));
+    CRM_CHECK(oz_launch_product_slices(Hx + h->m, ldH, yw, Ee, h->epitch, 1, k0, n, expo, A8, Mp, Kp, h->kr_R2, yw, on));
+    return oz_launch_product_slices(hK, q, q, A2, h->ld2, 1 + k0, npair, n, expo, A8, Mp, Kp, h->kr_R3, q, on);
 }
 static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStream_t st, int* used) {
     *used = 0;
     const long long B = blk.b;
-    const long long n = h->n, Mtot = (long long)h->kexp * h->ldH, Mp = round_up(Mtot, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
+    const bool compact = kr_active(h);
+    const long long Mfull = (long long)h->kexp * h->ldH;
+    const long long n = h->n, Mtot = plane_rows(h), Mp = round_up(Mtot, 16), Kp = round_up(n, 16), Bp = round_up(B, 16);
     const size_t a8_bytes = (size_t)OZAKI_SLICES * Mp * Kp;
     {
         bool fits = true;
@@ -588,13 +690,15 @@ static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStre
         if ((double)Kp * 64.0 * (double)std::max(flags[1], 1) >= 2147483648.0) return CRM_OK;   // int32 accumulation could overflow
     }
     tr.mark("genotypes->int8");
-    if (!h->oz_built) {
+    if (!h->oz_built || h->oz_built_kr != compact) {
         if (h->A8.reserve(a8_bytes) != CRM_OK) return CRM_OK;      // no room after all: the fp64 route takes over
         CRM_CHECK(h->a8expo.reserve((size_t)Mtot * sizeof(int)));
         CRM_CHECK(build_planes(h, st));
-        h->oz_built = true;
+        h->oz_built = true; h->oz_built_kr = compact;
         tr.mark("digit planes");
     }
+    double* Crot = C;                 // where the contraction writes: the full layout, or the compact one (expanded below)
+    if (compact) { CRM_CHECK(h->Cc.reserve((size_t)B * Mtot * 8)); Crot = h->Cc.as<double>(); }
     if (h->prof_on) {
         cudaEvent_t e0, e1;
         CRM_CUDA(cudaEventCreate(&e0)); CRM_CUDA(cudaEventCreate(&e1));
@@ -602,12 +706,16 @@ static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStre
         h->prof_oz_events.push_back(e0); h->prof_oz_events.push_back(e1);
         h->prof_oz_gemm_ops += 2.0 * (double)OZAKI_SLICES * (double)Mp * (double)Kp * (double)Bp;
     }
-    CRM_CHECK(int8_split_contract(h, h->A8.as<int8_t>(), Mp, Mtot, h->a8expo.as<int>(), h->Gt8.as<int8_t>(), Bp, B, Kp, C, Mtot, st));
+    CRM_CHECK(int8_split_contract(h, h->A8.as<int8_t>(), Mp, Mtot, h->a8expo.as<int>(), h->Gt8.as<int8_t>(), Bp, B, Kp, Crot, Mtot, st));
     if (h->prof_on) CRM_CUDA(cudaEventRecord(h->prof_oz_events.back(), st));
     tr.mark("int8 contraction");
+    if (compact) {
+        CRM_CHECK(kr_expand(h, Crot, Mtot, B, C, st));
+        tr.mark("expand");
+    }
     if (affine) {
         CRM_CHECK(ensure_column_sums(h, st));
-        CRM_CHECK(oz_launch_affine_fix(C, Mtot, B, Mtot, h->aff.as<double>(), round_up(B, 2), h->colsum.as<double>(), st));
+        CRM_CHECK(oz_launch_affine_fix(C, Mfull, B, Mfull, h->aff.as<double>(), round_up(B, 2), h->colsum.as<double>(), st));
         tr.mark("affine map");
     }
     tr.report("int8 rotation");
@@ -754,7 +862,7 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
     if (k1 + mL > 30000) { set_error("background half-covariance has %lld columns; limit is 30000", (long long)(k1 + mL)); return CRM_ERR_UNSUPPORTED; }
     h->ready = false;
     h->donors_set = false;
-    h->oz_built = false; h->oz_built_a2 = false;
+    h->oz_built = false; h->oz_built_a2 = false; h->kr = false;
     h->n = n; h->c = c; h->k0 = k0; h->k1 = k1; h->mL = mL; h->R = R;
     h->m = (int)(k1 + mL);
     h->mp = (int)round_up(h->m, 2);
@@ -1870,6 +1978,42 @@ int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* 
     AllocScope alloc_scope((cudaStream_t)stream); h->impl.last_stream = (cudaStream_t)stream;
     CRM_CHECK(adopt_buffers(&h->impl, (cudaStream_t)stream));
     return build_test_contexts(&h->impl, E0, lde0, (cudaStream_t)stream);
+}
+
+int crm_set_background_factors(crm_handle_t h, const double* hK, int64_t ldhk, int q, const double* M, int r, int* accepted, void* stream) {
+    if (accepted) *accepted = 0;
+    if (!h || !h->impl.ready) { set_error("crm_set_background_factors: handle not set up"); return CRM_ERR_STATE; }
+    Handle& H = h->impl;
+    if (!hK || !M || q <= 0 || r <= 0 || ldhk < q) { set_error("crm_set_background_factors: bad arguments"); return CRM_ERR_INVALID; }
+    H.kr = false;
+    const int rp = (r + KR_IT - 1) / KR_IT * KR_IT;
+    // shapes the structure cannot describe, or that the expansion kernel does not take: not an error, the full basis is used
+    if ((long long)r * q != H.mL || r > H.k0 || (size_t)H.k0 * rp * sizeof(double) > 48 * 1024) return CRM_OK;
+    CRM_CUDA(cudaSetDevice(H.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    AllocScope alloc_scope(st); H.last_stream = st;
+    CRM_CHECK(adopt_buffers(&H, st));
+    CRM_CHECK(H.krK.reserve((size_t)H.n * q * 8));
+    CRM_CHECK(H.krM.reserve((size_t)H.k0 * r * 8));
+    CRM_CHECK(H.ozflags.reserve(64));
+    CRM_CUDA(cudaMemcpy2DAsync(H.krK.ptr, (size_t)q * 8, hK, (size_t)ldhk * 8, (size_t)q * 8, (size_t)H.n, cudaMemcpyDeviceToDevice, st));
+    CRM_CUDA(cudaMemcpyAsync(H.krM.ptr, M, (size_t)H.k0 * r * 8, cudaMemcpyHostToDevice, st));
+    CRM_CUDA(cudaMemsetAsync(H.ozflags.ptr, 0, 4 * sizeof(int), st));
+    kr_check_kernel<<<blocks_for(H.n * (long long)r * q, 256), 256, 0, st>>>(H.Hx.as<double>(), H.ldH, H.k1, H.Eext.as<double>(), H.epitch, H.k0, H.krK.as<double>(), q,
+                                                                            H.krM.as<double>(), r, H.n, H.ozflags.as<int>());
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    int flag = 1;
+    CRM_CUDA(cudaMemcpyAsync(&flag, H.ozflags.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaStreamSynchronize(st));
+    if (flag != 0) return CRM_OK;                 // the basis is not the declared product: ignored
+    H.kr = true; H.kr_q = q; H.kr_r = r;
+    H.kr_R1 = H.ldH;
+    H.kr_R2 = H.kr_R1 + (long long)H.k0 * H.k1;
+    H.kr_R3 = H.kr_R2 + (long long)H.k0 * (1 + H.c);
+    H.kr_rows = H.kr_R3 + (long long)(H.k0 * (H.k0 + 1) / 2) * q;
+    if (H.kr_rows >= (long long)H.kexp * H.ldH) H.kr = false;     // nothing to gain (tiny k0)
+    if (accepted) *accepted = H.kr ? 1 : 0;
+    return CRM_OK;
 }
 
 long long crm_launch_count(void) { return g_launches.load(); }

@@ -14,22 +14,39 @@ static __global__ void oz_fill_kernel(int* p, long long count, int value) {
     if (i < count) p[i] = value;
 }
 
-int oz_launch_exponents(const double* Hx, int ldH, const double* Eext, int epitch, int kexp, long long n, int* expo, cudaStream_t st) {
-    const long long cols = (long long)kexp * ldH;
-    oz_fill_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(expo, cols, OZ_EXP_EMPTY);
-    CRM_CUDA(cudaGetLastError()); count_launch();
-    dim3 grid((unsigned)((ldH + 127) / 128), (unsigned)kexp, (unsigned)std::max<long long>(1, std::min<long long>(64, n / 512)));
-    oz_column_exponent_kernel<<<grid, 128, 0, st>>>(Hx, ldH, Eext, epitch, n, expo);
+int oz_launch_fill_exponents(int* expo, long long rows, cudaStream_t st) {
+    oz_fill_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(expo, rows, OZ_EXP_EMPTY);
     CRM_CUDA(cudaGetLastError()); count_launch();
     return CRM_OK;
+}
+// exponents and digit planes of the product columns F[:, j0 + jj] * X[:, a] at rows row0 + jj * rstride + a  (ozaki.cuh)
+int oz_launch_product_exponents(const double* X, long long ldx, int cols, const double* F, long long ldf, int j0, int nj, long long n, int* expo, long long row0,
+                                long long rstride, cudaStream_t st) {
+    if (cols <= 0 || nj <= 0) return CRM_OK;
+    for (int y0 = 0; y0 < nj; y0 += 32768) {
+        const int ny = std::min(32768, nj - y0);
+        dim3 grid((unsigned)((cols + 127) / 128), (unsigned)ny, (unsigned)std::max<long long>(1, std::min<long long>(64, n / 512)));
+        oz_column_exponent_kernel<<<grid, 128, 0, st>>>(X, ldx, cols, F, ldf, j0 + y0, n, expo, row0 + (long long)y0 * rstride, rstride);
+        CRM_CUDA(cudaGetLastError()); count_launch();
+    }
+    return CRM_OK;
+}
+int oz_launch_product_slices(const double* X, long long ldx, int cols, const double* F, long long ldf, int j0, int nj, long long n, const int* expo, int8_t* A8,
+                             long long Mp, long long Kp, long long row0, long long rstride, cudaStream_t st) {
+    if (cols <= 0 || nj <= 0) return CRM_OK;
+    dim3 grid((unsigned)((Kp + OZ_ROWS - 1) / OZ_ROWS), (unsigned)((cols + OZ_TILE - 1) / OZ_TILE), 1);
+    oz_slice_kernel<<<grid, 256, 0, st>>>(X, ldx, cols, F, ldf, j0, nj, n, expo, A8, Mp, Kp, row0, rstride);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+int oz_launch_exponents(const double* Hx, int ldH, const double* Eext, int epitch, int kexp, long long n, int* expo, cudaStream_t st) {
+    CRM_CHECK(oz_launch_fill_exponents(expo, (long long)kexp * ldH, st));
+    return oz_launch_product_exponents(Hx, ldH, ldH, Eext, epitch, 0, kexp, n, expo, 0, ldH, st);
 }
 
 int oz_launch_slices(const double* Hx, int ldH, const double* Eext, int epitch, int j0, int nj, long long n, const int* expo, int8_t* A8, long long Mp,
                      long long Kp, cudaStream_t st) {
-    dim3 grid((unsigned)((Kp + OZ_ROWS - 1) / OZ_ROWS), (unsigned)((ldH + OZ_TILE - 1) / OZ_TILE), 1);
-    oz_slice_kernel<<<grid, 256, 0, st>>>(Hx, ldH, Eext, epitch, j0, nj, n, expo, A8, Mp, Kp);
-    CRM_CUDA(cudaGetLastError()); count_launch();
-    return CRM_OK;
+    return oz_launch_product_slices(Hx, ldH, ldH, Eext, epitch, j0, nj, n, expo, A8, Mp, Kp, (long long)j0 * ldH, ldH, st);
 }
 
 int oz_launch_matrix_planes(const double* X, long long ldx, int cols, long long n, int* expo, int8_t* P8, long long Mp, long long Kp, cudaStream_t st) {

@@ -55,6 +55,12 @@ constexpr int OZAKI_SLICES = 8;
 int oz_launch_exponents(const double* Hx, int ldH, const double* Eext, int epitch, int kexp, long long n, int* expo, cudaStream_t st);
 int oz_launch_slices(const double* Hx, int ldH, const double* Eext, int epitch, int j0, int nj, long long n, const int* expo, int8_t* A8, long long Mp,
                      long long Kp, cudaStream_t st);
+// general form: product columns F[:, j0 + jj] * X[:, a] (a < cols, jj < nj) at rows row0 + jj * rstride + a of the plane set
+int oz_launch_fill_exponents(int* expo, long long rows, cudaStream_t st);
+int oz_launch_product_exponents(const double* X, long long ldx, int cols, const double* F, long long ldf, int j0, int nj, long long n, int* expo, long long row0,
+                                long long rstride, cudaStream_t st);
+int oz_launch_product_slices(const double* X, long long ldx, int cols, const double* F, long long ldf, int j0, int nj, long long n, const int* expo, int8_t* A8,
+                             long long Mp, long long Kp, long long row0, long long rstride, cudaStream_t st);
 int oz_launch_genotypes(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st);
 // int8 dosages stored row-major (cells x SNPs): K-major operands of the contraction (flags may be null), float64 image, finiteness
 int oz_launch_transpose_i8(const int8_t* G8, long long ld8, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st);

@@ -29,19 +29,21 @@ __device__ __forceinline__ int oz_next_digit(double& x) {
     return q;
 }
 
-// exponent e with |x| < 2^e for the largest |x| of each column of HxE = Eext[:, j] * Hx[:, a]  (col = j * ldH + a);
-// expo must be pre-filled with OZ_EXP_EMPTY; rows are split over blockIdx.z and merged with atomicMax
-__global__ void oz_column_exponent_kernel(const double* Hx, int ldH, const double* Eext, int epitch, long long n, int* expo) {
+// exponent e with |x| < 2^e for the largest |x| of each product column F[:, j0 + jj] * X[:, a]  (a < cols, jj < gridDim.y), stored at
+// expo[row0 + jj * rstride + a]; the expanded basis [Hx | Hx.E0_j] is X = Hx, F = Eext, rstride = ldH.  expo must be pre-filled with
+// OZ_EXP_EMPTY; cells are split over blockIdx.z and merged with atomicMax
+__global__ void oz_column_exponent_kernel(const double* X, long long ldx, int cols, const double* F, long long ldf, int j0, long long n, int* expo, long long row0,
+                                          long long rstride) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (a >= ldH) return;
+    const int jj = blockIdx.y;
+    if (a >= cols) return;
     const long long chunk = (n + gridDim.z - 1) / gridDim.z, i0 = (long long)blockIdx.z * chunk, i1 = min(n, i0 + chunk);
     double mx = 0.0;
-    for (long long i = i0; i < i1; i++) mx = fmax(mx, fabs(Eext[i * epitch + j] * Hx[i * ldH + a]));
+    for (long long i = i0; i < i1; i++) mx = fmax(mx, fabs(F[i * ldf + j0 + jj] * X[i * ldx + a]));
     if (mx > 0.0) {
         int e = 0;
         frexp(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)  ->  mx < 2^e
-        atomicMax(&expo[(long long)j * ldH + a], e);
+        atomicMax(&expo[row0 + (long long)jj * rstride + a], e);
     }
 }
 
@@ -53,32 +55,33 @@ constexpr int OZ_ROWS = 128;               // cells per block of the slicing ker
 // that is conflict-free, where the identity mapping is an 8-way bank conflict (ncu: 429 M conflicts per launch, profiles/r02_ncu_oz_slice_kernel.txt).
 __device__ __forceinline__ int oz_tile_slot(int r) { return ((r & 3) << 5) | (r >> 2); }
 
-// digit planes, K-major: A8[t][col][i] (plane stride = Mp * Kp, row stride = Kp, Kp a multiple of 4)
-__global__ void __launch_bounds__(256) oz_slice_kernel(const double* Hx, int ldH, const double* Eext, int epitch, int j0, int nj, long long n, const int* expo,
-                                                       int8_t* A8, long long Mp, long long Kp) {
+// digit planes, K-major: A8[t][col][i] (plane stride = Mp * Kp, row stride = Kp, Kp a multiple of 4) of the product columns
+// F[:, j0 + jj] * X[:, a], col = row0 + jj * rstride + a  (a < cols, jj < nj)
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* X, long long ldx, int cols, const double* F, long long ldf, int j0, int nj, long long n,
+                                                       const int* expo, int8_t* A8, long long Mp, long long Kp, long long row0, long long rstride) {
     __shared__ double tile[OZ_ROWS][OZ_TILE + 1];
     const long long i0 = (long long)blockIdx.x * OZ_ROWS;
     const int a0 = blockIdx.y * OZ_TILE;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-    // this thread's 16 entries of the Hx tile stay in registers for all context blocks j (the basis is read once, not 1 + k times)
+    // this thread's 16 entries of the X tile stay in registers for all factor columns (the basis is read once, not 1 + k times)
     double hx[OZ_ROWS / 8];
 #pragma unroll
     for (int q = 0; q < OZ_ROWS / 8; q++) {
         const long long i = i0 + ty + 8 * q; const int a = a0 + tx;
-        hx[q] = (i < n && a < ldH) ? Hx[i * ldH + a] : 0.0;
+        hx[q] = (i < n && a < cols) ? X[i * ldx + a] : 0.0;
     }
     for (int jj = 0; jj < nj; jj++) {
         const int j = j0 + jj;
 #pragma unroll
-        for (int q = 0; q < OZ_ROWS / 8; q++) {                   // rows i, columns a (coalesced along a); Eext[i][j] is a warp-wide broadcast
+        for (int q = 0; q < OZ_ROWS / 8; q++) {                   // rows i, columns a (coalesced along a); F[i][j] is a warp-wide broadcast
             const int r = ty + 8 * q; const long long i = i0 + r;
-            tile[oz_tile_slot(r)][tx] = (i < n) ? Eext[i * epitch + j] * hx[q] : 0.0;
+            tile[oz_tile_slot(r)][tx] = (i < n) ? F[i * ldf + j] * hx[q] : 0.0;
         }
         __syncthreads();
         for (int r = ty; r < OZ_TILE; r += 8) {                   // write: rows a, 4 consecutive cells per thread
             const int a = a0 + r; const long long i = i0 + 4 * tx;
-            if (a < ldH && i < Kp) {
-                const long long col = (long long)j * ldH + a;
+            if (a < cols && i < Kp) {
+                const long long col = row0 + (long long)jj * rstride + a;
                 const int e = expo[col];
                 const double scale = (e == OZ_EXP_EMPTY) ? 0.0 : ldexp(1.0, -(e + 1));     // exact power of two
                 double x[4];

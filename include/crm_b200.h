@@ -105,6 +105,21 @@ CRM_API int crm_host_narrow(const void* src_host, int dtype, int64_t ld, int64_t
 CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* stream);
 
 /*
+ * Declares how the background half-covariance was built (reference get_L_values, _cellregmap.py:533-545, as called by
+ * run_interaction :577-580 / estimate_betas :672-675 with E2 = E):  L[:, i q + c] = (E0 M)[:, i] * hK[:, c]  with hK the n x q
+ * kinship factor (device, leading dimension ldhk) and M the k0 x r map from the contexts to the scaled left singular vectors
+ * U S = E0 M of the context matrix (host, row-major).  The products L.E0_j that the rotation needs are then combinations of the
+ * triple products hK_c.E0_l.E0_j, symmetric in (l, j): the rotation contracts only the k0 (k0 + 1) / 2 q distinct ones
+ * (plus Hx itself and the products of E1, y and W) and rebuilds the rest with the k0 x r map -- 0.56 of the contraction work and of
+ * the digit planes at k0 = 20.  The library verifies the claim against the basis it was set up with (one pass over L, one
+ * synchronisation of `stream`); *accepted = 1 when the structure is used, 0 when it does not hold or does not apply (then the call
+ * changes nothing).  Call after crm_setup / crm_setup_finish; crm_set_test_contexts drops the declaration (tested contexts that
+ * differ from the contexts inside L have no such symmetry).  CRM_KR=0 in the environment ignores it.
+ */
+CRM_API int crm_set_background_factors(crm_handle_t h, const double* hK, int64_t ldhk, int q, const double* M, int r, int* accepted,
+                                       void* stream);
+
+/*
  * New phenotype y (n doubles, device) for the same cells, contexts, covariates and background (extension): refreshes only
  * the y-dependent state of the model; the Gram of the half-basis and the per-rho eigendecompositions are kept.  Equivalent
  * to crm_setup with the new y.  Typical use: one model per data set, one crm_update_phenotype + scan per gene.

@@ -291,6 +291,68 @@ def test_rotation_routes_agree(cuda_device, monkeypatch):
         np.testing.assert_array_equal(info_c[key], info_a[key])
 
 
+@pytest.mark.parametrize("shape", ["k7 q5", "k3 q11 covariates", "rank-deficient contexts"])
+def test_structured_background_route(cuda_device, monkeypatch, shape):
+    """run_interaction builds L = get_L_values(hK, E): L[:, i q + c] = (E V)[:, i] hK[:, c], so L.E_j is a combination of the symmetric
+    triple products hK_c.E_l.E_j (crm_set_background_factors).  The compact int8 contraction + expansion gives the scan of the full
+    basis: same rho1, p-values and variance components at rounding level; idx_E scans drop and restore the declaration."""
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    if shape == "k7 q5":
+        d = make_data(n=900, donors=60, k=7, p=130, q=5, seed=17)
+        E = d.E
+    elif shape == "k3 q11 covariates":
+        d = make_data(n=1201, donors=80, k=3, p=70, q=11, seed=5, n_covariates=3)
+        E = d.E
+    else:
+        d = make_data(n=800, donors=50, k=5, p=64, q=4, seed=9)
+        lab = np.random.default_rng(3).integers(0, 5, 800)
+        E = np.eye(5)[lab]
+        E = (E - E.mean(0)) / E.std(0) / np.sqrt(5)            # centred one-hot contexts: rank 4, get_L_values keeps 4 blocks
+    model = _make_interaction_model(d.y, E, d.W, None, None, d.hK)
+    assert model._background_factors is not None
+    pv_s, info_s = model.scan_interaction(d.G)
+    monkeypatch.setenv("CRM_KR", "0")
+    pv_f, info_f = model.scan_interaction(d.G)                 # same model, full basis (digit planes rebuilt)
+    monkeypatch.delenv("CRM_KR")
+    np.testing.assert_array_equal(info_s["rho1"], info_f["rho1"])
+    assert np.max(np.abs(np.log10(pv_s) - np.log10(pv_f))) <= 1e-8
+    for key in ("e2", "g2", "eps2"):
+        np.testing.assert_allclose(info_s[key], info_f[key], rtol=1e-8, atol=1e-13)
+    pv_s2, _ = model.scan_interaction(d.G)                     # and back: bit-identical to the first structured scan
+    np.testing.assert_array_equal(pv_s2, pv_s)
+    # permuted tested contexts: no symmetry, the declaration is dropped for that scan and restored afterwards
+    idx = np.random.default_rng(1).permutation(d.y.shape[0])
+    pv_p, _ = model.scan_interaction(d.G, idx_E=idx)
+    monkeypatch.setenv("CRM_KR", "0")
+    pv_pf, _ = model.scan_interaction(d.G, idx_E=idx)
+    monkeypatch.delenv("CRM_KR")
+    np.testing.assert_array_equal(pv_p, pv_pf)
+    pv_s3, _ = model.scan_interaction(d.G)
+    np.testing.assert_array_equal(pv_s3, pv_s)
+
+
+def test_structured_background_needs_matching_contexts(cuda_device):
+    """E2 != E (background built from other contexts) or a basis that is not the declared product: the declaration is refused and
+    the full basis is used."""
+    import torch
+    from cellregmap_b200._cellregmap import _make_interaction_model, _to_dev
+    d = make_data(n=700, donors=40, k=6, p=40, q=5, seed=31)
+    E2 = np.random.default_rng(0).standard_normal((700, 6))
+    model = _make_interaction_model(d.y, d.E, d.W, None, E2, d.hK)
+    assert getattr(model, "_background_factors", None) is None
+    same = _make_interaction_model(d.y, d.E, d.W, None, d.E.copy(), d.hK)       # equal values, other object: accepted
+    assert same._background_factors is not None
+    # a wrong claim (another map) is detected by the library
+    hK = _to_dev(d.hK, model._device, two_d=True)
+    V = np.linalg.qr(np.random.default_rng(2).standard_normal((6, 6)))[0]
+    assert model._declare_background_factors(hK, V) is False
+    assert same._declare_background_factors(*same._background_factors) is True
+    pv_a, _ = model.scan_interaction(d.G)
+    ref = _make_interaction_model(d.y, d.E, d.W, None, E2, d.hK)
+    pv_b, _ = ref.scan_interaction(torch.from_numpy(d.G).cuda())
+    np.testing.assert_array_equal(pv_a, pv_b)
+
+
 def test_donor_level_genotypes_match_expanded(cuda_device):
     """Extension: donor-level genotypes + donor_index give the results of the expanded call (all scans)."""
     import torch

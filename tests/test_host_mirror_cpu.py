@@ -19,7 +19,7 @@ def test_scaled_left_vectors_match_numpy_svd(case):
     else:
         E = np.eye(6)[rng.integers(0, 6, 500)]
         E = np.hstack([E, np.ones((500, 1))])          # intercept + one-hot: rank 6 of 7
-    us = api._scaled_left_vectors(torch.from_numpy(E)).numpy()
+    us = api._scaled_left_vectors(torch.from_numpy(E))[0].numpy()
     U, S, _ = np.linalg.svd(E, full_matrices=False)
     keep = S >= api.EPS_SMALL
     assert us.shape == (E.shape[0], int(keep.sum()))
