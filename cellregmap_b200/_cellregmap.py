@@ -386,6 +386,10 @@ class CellRegMap:
             PROFILE["rot_ms"] += ms.value
             PROFILE["rot_flops"] += fl.value
             PROFILE["rot_launches"] += nl.value
+            full, used = ctypes.c_int64(0), ctypes.c_int64(0)
+            _lib.call("crm_rotation_rows", self._handle, ctypes.byref(full), ctypes.byref(used))
+            PROFILE["rot_flops_executed"] = PROFILE.get("rot_flops_executed", 0.0) + fl.value * used.value / max(1, full.value)
+            PROFILE["rotation_rows"] = (int(full.value), int(used.value))
             _lib.call("crm_profile_int8", self._handle, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(nl))
             PROFILE["int8_ms"] += ms.value
             PROFILE["int8_ops"] += fl.value

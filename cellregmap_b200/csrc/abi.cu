@@ -156,7 +156,7 @@ struct Handle {
     // Khatri-Rao structure of the background basis (crm_set_background_factors): L[:, i q + c] = (E0 M)[:, i] * hK[:, c], so that the
     // products L.E0_j are combinations of the symmetric triple products hK_c.E0_l.E0_j -- the rotation contracts the compact set of
     // distinct columns (kr_rows of them, layout in kr_layout) and kr_expand_kernel rebuilds the full C from it
-    bool kr = false, oz_built_kr = false;
+    bool kr = false, oz_built_kr = false, hxe_built_kr = false;
     int kr_q = 0, kr_r = 0;
     long long kr_R1 = 0, kr_R2 = 0, kr_R3 = 0, kr_rows = 0;
     DevBuf krK, krM, Cc;
@@ -294,6 +294,23 @@ __global__ void __launch_bounds__(256) kr_expand_kernel(const double* __restrict
 #pragma unroll
                 for (int u = 0; u < KR_IT; u++) if (i0 + u < r) out[(long long)(i0 + u) * q] = acc[u];
             }
+        }
+    }
+}
+// fp64 image of the compact basis (same columns and the same products as the digit planes of the int8 route): out[i][row]
+__global__ void build_hxe_compact_kernel(const double* Hx, int ldH, int k1, int m, int c, const double* Eext, int epitch, int k0, const double* A2, int ld2,
+                                         const double* hK, int q, long long R1, long long R2, long long R3, long long rows, long long n, double* out) {
+    const long long sym_end = R3 + (long long)(k0 * (k0 + 1) / 2) * q;
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+        const double* hrow = Hx + i * ldH; const double* erow = Eext + i * epitch + 1; const double* prow = A2 + i * ld2 + 1 + k0; const double* krow = hK + i * q;
+        double* orow = out + i * rows;
+        for (long long col = threadIdx.x; col < rows; col += blockDim.x) {
+            double v = 0.0;
+            if (col < R1) v = hrow[col];
+            else if (col < R2) { const int t = (int)(col - R1), j = t / k1, a = t - j * k1; v = erow[j] * hrow[a]; }
+            else if (col < R3) { const int t = (int)(col - R2), j = t / (1 + c), w = t - j * (1 + c); v = erow[j] * hrow[m + w]; }
+            else if (col < sym_end) { const long long t = col - R3; const int pi = (int)(t / q), cc = (int)(t - (long long)pi * q); v = prow[pi] * krow[cc]; }
+            orow[col] = v;
         }
     }
 }
@@ -780,12 +797,28 @@ static int launch_rotation(Handle* h, GBlock& blk, double* C, cudaStream_t st) {
     if (h->rotation_mode == 1) CRM_CHECK(check_block_finite(h, blk, st));     // (the int8 conversion kernel reported it otherwise)
     op.B = blk.G; op.ldb = blk.ld; op.b_cols = blk.cols; op.B2 = blk.G; op.ldb2 = blk.ld; op.b2_cols = blk.cols;
     CRM_CHECK(decide_hxe(h));
+    if (h->use_hxe && h->hxe_blocks == h->kexp && kr_active(h)) {
+        // structured background, basis resident: plain contraction against the compact basis, then the expansion (see kr_layout)
+        const long long rows = h->kr_rows;
+        CRM_CHECK(h->HxE.reserve((size_t)h->n * rows * 8));
+        if (!(h->hxe_built && h->hxe_built_kr)) {
+            build_hxe_compact_kernel<<<(unsigned)std::min<long long>(h->n, 148 * 16), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->k1, h->m, h->c, h->Eext.as<double>(), h->epitch,
+                                                                                                h->k0, h->A2.as<double>(), h->ld2, h->krK.as<double>(), h->kr_q, h->kr_R1,
+                                                                                                h->kr_R2, h->kr_R3, rows, h->n, h->HxE.as<double>());
+            CRM_CUDA(cudaGetLastError()); count_launch();
+        }
+        CRM_CHECK(h->Cc.reserve((size_t)B * rows * 8));
+        op.A = h->HxE.as<double>(); op.lda = rows; op.a_cols = rows;
+        CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, (int)rows, 0, (int)B, h->Cc.as<double>(), rows, 1, st));
+        h->hxe_built = true; h->hxe_built_kr = true;
+        return kr_expand(h, h->Cc.as<double>(), rows, B, C, st);
+    }
     if (h->use_hxe) {
         const int nb = h->hxe_blocks;
         CRM_CHECK(h->HxE.reserve((size_t)h->n * nb * h->ldH * 8));
         for (int j0 = 0; j0 < h->kexp; j0 += nb) {
             const int nj = std::min(nb, h->kexp - j0);
-            if (!(nb == h->kexp && h->hxe_built)) {
+            if (!(nb == h->kexp && h->hxe_built && !h->hxe_built_kr)) {
                 build_hxe_kernel<<<(unsigned)std::min<long long>(h->n, 148 * 16), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->Eext.as<double>(), h->epitch, j0, nj, h->n,
                                                                                           h->HxE.as<double>());
                 CRM_CUDA(cudaGetLastError()); count_launch();
@@ -793,7 +826,7 @@ static int launch_rotation(Handle* h, GBlock& blk, double* C, cudaStream_t st) {
             op.A = h->HxE.as<double>(); op.lda = (long long)nj * h->ldH; op.a_cols = op.lda;
             CRM_CHECK(launch_gemm(GEMM_PLAIN, op, (int)h->n, 0, (int)op.lda, 0, (int)B, C + (long long)j0 * h->ldH, ldE, 1, st));
         }
-        h->hxe_built = (nb == h->kexp);
+        h->hxe_built = (nb == h->kexp); h->hxe_built_kr = false;
         return CRM_OK;
     }
     op.A = h->Hx.as<double>(); op.lda = h->ldH; op.a_cols = h->Mx;
@@ -1057,7 +1090,8 @@ static int do_update_phenotype(Handle* h, const double* y, cudaStream_t st) {
     CRM_CUDA(cudaGetLastError()); count_launch();
     h->oz_built = false;     // the digit planes of the y column (and its exponent) change with the phenotype: rebuilt on demand
     h->colsum_valid = false;
-    if (h->use_hxe && h->hxe_built && h->hxe_blocks == h->kexp) {
+    if (h->hxe_built && h->hxe_built_kr) h->hxe_built = false;        // compact fp64 basis: rebuilt by the next float64 rotation
+    else if (h->use_hxe && h->hxe_built && h->hxe_blocks == h->kexp) {
         refresh_y_hxe_kernel<<<blocks_for(h->n * h->kexp, 256), 256, 0, st>>>(Hx, ldH, m, h->Eext.as<double>(), h->epitch, h->kexp, h->n, h->HxE.as<double>());
         CRM_CUDA(cudaGetLastError()); count_launch();
     }
@@ -2010,9 +2044,16 @@ int crm_set_background_factors(crm_handle_t h, const double* hK, int64_t ldhk, i
     H.kr_R1 = H.ldH;
     H.kr_R2 = H.kr_R1 + (long long)H.k0 * H.k1;
     H.kr_R3 = H.kr_R2 + (long long)H.k0 * (1 + H.c);
-    H.kr_rows = H.kr_R3 + (long long)(H.k0 * (H.k0 + 1) / 2) * q;
+    H.kr_rows = round_up(H.kr_R3 + (long long)(H.k0 * (H.k0 + 1) / 2) * q, 2);     // even: leading dimension of fp64 TMA operands
     if (H.kr_rows >= (long long)H.kexp * H.ldH) H.kr = false;     // nothing to gain (tiny k0)
     if (accepted) *accepted = H.kr ? 1 : 0;
+    return CRM_OK;
+}
+
+int crm_rotation_rows(crm_handle_t h, int64_t* full_rows, int64_t* used_rows) {
+    if (!h || !h->impl.ready) { set_error("crm_rotation_rows: handle not set up"); return CRM_ERR_STATE; }
+    if (full_rows) *full_rows = (int64_t)h->impl.kexp * h->impl.ldH;
+    if (used_rows) *used_rows = (int64_t)plane_rows(&h->impl);
     return CRM_OK;
 }
 

@@ -23,6 +23,7 @@ constexpr int SY_MAX_GROUP = 16;      // CTAs per matrix (chosen at launch: SMs 
 constexpr int SY_MAX_BATCH = 64;
 constexpr int SY_THREADS = 512;
 constexpr int SY_MAX_N = 4096;        // five vectors of n doubles in shared memory
+constexpr int SY_SMEM_MAX = 226 * 1024;   // dynamic shared memory of the tridiagonalisation (static: < 1 KB)
 
 struct SytrdArgs {
     double* A;            // [batch][nmax][nmax] slots; matrix b is n_of[b] x n_of[b] (leading dimension n_of[b]) at A + b * nmax * nmax
@@ -35,6 +36,7 @@ struct SytrdArgs {
     double* pbuf;         // [batch][nmax]   exchange of A v, even columns
     double* part;         // [batch][2][SY_MAX_GROUP]  exchange of the partial sums of p'v (even / odd columns)
     unsigned int* bar;    // [batch]      group barrier counters (zeroed before the launch)
+    int resident;         // rows per CTA kept in shared memory for the whole factorisation (its last owned rows, the longest-lived ones)
 };
 
 // barrier among the `group` CTAs of one matrix (all resident: cooperative launch); counter grows monotonically
@@ -63,6 +65,11 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
     double* v_cur = sy_smem + 2 * npad;
     double* buf = sy_smem + 3 * npad;    // staging: next column / A v
     double* rowbuf = sy_smem + 4 * npad; // pivot row of the next step, fetched together with A v
+    // The last `resident` rows this CTA owns live in shared memory: row i is read and written once per column step j < i, so the rows
+    // at the bottom carry most of the traffic (the bottom 28 % of the rows: 41 % of it) -- the kernel is bound by L2 bandwidth.
+    double* res = sy_smem + 5 * npad;
+    const int owned = (n - r + SY_GROUP - 1) / SY_GROUP;                 // rows r, r + G, ...
+    const int l_res0 = max(0, owned - a.resident);
     __shared__ double s_red[SY_THREADS / 32];
     __shared__ double s_scalar[4];       // beta, tau, scale of the current step; p'v
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SY_THREADS / 32;
@@ -77,6 +84,11 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
     unsigned int* bar = a.bar + b;
     unsigned int epoch = 0;
     for (int i = tid; i < npad; i += SY_THREADS) { v_prev[i] = 0.0; w_prev[i] = 0.0; v_cur[i] = 0.0; }
+    for (int l = l_res0 + warp; l < owned; l += nwarps) {
+        const double* src = A + (size_t)(r + SY_GROUP * l) * n;
+        double* dst = res + (size_t)(l - l_res0) * npad;
+        for (int c = lane; c < n; c += 32) dst[c] = __ldcg(&src[c]);
+    }
     __syncthreads();
 
     // Column jn of the current matrix = its row jn (symmetry), which its owner finished updating in the previous pass; with the
@@ -131,7 +143,8 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
             for (int l = l0 + warp; ; l += nwarps) {
                 const int i = r + SY_GROUP * l;
                 if (i >= n) break;
-                double* row = A + (size_t)i * n;
+                const bool in_smem = l >= l_res0;
+                double* row = in_smem ? res + (size_t)(l - l_res0) * npad : A + (size_t)i * n;
                 const double vpi = v_prev[i], wpi = w_prev[i];
                 double acc = 0.0;
                 if ((n & 1) == 0) {
@@ -168,6 +181,11 @@ __global__ void __launch_bounds__(SY_THREADS, 1) crm_sytrd_kernel(SytrdArgs a) {
                         row[c] = a0;
                         acc += a0 * v_cur[c];
                     }
+                }
+                if (in_smem && i == j + 1) {           // pivot row of the next step: every CTA reads it from global memory after the barrier
+                    __syncwarp();
+                    double* grow = A + (size_t)i * n;
+                    for (int c = j + 1 + lane; c < n; c += 32) grow[c] = row[c];
                 }
                 acc = warp_sum(acc);
                 if (lane == 0) { pbuf[i] = acc; pv += acc * v_cur[i]; }

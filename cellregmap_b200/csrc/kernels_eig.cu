@@ -121,7 +121,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
     // 1. tridiagonalisation: every group of SY_GROUP CTAs must be resident -> cooperative launch
     {
         static bool attr = false;
-        if (!attr) { CRM_CUDA(cudaFuncSetAttribute(crm_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * (SY_MAX_N + 1) * 8)); attr = true; }
+        if (!attr) { CRM_CUDA(cudaFuncSetAttribute(crm_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_MAX)); attr = true; }
         static int sms = 0;
         if (!sms) { int dev = 0; CRM_CUDA(cudaGetDevice(&dev)); CRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
         SytrdArgs sa{};
@@ -131,9 +131,16 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
         sa.group = std::max(1, std::min(SY_MAX_GROUP, sms / std::max(batch, group_batch)));
         for (int b = 0; b < batch; b++) sa.n_of[b] = sz.n_of[b];
         sa.A = A; sa.nmax = n; sa.batch = batch; sa.d = d; sa.e = e; sa.tau = tau; sa.xbuf = xbuf; sa.pbuf = pbuf; sa.part = part; sa.bar = bar;
+        // shared memory left after the five work vectors holds the last rows each CTA owns (CRM_SYTRD_RESIDENT=0: none)
+        const size_t npad = (size_t)((n + 1) & ~1), base = 5 * npad * 8;
+        static const int res_env = [] { const char* v = getenv("CRM_SYTRD_RESIDENT"); return v ? atoi(v) : -1; }();
+        const int owned_max = (n + sa.group - 1) / sa.group;
+        sa.resident = base < (size_t)SY_SMEM_MAX ? (int)std::min<size_t>((size_t)owned_max, ((size_t)SY_SMEM_MAX - base) / (npad * 8)) : 0;
+        if (res_env >= 0) sa.resident = std::min(sa.resident, res_env);
+        const size_t smem = std::max(base + (size_t)sa.resident * npad * 8, (size_t)5 * (n + 1) * 8);
         void* params[] = {&sa};
         SlowSection sec("eig: cooperative launch of sytrd");
-        CRM_CUDA(cudaLaunchCooperativeKernel((const void*)crm_sytrd_kernel, dim3((unsigned)(batch * sa.group)), dim3(SY_THREADS), params, (size_t)5 * (n + 1) * 8, st));
+        CRM_CUDA(cudaLaunchCooperativeKernel((const void*)crm_sytrd_kernel, dim3((unsigned)(batch * sa.group)), dim3(SY_THREADS), params, smem, st));
         count_launch();
     }
     tr.mark("sytrd");

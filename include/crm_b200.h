@@ -119,6 +119,11 @@ CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0
 CRM_API int crm_set_background_factors(crm_handle_t h, const double* hK, int64_t ldhk, int q, const double* M, int r, int* accepted,
                                        void* stream);
 
+/* Columns of the basis operand that the rotation contracts per SNP: the expanded basis [Hx | Hx.E0_j] (full_rows = (1 + k0) * ld)
+ * and what is contracted once a structure of the background has been accepted (used_rows; equal to full_rows otherwise).
+ * bench.py scales the algorithmic flop of the rotation by used_rows / full_rows to report the work actually executed. */
+CRM_API int crm_rotation_rows(crm_handle_t h, int64_t* full_rows, int64_t* used_rows);
+
 /*
  * New phenotype y (n doubles, device) for the same cells, contexts, covariates and background (extension): refreshes only
  * the y-dependent state of the model; the Gram of the half-basis and the per-rho eigendecompositions are kept.  Equivalent
