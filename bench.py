@@ -542,7 +542,7 @@ def run_b200_arm(a):
         Gdon_d = torch.from_numpy(Gd).to(dev)
 
         def step_donor():
-            model = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev)
+            model = api._make_interaction_model(y_d, E_d, W_d, None, None, hK_d, device=dev, donor_level=True)
             return stack5(model._scan_interaction_device(Gdon_d, donor_index=donor_d))
 
         warm_up(step_donor, 2, at_most_extra=6)

@@ -153,7 +153,8 @@ class CellRegMap:
         u ~ N(0, v1 (1-rho1) K o E2 E2'),  eps ~ N(0, v2 I)
     """
 
-    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None, device=None, _prefetch=None, _group=None):
+    def __init__(self, y, E, W=None, Ls=None, E1=None, hK=None, device=None, _prefetch=None, _group=None, _background_factors=None,
+                 _integer_genotypes_likely=False):
         self._device = _device(device)
         dev = self._device
         self._y = _to_dev(y, dev).flatten()
@@ -210,6 +211,16 @@ class CellRegMap:
                 basis_cols = (1 + int(self._E0.shape[1])) * (width + (width & 1))
                 _lib.call("crm_stage_genotypes_typed", self._handle, ctypes.c_void_p(geno.ptr), geno.dtype, geno.ld, geno.rows, geno.p, basis_cols, _stream())
             self._prefetched = (_prefetch, geno)
+        self._background_factors = None
+        if _background_factors is not None:
+            # Ls = get_L_values(hK, E) with U S = E V: declared ahead of the set-up, which verifies it (crm_set_background_factors)
+            hKf, V = _background_factors
+            self._background_factors = (hKf, np.ascontiguousarray(V, dtype=np.float64))
+            hKf, V = self._background_factors
+            _lib.call("crm_set_background_factors", self._handle, _ptr(hKf), hKf.stride(0), int(hKf.shape[1]),
+                      V.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(V.shape[1]), None, _stream())
+        if _integer_genotypes_likely:
+            _lib.call("crm_hint_integer_genotypes", self._handle, 1)
         rho = np.ascontiguousarray(np.asarray(self._rho1, dtype=np.float64))
         mL = 0 if Lcat is None else int(Lcat.shape[1])
         setup_args = (self._handle, _ptr(self._y), _ptr(self._W), self._W.stride(0), _ptr(self._E0),
@@ -248,6 +259,12 @@ class CellRegMap:
             for j, r in enumerate(range(other, R, world)):
                 _lib.call("crm_import_basis", self._handle, r, _ptr(everything[other, j]), _stream())
         _lib.call("crm_setup_finish", self._handle, _stream())
+
+    def _structured_rotation(self):
+        """True when the rotation contracts the compact basis of a structured background (crm_rotation_rows)."""
+        full, used = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.call("crm_rotation_rows", self._handle, ctypes.byref(full), ctypes.byref(used))
+        return used.value < full.value
 
     def _declare_background_factors(self, hK, V):
         """Tells the library that Ls = get_L_values(hK, E) with U S = E V (crm_set_background_factors); verified there."""
@@ -474,35 +491,36 @@ def run_association_fast(y, W, E, G, hK=None, *, donor_index=None):
     return crm.scan_association_fast(G, donor_index=donor_index)
 
 
-def _make_interaction_model(y, E, W, E1, E2, hK, device=None, prefetch=None, group=None):
+def _make_interaction_model(y, E, W, E1, E2, hK, device=None, prefetch=None, group=None, donor_level=False):
     dev = _device(device)
-    E1 = E if E1 is None else E1
+    E_dev = _to_dev(E, dev)
+    E1 = E_dev if E1 is None else E1
     same_contexts = E2 is None or E2 is E
-    E2 = E if E2 is None else E2
-    Ls, V, hK_dev = None, None, None
+    E2_dev = E_dev if same_contexts else _to_dev(E2, dev)
+    Ls, factors = None, None
     if hK is not None:
         hK_dev = _to_dev(hK, dev, two_d=True)
-        Ls, V = _L_concat(hK_dev, _to_dev(E2, dev), with_map=True)
-    crm = CellRegMap(y=y, E=E, W=W, E1=E1, Ls=Ls, device=dev, _prefetch=prefetch, _group=group)
-    if V is not None and not same_contexts:
-        same_contexts = tuple(E2.shape) == tuple(E.shape) and bool(torch.equal(_to_dev(E2, dev), crm._E0))
-    if V is not None and same_contexts:
-        # the background was built from the tested contexts themselves: L.E_j products are symmetric triple products (see the header)
-        crm._declare_background_factors(hK_dev, V)
-    return crm
+        Ls, V = _L_concat(hK_dev, E2_dev, with_map=True)
+        if V is not None and not same_contexts:
+            same_contexts = tuple(E2_dev.shape) == tuple(E_dev.shape) and bool(torch.equal(E2_dev, E_dev))
+        if V is not None and same_contexts:
+            # the background was built from the tested contexts themselves: L.E_j products are symmetric triple products (see the header)
+            factors = (hK_dev, V)
+    return CellRegMap(y=y, E=E_dev, W=W, E1=E1, Ls=Ls, device=dev, _prefetch=prefetch, _group=group, _background_factors=factors,
+                      _integer_genotypes_likely=not donor_level)
 
 
 def run_interaction(y, E, G, W=None, E1=None, E2=None, hK=None, idx_G=None, *, donor_index=None):
     """Interaction test (reference :547-587).  NB `idx_G` is forwarded as scan_interaction's second
     positional argument, i.e. it permutes the rows of E (reference :586); kept.
     Extension: with `donor_index` (n,), G is the d x p donor-level genotype matrix (G_cells = G[donor_index])."""
-    crm = _make_interaction_model(y, E, W, E1, E2, hK, prefetch=G if donor_index is None else None)
+    crm = _make_interaction_model(y, E, W, E1, E2, hK, prefetch=G if donor_index is None else None, donor_level=donor_index is not None)
     return crm.scan_interaction(G, idx_G, donor_index=donor_index)
 
 
 def estimate_betas(y, W, E, G, maf=None, E1=None, E2=None, hK=None, *, donor_index=None):
     """Effect-size estimator (reference :640-682): returns (beta_g (p,), beta_gxe (1, n, p))."""
-    crm = _make_interaction_model(y, E, W, E1, E2, hK)
+    crm = _make_interaction_model(y, E, W, E1, E2, hK, donor_level=True)      # (no rotation of genotypes through digit planes here)
     if maf is None:      # reference: MAF of the expanded matrix
         maf = compute_maf(G if donor_index is None else crm._expand(G, donor_index))
     return crm.predict_interaction(G, maf, donor_index=donor_index)

@@ -49,6 +49,7 @@ SIGNATURES = {
     "crm_set_test_contexts": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_void_p]),
     "crm_set_background_factors": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                                   ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    "crm_hint_integer_genotypes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "crm_rotation_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "crm_update_phenotype": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_void_p]),
     "crm_set_donors": (ctypes.c_int, [ctypes.c_void_p, c_int32_p, c_int32_p, ctypes.c_int64, ctypes.c_void_p]),

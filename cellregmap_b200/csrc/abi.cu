@@ -160,6 +160,14 @@ struct Handle {
     int kr_q = 0, kr_r = 0;
     long long kr_R1 = 0, kr_R2 = 0, kr_R3 = 0, kr_rows = 0;
     DevBuf krK, krM, Cc;
+    // declaration made before crm_setup: applied (and verified, result read at the end of the set-up) inside it
+    bool kr_pending = false, kr_unverified = false;
+    const double* kr_pending_hK = nullptr; long long kr_pending_ld = 0; int kr_pending_q = 0, kr_pending_r = 0;
+    const double* kr_pending_M = nullptr;
+    // digit planes built during the set-up on a side stream (crm_hint_integer_genotypes): the first int8 rotation waits for planes_ev
+    bool early_planes = false, planes_ev_pending = false;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_ev = nullptr, planes_ev = nullptr;
     int hxe_blocks = 0;   // context blocks j held by HxE at a time: kexp = whole basis resident, fewer = streamed in groups
     DevBuf Hx, Eext, A2, gram, S, yr, Wr, Tt, stats, eigwork, eigmat, eigval, devinfo;
     // null-model state for the association scans
@@ -605,6 +613,32 @@ static int ensure_column_sums(Handle* h, cudaStream_t st) {
 
 // room for the digit planes of [Hx | Hx.E0_j]?  (cudaMemGetInfo costs milliseconds: only asked for large requests); extra = further
 // bytes the caller needs next to them
+// Applies a declared structure of the background (crm_set_background_factors): copies the factors, starts the verification against the
+// L columns of Hx (result in devinfo[2 R], non-zero = the claim does not hold) and lays out the compact rows.  h->kr is set tentatively:
+// the caller reads the flag (at once, or with the read-back that ends the set-up).  *applicable = false: shapes the structure cannot
+// describe or the expansion kernel does not take -- nothing is changed, the full basis is used.
+static int kr_apply(Handle* h, const double* hK, long long ldhk, int q, const double* M, int r, cudaStream_t st, bool* applicable) {
+    *applicable = false;
+    h->kr = false;
+    const int rp = (r + KR_IT - 1) / KR_IT * KR_IT;
+    if ((long long)r * q != h->mL || r > h->k0 || (size_t)h->k0 * rp * sizeof(double) > 48 * 1024) return CRM_OK;
+    const long long R1 = h->ldH, R2 = R1 + (long long)h->k0 * h->k1, R3 = R2 + (long long)h->k0 * (1 + h->c);
+    const long long rows = round_up(R3 + (long long)(h->k0 * (h->k0 + 1) / 2) * q, 2);     // even: leading dimension of fp64 TMA operands
+    if (rows >= (long long)h->kexp * h->ldH) return CRM_OK;                                   // nothing to gain (tiny k0)
+    CRM_CHECK(h->krK.reserve((size_t)h->n * q * 8));
+    CRM_CHECK(h->krM.reserve((size_t)h->k0 * r * 8));
+    int* flag = h->devinfo.as<int>() + 2 * h->R;
+    CRM_CUDA(cudaMemcpy2DAsync(h->krK.ptr, (size_t)q * 8, hK, (size_t)ldhk * 8, (size_t)q * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+    CRM_CUDA(cudaMemcpyAsync(h->krM.ptr, M, (size_t)h->k0 * r * 8, cudaMemcpyHostToDevice, st));
+    CRM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    kr_check_kernel<<<blocks_for(h->n * (long long)r * q, 256), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->k1, h->Eext.as<double>(), h->epitch, h->k0, h->krK.as<double>(), q,
+                                                                             h->krM.as<double>(), r, h->n, flag);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    h->kr = true; h->kr_unverified = true; h->kr_q = q; h->kr_r = r;
+    h->kr_R1 = R1; h->kr_R2 = R2; h->kr_R3 = R3; h->kr_rows = rows;
+    *applicable = true;
+    return CRM_OK;
+}
 static int kr_expand(Handle* h, const double* S, long long lds, long long B, double* C, cudaStream_t st) {
     const int rp = (h->kr_r + KR_IT - 1) / KR_IT * KR_IT;
     const size_t smem = (size_t)h->k0 * rp * sizeof(double);
@@ -659,6 +693,37 @@ static int build_planes(Handle* h, cudaStream_t on) {
     CRM_CHECK(oz_launch_product_slices(Hx + h->m, ldH, yw, Ee, h->epitch, 1, k0, n, expo, A8, Mp, Kp, h->kr_R2, yw, on));
     return oz_launch_product_slices(hK, q, q, A2, h->ld2, 1 + k0, npair, n, expo, A8, Mp, Kp, h->kr_R3, q, on);
 }
+// work of the side stream on the digit planes must be over before `st` touches them (or hands their memory on)
+static int wait_early_planes(Handle* h, cudaStream_t st) {
+    if (!h->planes_ev_pending) return CRM_OK;
+    CRM_CUDA(cudaStreamWaitEvent(st, h->planes_ev, 0));
+    h->planes_ev_pending = false;
+    return CRM_OK;
+}
+// digit planes on the side stream, ordered after everything enqueued on `st` so far (crm_hint_integer_genotypes; called from the set-up)
+static int start_early_planes(Handle* h, cudaStream_t st) {
+    static const bool off = [] { const char* v = getenv("CRM_EARLY_PLANES"); return v && atoi(v) == 0; }();
+    if (off || h->rotation_mode == 1 || h->oz_built) return CRM_OK;
+    const long long Mtot = plane_rows(h), Mp = round_up(Mtot, 16), Kp = round_up(h->n, 16);
+    bool fits = true;
+    CRM_CHECK(planes_fit(h, 0.0, &fits));
+    if (!fits) return CRM_OK;
+    CRM_CHECK(wait_early_planes(h, st));
+    if (h->A8.reserve((size_t)OZAKI_SLICES * Mp * Kp) != CRM_OK) { cudaGetLastError(); return CRM_OK; }
+    CRM_CHECK(h->a8expo.reserve((size_t)Mtot * sizeof(int)));
+    if (!h->side_stream) {
+        CRM_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        CRM_CUDA(cudaEventCreateWithFlags(&h->side_ev, cudaEventDisableTiming));
+        CRM_CUDA(cudaEventCreateWithFlags(&h->planes_ev, cudaEventDisableTiming));
+    }
+    CRM_CUDA(cudaEventRecord(h->side_ev, st));
+    CRM_CUDA(cudaStreamWaitEvent(h->side_stream, h->side_ev, 0));
+    CRM_CHECK(build_planes(h, h->side_stream));
+    CRM_CUDA(cudaEventRecord(h->planes_ev, h->side_stream));
+    h->planes_ev_pending = true;
+    h->oz_built = true; h->oz_built_kr = kr_active(h);
+    return CRM_OK;
+}
 static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStream_t st, int* used) {
     *used = 0;
     const long long B = blk.b;
@@ -707,6 +772,7 @@ static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStre
         if ((double)Kp * 64.0 * (double)std::max(flags[1], 1) >= 2147483648.0) return CRM_OK;   // int32 accumulation could overflow
     }
     tr.mark("genotypes->int8");
+    CRM_CHECK(wait_early_planes(h, st));
     if (!h->oz_built || h->oz_built_kr != compact) {
         if (h->A8.reserve(a8_bytes) != CRM_OK) return CRM_OK;      // no room after all: the fp64 route takes over
         CRM_CHECK(h->a8expo.reserve((size_t)Mtot * sizeof(int)));
@@ -846,9 +912,13 @@ static int finish_setup(Handle* h, cudaStream_t st) {
     build_yw_kernel<<<blocks_for(std::max<long long>((long long)R * (1 + c) * mp, (long long)(1 + c) * (1 + c)), 256), 256, 0, st>>>(
         h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
-    std::vector<int> info(2 * R, 0);
-    CRM_CUDA(cudaMemcpyAsync(info.data(), h->devinfo.as<int>(), (size_t)(2 * R) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    std::vector<int> info(2 * R + 1, 0);
+    CRM_CUDA(cudaMemcpyAsync(info.data(), h->devinfo.as<int>(), (size_t)(2 * R + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
     CRM_CUDA(cudaStreamSynchronize(st));
+    if (h->kr_unverified) {               // verdict on the structure declared before the set-up (kr_apply)
+        h->kr_unverified = false;
+        if (info[2 * R] != 0) { h->kr = false; if (h->oz_built && h->oz_built_kr) h->oz_built = false; }
+    }
     h->max_rank = 0;
     for (int r = 0; r < R; r++) {
         if (info[r] != 0) { set_error("cusolverDnDsyevd did not converge for grid point %d (devInfo=%d)", r, info[r]); return CRM_ERR_SOLVER; }
@@ -940,6 +1010,12 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
         h->rotation_mode = (rm && !strcmp(rm, "dmma")) ? 1 : (rm && !strcmp(rm, "int8")) ? 2 : 0;
     }
     CRM_CHECK(build_test_contexts(h, E0, lde0, st));
+    h->kr_unverified = false;
+    if (h->kr_pending) {            // structure declared ahead of the set-up: verified on the device now, the verdict is read with the solver status below
+        bool applicable = false;
+        CRM_CHECK(kr_apply(h, h->kr_pending_hK, h->kr_pending_ld, h->kr_pending_q, h->kr_pending_M, h->kr_pending_r, st, &applicable));
+        h->kr_pending = false;
+    }
     delete sec;
     sec = new SlowSection("set-up: gram launch");
 
@@ -1014,8 +1090,12 @@ static int do_setup(Handle* h, const double* y, const double* W, long long ldw, 
             int* lib_info = reinterpret_cast<int*>(e.quality.as<double>() + nsel);
             CRM_CUDA(cudaMemsetAsync(lib_info, 0, (size_t)2 * nsel * 4, st));
             tr.mark("scaled grams");
+            // The digit planes of the basis do not depend on the decompositions: with crm_hint_integer_genotypes they are built on a side
+            // stream once the tridiagonalisation (a cooperative kernel that wants every SM) has finished, next to the latency-bound phases
+            // that follow it (multisection, inverse iteration, back-transformation of 1 020-column problems leave most SMs idle).
+            std::function<int()> planes_hook = [h, st]() -> int { return start_early_planes(h, st); };
             CRM_CHECK(eig_batched(e.solver, e.blas, e.mat.as<double>(), n_of.data(), m, nsel, e.val.as<double>(), e.vec.as<double>(), e.quality.as<double>(), e.ws.ptr,
-                                  e.work.as<double>(), std::max(lib_lwork, lwork), lib_info, st, R, sel.data()));
+                                  e.work.as<double>(), std::max(lib_lwork, lwork), lib_info, st, R, sel.data(), h->early_planes ? &planes_hook : nullptr));
             tr.mark("batched eigensolver");
             std::vector<double> q(nsel); std::vector<int> li(2 * nsel);
             CRM_CUDA(cudaMemcpyAsync(q.data(), e.quality.ptr, (size_t)nsel * 8, cudaMemcpyDeviceToHost, st));
@@ -1875,6 +1955,7 @@ int crm_destroy(crm_handle_t h) {
         cudaEvent_t drained = h->impl.ev_copy[0];
         if (cudaEventRecord(drained, h->impl.copy_stream) == cudaSuccess) cudaStreamWaitEvent(st, drained, 0);
     }
+    if (h->impl.planes_ev_pending) { cudaStreamWaitEvent(st, h->impl.planes_ev, 0); h->impl.planes_ev_pending = false; }
     {
         AllocScope alloc_scope(st);
         if (h->impl.adopt_ev) { cudaStreamWaitEvent(st, h->impl.adopt_ev, 0); cudaEventDestroy(h->impl.adopt_ev); h->impl.adopt_ev = nullptr; }
@@ -1899,6 +1980,7 @@ int crm_destroy(crm_handle_t h) {
         cudaStreamDestroy(h->impl.copy_stream);     // asynchronous: resources are released once the stream has drained
         for (int i = 0; i < 2; i++) { cudaEventDestroy(h->impl.ev_copy[i]); cudaEventDestroy(h->impl.ev_done[i]); }
     }
+    if (h->impl.side_stream) { cudaStreamDestroy(h->impl.side_stream); cudaEventDestroy(h->impl.side_ev); cudaEventDestroy(h->impl.planes_ev); }
     for (cudaEvent_t e : h->impl.stage_events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->impl.prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->impl.prof_oz_events) cudaEventDestroy(e);
@@ -2016,37 +2098,34 @@ int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0, void* 
 
 int crm_set_background_factors(crm_handle_t h, const double* hK, int64_t ldhk, int q, const double* M, int r, int* accepted, void* stream) {
     if (accepted) *accepted = 0;
-    if (!h || !h->impl.ready) { set_error("crm_set_background_factors: handle not set up"); return CRM_ERR_STATE; }
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
     Handle& H = h->impl;
     if (!hK || !M || q <= 0 || r <= 0 || ldhk < q) { set_error("crm_set_background_factors: bad arguments"); return CRM_ERR_INVALID; }
+    if (!H.ready) {
+        // before crm_setup: applied by the set-up once its operands exist (hK and M must stay valid until crm_setup returns)
+        H.kr_pending = true; H.kr_pending_hK = hK; H.kr_pending_ld = ldhk; H.kr_pending_q = q; H.kr_pending_r = r; H.kr_pending_M = M;
+        return CRM_OK;
+    }
     H.kr = false;
-    const int rp = (r + KR_IT - 1) / KR_IT * KR_IT;
-    // shapes the structure cannot describe, or that the expansion kernel does not take: not an error, the full basis is used
-    if ((long long)r * q != H.mL || r > H.k0 || (size_t)H.k0 * rp * sizeof(double) > 48 * 1024) return CRM_OK;
     CRM_CUDA(cudaSetDevice(H.device));
     cudaStream_t st = (cudaStream_t)stream;
     AllocScope alloc_scope(st); H.last_stream = st;
     CRM_CHECK(adopt_buffers(&H, st));
-    CRM_CHECK(H.krK.reserve((size_t)H.n * q * 8));
-    CRM_CHECK(H.krM.reserve((size_t)H.k0 * r * 8));
-    CRM_CHECK(H.ozflags.reserve(64));
-    CRM_CUDA(cudaMemcpy2DAsync(H.krK.ptr, (size_t)q * 8, hK, (size_t)ldhk * 8, (size_t)q * 8, (size_t)H.n, cudaMemcpyDeviceToDevice, st));
-    CRM_CUDA(cudaMemcpyAsync(H.krM.ptr, M, (size_t)H.k0 * r * 8, cudaMemcpyHostToDevice, st));
-    CRM_CUDA(cudaMemsetAsync(H.ozflags.ptr, 0, 4 * sizeof(int), st));
-    kr_check_kernel<<<blocks_for(H.n * (long long)r * q, 256), 256, 0, st>>>(H.Hx.as<double>(), H.ldH, H.k1, H.Eext.as<double>(), H.epitch, H.k0, H.krK.as<double>(), q,
-                                                                            H.krM.as<double>(), r, H.n, H.ozflags.as<int>());
-    CRM_CUDA(cudaGetLastError()); count_launch();
+    bool applicable = false;
+    CRM_CHECK(kr_apply(&H, hK, ldhk, q, M, r, st, &applicable));
+    if (!applicable) return CRM_OK;
     int flag = 1;
-    CRM_CUDA(cudaMemcpyAsync(&flag, H.ozflags.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CRM_CUDA(cudaMemcpyAsync(&flag, H.devinfo.as<int>() + 2 * H.R, sizeof(int), cudaMemcpyDeviceToHost, st));
     CRM_CUDA(cudaStreamSynchronize(st));
-    if (flag != 0) return CRM_OK;                 // the basis is not the declared product: ignored
-    H.kr = true; H.kr_q = q; H.kr_r = r;
-    H.kr_R1 = H.ldH;
-    H.kr_R2 = H.kr_R1 + (long long)H.k0 * H.k1;
-    H.kr_R3 = H.kr_R2 + (long long)H.k0 * (1 + H.c);
-    H.kr_rows = round_up(H.kr_R3 + (long long)(H.k0 * (H.k0 + 1) / 2) * q, 2);     // even: leading dimension of fp64 TMA operands
-    if (H.kr_rows >= (long long)H.kexp * H.ldH) H.kr = false;     // nothing to gain (tiny k0)
+    H.kr_unverified = false;
+    if (flag != 0) { H.kr = false; return CRM_OK; }                 // the basis is not the declared product: ignored
     if (accepted) *accepted = H.kr ? 1 : 0;
+    return CRM_OK;
+}
+
+int crm_hint_integer_genotypes(crm_handle_t h, int likely) {
+    if (!h) { set_error("null handle"); return CRM_ERR_INVALID; }
+    h->impl.early_planes = likely != 0;
     return CRM_OK;
 }
 

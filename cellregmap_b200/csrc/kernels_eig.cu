@@ -89,7 +89,7 @@ int eig_workspace_bytes(int n, int batch, size_t* bytes) {
 // largest residual |T z - lambda z|_inf / |T| over the vectors (NaN/inf when the Cholesky-QR step broke down).
 // ws: eig_workspace_bytes(n, batch) bytes; lib_work: at least lib_lwork doubles (max of potrf / ormtr needs, queried by the caller).
 int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n, int batch, double* W, double* V, double* quality, void* ws, double* lib_work,
-                int lib_lwork, int* info_dev, cudaStream_t st, int group_batch, const int* ids) {
+                int lib_lwork, int* info_dev, cudaStream_t st, int group_batch, const int* ids, const std::function<int()>* after_sytrd) {
     cusolverDnHandle_t solver = (cusolverDnHandle_t)solver_v;
     cublasHandle_t blas = (cublasHandle_t)blas_v;
     if (n < 2 || n > SY_MAX_N || batch < 1 || batch > SY_MAX_BATCH) { set_error("eig_batched: n = %d outside [2, %d] or batch = %d outside [1, %d]", n, SY_MAX_N, batch, SY_MAX_BATCH); return CRM_ERR_UNSUPPORTED; }
@@ -144,6 +144,7 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
         count_launch();
     }
     tr.mark("sytrd");
+    if (after_sytrd && *after_sytrd) CRM_CHECK((*after_sytrd)());
     // 2. eigenvalues
     crm_tridiag_bisect_kernel<<<dim3((unsigned)(((long long)n * BS_LANES + 255) / 256), (unsigned)batch), 256, (size_t)2 * n * 8, st>>>(d, e, sz, W, tnorm);
     CRM_CUDA(cudaGetLastError()); count_launch();

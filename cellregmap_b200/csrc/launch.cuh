@@ -1,5 +1,6 @@
 // Host-callable launchers of the kernels in this directory (each defined in its own translation unit).
 #pragma once
+#include <functional>
 #include "common.cuh"
 #include "args.cuh"
 
@@ -85,7 +86,9 @@ int oz_int8_gemm(const int8_t* A8, long long Mrows, const int8_t* Gt8, long long
 int eig_workspace_bytes(int n, int batch, size_t* bytes);
 int eig_lib_lwork(void* solver, int n, int* lwork);
 int eig_batched(void* solver, void* blas, double* A, const int* n_of, int n, int batch, double* W, double* V, double* quality, void* ws, double* lib_work, int lib_lwork,
-                int* info_dev, cudaStream_t st, int group_batch = 0, const int* ids = nullptr);
+                int* info_dev, cudaStream_t st, int group_batch = 0, const int* ids = nullptr, const std::function<int()>* after_sytrd = nullptr);
+// after_sytrd: called on the host right after the tridiagonalisation has been enqueued (work that may share the device with the
+// latency-bound phases that follow)
 // group_batch: size of the batch this one is a share of (0: itself); ids: position of each matrix in that batch (seeds of the start vectors).
 // With both given, a matrix is decomposed to the same bits whichever share of the batch it is solved in.
 

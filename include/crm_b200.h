@@ -113,11 +113,19 @@ CRM_API int crm_set_test_contexts(crm_handle_t h, const double* E0, int64_t lde0
  * (plus Hx itself and the products of E1, y and W) and rebuilds the rest with the k0 x r map -- 0.56 of the contraction work and of
  * the digit planes at k0 = 20.  The library verifies the claim against the basis it was set up with (one pass over L, one
  * synchronisation of `stream`); *accepted = 1 when the structure is used, 0 when it does not hold or does not apply (then the call
- * changes nothing).  Call after crm_setup / crm_setup_finish; crm_set_test_contexts drops the declaration (tested contexts that
- * differ from the contexts inside L have no such symmetry).  CRM_KR=0 in the environment ignores it.
+ * changes nothing).  Two ways to call it.  After crm_setup / crm_setup_finish: verified at once.  Before crm_setup (hK and M must
+ * stay valid until the set-up returns): applied and verified inside the set-up without an extra synchronisation, *accepted stays 0 and
+ * crm_rotation_rows tells afterwards whether the compact form is in use.  crm_set_test_contexts drops the declaration (tested
+ * contexts that differ from the contexts inside L have no such symmetry).  CRM_KR=0 in the environment ignores it.
  */
 CRM_API int crm_set_background_factors(crm_handle_t h, const double* hK, int64_t ldhk, int q, const double* M, int r, int* accepted,
                                        void* stream);
+
+/* Hint before crm_setup: the scans of this model will most likely receive integer (or affine-integer) dosages at cell level.  The
+ * set-up then builds the int8 digit planes of the basis on a side stream next to the latency-bound phases of its eigensolver instead
+ * of leaving them to the first rotation (7 ms of a 147 ms step at BASELINE configs[2]); costs nothing but that kernel time if the
+ * genotypes turn out to be real-valued.  CRM_EARLY_PLANES=0 ignores the hint. */
+CRM_API int crm_hint_integer_genotypes(crm_handle_t h, int likely);
 
 /* Columns of the basis operand that the rotation contracts per SNP: the expanded basis [Hx | Hx.E0_j] (full_rows = (1 + k0) * ld)
  * and what is contracted once a structure of the background has been accepted (used_rows; equal to full_rows otherwise).
