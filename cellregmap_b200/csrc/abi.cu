@@ -253,17 +253,29 @@ __global__ void build_hxe_kernel(const double* Hx, int ldH, const double* Eext, 
 //   R3 + pair(l, j) q + cc        hK[:, cc] * E0[:, l] * E0[:, j]         l <= j, pair = j (j + 1) / 2 + l  (the pair columns of A2)
 // Full layout (row = j ldH + a): block j >= 1, column k1 + i q + cc  =  sum_l M[l][i] * compact[R3 + pair(l, j-1) q + cc].
 // does the declared structure reproduce the L columns of Hx?  flag |= 1 on the first entry that does not
-__global__ void kr_check_kernel(const double* Hx, int ldH, int k1, const double* Eext, int epitch, int k0, const double* hK, int q, const double* M, int r,
-                                long long n, int* flag) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long per = (long long)r * q;
-    if (idx >= n * per) return;
-    const long long i = idx / per; const int col = (int)(idx - i * per); const int ii = col / q, cc = col - ii * q;
-    double us = 0.0, mag = 0.0;
-    for (int l = 0; l < k0; l++) { const double t = Eext[i * epitch + 1 + l] * M[l * r + ii]; us += t; mag += fabs(t); }
-    const double hk = hK[i * q + cc];
-    const double want = us * hk, got = Hx[i * ldH + k1 + col];
-    if (!(fabs(got - want) <= 1e-11 * mag * fabs(hk) + 1e-290)) atomicOr(flag, 1);
+constexpr int KR_CHECK_CELLS = 8;
+__global__ void __launch_bounds__(256) kr_check_kernel(const double* Hx, int ldH, int k1, const double* Eext, int epitch, int k0, const double* hK, int q, const double* M,
+                                                       int r, long long n, int* flag) {
+    extern __shared__ double kc_smem[];               // us[cell][ii], mag[cell][ii] of KR_CHECK_CELLS cells
+    double* us = kc_smem; double* mag = kc_smem + KR_CHECK_CELLS * r;
+    const long long i0 = (long long)blockIdx.x * KR_CHECK_CELLS;
+    for (int t = threadIdx.x; t < KR_CHECK_CELLS * r; t += blockDim.x) {
+        const int ci = t / r, ii = t - ci * r; const long long i = i0 + ci;
+        double u = 0.0, a = 0.0;
+        if (i < n) for (int l = 0; l < k0; l++) { const double v = Eext[i * epitch + 1 + l] * M[l * r + ii]; u += v; a += fabs(v); }
+        us[t] = u; mag[t] = a;
+    }
+    __syncthreads();
+    const int per = r * q;
+    bool bad = false;
+    for (int t = threadIdx.x; t < KR_CHECK_CELLS * per; t += blockDim.x) {
+        const int ci = t / per, col = t - ci * per, ii = col / q, cc = col - ii * q; const long long i = i0 + ci;
+        if (i >= n) break;
+        const double hk = hK[i * q + cc];
+        const double want = us[ci * r + ii] * hk, got = Hx[i * ldH + k1 + col];
+        if (!(fabs(got - want) <= 1e-11 * mag[ci * r + ii] * fabs(hk) + 1e-290)) bad = true;
+    }
+    if (bad) atomicOr(flag, 1);
 }
 // full rotation output C[(s kexp + j)][a] from the compact one S[s][row] (one block per SNP; M in shared memory, k0 x rp)
 constexpr int KR_IT = 8;
@@ -631,8 +643,8 @@ static int kr_apply(Handle* h, const double* hK, long long ldhk, int q, const do
     CRM_CUDA(cudaMemcpy2DAsync(h->krK.ptr, (size_t)q * 8, hK, (size_t)ldhk * 8, (size_t)q * 8, (size_t)h->n, cudaMemcpyDeviceToDevice, st));
     CRM_CUDA(cudaMemcpyAsync(h->krM.ptr, M, (size_t)h->k0 * r * 8, cudaMemcpyHostToDevice, st));
     CRM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-    kr_check_kernel<<<blocks_for(h->n * (long long)r * q, 256), 256, 0, st>>>(h->Hx.as<double>(), h->ldH, h->k1, h->Eext.as<double>(), h->epitch, h->k0, h->krK.as<double>(), q,
-                                                                             h->krM.as<double>(), r, h->n, flag);
+    kr_check_kernel<<<(unsigned)((h->n + KR_CHECK_CELLS - 1) / KR_CHECK_CELLS), 256, (size_t)2 * KR_CHECK_CELLS * r * sizeof(double), st>>>(
+        h->Hx.as<double>(), h->ldH, h->k1, h->Eext.as<double>(), h->epitch, h->k0, h->krK.as<double>(), q, h->krM.as<double>(), r, h->n, flag);
     CRM_CUDA(cudaGetLastError()); count_launch();
     h->kr = true; h->kr_unverified = true; h->kr_q = q; h->kr_r = r;
     h->kr_R1 = R1; h->kr_R2 = R2; h->kr_R3 = R3; h->kr_rows = rows;

@@ -85,13 +85,22 @@ int oz_launch_mma(const int8_t* A8, long long Mp, long long Mtot, const int* exp
         return CRM_OK;
     }
     const long long units = (long long)a.m_tiles * a.n_tiles;
-    // Few tiles over a long contraction (the g^2 Grams: 2 column tiles): one CTA per tile would walk all of K alone (2 ms whatever
-    // the batch width) -> cut K into chunks, one unit per (tile, chunk), integer partial sums added in global memory.
+    // Few tiles over a long contraction (the g^2 Grams: 2 column tiles x the SNP tiles of the batch): one CTA per tile would walk all of K
+    // alone and leave SMs idle (2 tiles: 2 ms whatever the batch width; 80 tiles on 148 SMs: 46 % idle) -> cut K into chunks, one unit per
+    // (tile, chunk), integer partial sums added in global memory; chunks of >= 16 K-blocks.
     static const bool splitk_on = [] { const char* v = getenv("CRM_OZ_SPLITK"); return !(v && atoi(v) == 0); }();
-    if (splitk_on && units * 2 <= sms && a.kblocks >= 32) {
+    int ks = 1;
+    if (splitk_on && units < 2 * sms && a.kblocks >= 32) {
+        // cost of a launch in K-blocks: waves x (chunk length + ~24 K-blocks' worth of pipeline fill and integer reductions per unit)
+        double best = (double)((units + sms - 1) / sms) * (a.kblocks + 24.0);
+        for (int cand = 2; cand <= a.kblocks / 16 && (long long)cand * units <= 16LL * sms; cand++) {
+            const double cost = (double)((units * cand + sms - 1) / sms) * ((double)a.kblocks / cand + 24.0);
+            if (cost < best) { best = cost; ks = cand; }
+        }
+    }
+    if (ks > 1) {
         static bool attr3 = false;
         if (!attr3) { CRM_CUDA(cudaFuncSetAttribute(oz_mma_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZM_SMEM_BYTES)); attr3 = true; }
-        int ks = (int)std::min<long long>(sms / units, a.kblocks / 16);
         a.kchunk = (a.kblocks + ks - 1) / ks;
         ks = (a.kblocks + a.kchunk - 1) / a.kchunk;
         a.ksplit = ks;
