@@ -736,6 +736,27 @@ static int start_early_planes(Handle* h, cudaStream_t st) {
     h->oz_built = true; h->oz_built_kr = kr_active(h);
     return CRM_OK;
 }
+// the y column of Hx changed (crm_update_phenotype): only the plane rows that contain it are rebuilt -- y itself and y.E0_j
+static int refresh_y_planes(Handle* h, cudaStream_t st) {
+    if (!h->oz_built) return CRM_OK;
+    CRM_CHECK(wait_early_planes(h, st));
+    const bool compact = kr_active(h);
+    if (h->oz_built_kr != compact) { h->oz_built = false; return CRM_OK; }
+    const long long n = h->n, Mtot = plane_rows(h), Mp = round_up(Mtot, 16), Kp = round_up(n, 16);
+    const double* ycol = h->Hx.as<double>() + h->m; const double* Ee = h->Eext.as<double>();
+    int* expo = h->a8expo.as<int>(); int8_t* A8 = h->A8.as<int8_t>();
+    struct Part { int j0, nj; long long row0, rstride; } parts[2];
+    int np = 0;
+    if (compact) { parts[np++] = {0, 1, (long long)h->m, (long long)h->ldH}; parts[np++] = {1, h->k0, h->kr_R2, (long long)(1 + h->c)}; }
+    else parts[np++] = {0, h->kexp, (long long)h->m, (long long)h->ldH};
+    for (int i = 0; i < np; i++) {
+        const Part& pt = parts[i];
+        CRM_CHECK(oz_launch_fill_exponents_strided(expo, pt.row0, pt.rstride, pt.nj, st));
+        CRM_CHECK(oz_launch_product_exponents(ycol, h->ldH, 1, Ee, h->epitch, pt.j0, pt.nj, n, expo, pt.row0, pt.rstride, st));
+        CRM_CHECK(oz_launch_product_slices(ycol, h->ldH, 1, Ee, h->epitch, pt.j0, pt.nj, n, expo, A8, Mp, Kp, pt.row0, pt.rstride, st));
+    }
+    return CRM_OK;
+}
 static int rotation_int8_split(Handle* h, const GBlock& blk, double* C, cudaStream_t st, int* used) {
     *used = 0;
     const long long B = blk.b;
@@ -1180,7 +1201,7 @@ static int do_update_phenotype(Handle* h, const double* y, cudaStream_t st) {
     build_yw_kernel<<<blocks_for(std::max<long long>((long long)R * (1 + c) * mp, (long long)(1 + c) * (1 + c)), 256), 256, 0, st>>>(
         h->yr.as<double>(), h->Wr.as<double>(), h->stats.as<double>(), R, c, mp, h->YW.as<double>(), h->ywgram.as<double>());
     CRM_CUDA(cudaGetLastError()); count_launch();
-    h->oz_built = false;     // the digit planes of the y column (and its exponent) change with the phenotype: rebuilt on demand
+    CRM_CHECK(refresh_y_planes(h, st));     // the digit planes of the y column (and their exponents) change with the phenotype
     h->colsum_valid = false;
     if (h->hxe_built && h->hxe_built_kr) h->hxe_built = false;        // compact fp64 basis: rebuilt by the next float64 rotation
     else if (h->use_hxe && h->hxe_built && h->hxe_blocks == h->kexp) {

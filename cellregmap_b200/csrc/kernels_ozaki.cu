@@ -14,6 +14,16 @@ static __global__ void oz_fill_kernel(int* p, long long count, int value) {
     if (i < count) p[i] = value;
 }
 
+static __global__ void oz_fill_strided_kernel(int* p, long long stride, int count, int value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[(long long)i * stride] = value;
+}
+int oz_launch_fill_exponents_strided(int* expo, long long row0, long long rstride, int count, cudaStream_t st) {
+    if (count <= 0) return CRM_OK;
+    oz_fill_strided_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(expo + row0, rstride, count, OZ_EXP_EMPTY);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
 int oz_launch_fill_exponents(int* expo, long long rows, cudaStream_t st) {
     oz_fill_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(expo, rows, OZ_EXP_EMPTY);
     CRM_CUDA(cudaGetLastError()); count_launch();

@@ -58,6 +58,7 @@ int oz_launch_slices(const double* Hx, int ldH, const double* Eext, int epitch, 
                      long long Kp, cudaStream_t st);
 // general form: product columns F[:, j0 + jj] * X[:, a] (a < cols, jj < nj) at rows row0 + jj * rstride + a of the plane set
 int oz_launch_fill_exponents(int* expo, long long rows, cudaStream_t st);
+int oz_launch_fill_exponents_strided(int* expo, long long row0, long long rstride, int count, cudaStream_t st);
 int oz_launch_product_exponents(const double* X, long long ldx, int cols, const double* F, long long ldf, int j0, int nj, long long n, int* expo, long long row0,
                                 long long rstride, cudaStream_t st);
 int oz_launch_product_slices(const double* X, long long ldx, int cols, const double* F, long long ldf, int j0, int nj, long long n, const int* expo, int8_t* A8,

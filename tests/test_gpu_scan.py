@@ -426,10 +426,13 @@ def test_edge_cases(cuda_device):
         CellRegMap(ybad, d2.E)
 
 
-def test_set_phenotype_equals_new_model(cuda_device):
+@pytest.mark.parametrize("basis", ["compact", "full"])
+def test_set_phenotype_equals_new_model(cuda_device, monkeypatch, basis):
     """Extension: swapping the phenotype of a model gives the results of a freshly constructed model (all scans, both
-    genotype ingress forms)."""
+    genotype ingress forms); only the digit-plane rows that hold y are rebuilt, in either layout of the planes."""
     from cellregmap_b200._cellregmap import _make_interaction_model
+    if basis == "full":
+        monkeypatch.setenv("CRM_KR", "0")
     d = make_data(n=500, donors=25, k=5, p=40, q=4, seed=41)
     y2 = make_data(n=500, donors=25, k=5, p=40, q=4, seed=42).y
     Gd = np.zeros((25, 40)); Gd[d.donor] = d.G
