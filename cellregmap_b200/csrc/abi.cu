@@ -159,7 +159,7 @@ struct Handle {
     bool kr = false, oz_built_kr = false, hxe_built_kr = false;
     int kr_q = 0, kr_r = 0;
     long long kr_R1 = 0, kr_R2 = 0, kr_R3 = 0, kr_rows = 0;
-    DevBuf krK, krM, Cc;
+    DevBuf krK, krM, Cc, fittab;
     // declaration made before crm_setup: applied (and verified, result read at the end of the set-up) inside it
     bool kr_pending = false, kr_unverified = false;
     const double* kr_pending_hK = nullptr; long long kr_pending_ld = 0; int kr_pending_q = 0, kr_pending_r = 0;
@@ -199,7 +199,7 @@ struct Handle {
         DevBuf* all[] = {&A8, &a8expo, &Gt8, &G2t8, &D32, &ozflags, &A28, &a28expo, &HxE_D, &A2_D, &dperm, &doff, &HxE, &Hx, &Eext, &A2, &gram, &S, &yr, &Wr, &Tt, &stats, &eigwork, &eigmat, &eigval, &devinfo, &C, &sq, &Hg, &gr,
                          &Vg, &GEr, &fit_lml, &fit_delta, &fit_scale, &fit_beta, &fit_x, &fit_nfev, &fit_flags, &rho_idx, &best_lml,
                          &v0, &v1, &perm, &offsets, &Q, &lam, &nlam, &sflags, &liu, &ifault, &conv, &gchunk[0], &gchunk[1],
-                         &gtchunk[0], &gtchunk[1], &gstage, &g8dev[0], &g8dev[1], &gwide, &gwide2, &aff, &affscratch, &colsum, &colsum2, &sq1, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram, &krK, &krM, &Cc};
+                         &gtchunk[0], &gtchunk[1], &gstage, &g8dev[0], &g8dev[1], &gwide, &gwide2, &aff, &affscratch, &colsum, &colsum2, &sq1, &scratch, &Ys, &sgram, &HY, &Zs, &lin, &Zp, &ucoef, &coef, &YW, &ywgram, &krK, &krM, &Cc, &fittab};
         for (DevBuf* b : all) fn(*b);
     }
     void free_all() { for_each_buf([](DevBuf& b) { b.release(); }); }
@@ -1219,6 +1219,19 @@ static int do_update_phenotype(Handle* h, const double* y, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // interaction scan
 // ------------------------------------------------------------------------------------------------
+// What the bracket searches of all SNPs of a batch share at their common points is tabulated once (fit.cuh: FIT_TAB_*; CRM_FIT_TABLE=0: off);
+// fa must describe the per-rho vectors of the fits that follow.
+static int attach_fit_table(Handle* h, FitArgs& fa, cudaStream_t st) {
+    const char* ft = getenv("CRM_FIT_TABLE");
+    fa.tab = nullptr;
+    if ((ft && atoi(ft) == 0) || fa.fixed_x || fa.c < 1 || fa.c > 7) return CRM_OK;
+    fa.tab_k = fit_table_points();
+    CRM_CHECK(h->fittab.reserve(fit_table_bytes(fa.R, fa.mp)));
+    CRM_CHECK(launch_fit_table(fa, h->fittab.as<double>(), st));
+    fa.tab = h->fittab.as<double>();
+    return CRM_OK;
+}
+
 struct BatchPlan { long long batch; };
 
 static long long pick_batch(const Handle* h, long long p, bool interaction) {
@@ -1645,6 +1658,7 @@ static int interaction_batch(Handle* h, GBlock blk, double* out_pv, double* out_
         wa.lml = fa.lml; wa.delta = fa.delta; wa.scale = fa.scale; wa.beta = fa.beta; wa.ucoef = nullptr; wa.xopt = fa.xopt; wa.nfev = fa.nfev; wa.flags = fa.flags;
         CRM_CHECK(launch_beta_fit(wa, st));
     } else {
+        CRM_CHECK(attach_fit_table(h, fa, st));
         CRM_CHECK(launch_fit(fa, true, st));
     }
     tr.mark("fits");
@@ -1817,6 +1831,7 @@ static int do_scan_association(Handle* h, int donor_level, const GSource& G, lon
             wb.lml = fb.lml; wb.xopt = nullptr;
             CRM_CHECK(launch_beta_fit(wb, st));
         } else {
+            CRM_CHECK(attach_fit_table(h, fb, st));
             CRM_CHECK(launch_fit(fb, true, st));
         }
         CRM_CHECK(launch_lrt(fb.lml, best, b, out_pv + s0, st));

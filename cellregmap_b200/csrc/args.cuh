@@ -27,6 +27,8 @@ struct FitArgs {
     double n;           // number of samples
     int restricted;
     const double* fixed_x;   // when non-null: no search, evaluate at logit(delta) = *fixed_x (FastScanner semantics)
+    // optional table of the SNP-independent part of the objective at the points every bracket search visits (fit.cuh: FIT_TAB_*), [R][2][tab_k] records
+    const double* tab; int tab_k;
     // outputs, [p][R] (beta: [p][R][P]); xopt may be null
     double* lml; double* delta; double* scale; double* beta; double* xopt; int* nfev; int* flags;
 };

@@ -87,6 +87,7 @@ struct BetaProblem {
     }
 
     // -lml at logistic value x; CTA-collective, identical result in all threads
+    __device__ __forceinline__ double eval_point(double x, int, int) { return eval(x); }     // (no table of bracket points for wide designs)
     __device__ double eval(double x) {
         nfev++;
         const double delta = logistic_delta(x), omd = 1.0 - delta;

@@ -20,8 +20,37 @@ __device__ __forceinline__ double logistic_delta(double x) {
     return fmin(fmax(v, CRM_EPS_TINY), 1.0 - CRM_EPS_TINY);
 }
 
+// ---- table of the bracket points ----
+// The bracket search starts at logit(delta) = 0 with a step of 2e-6 and doubles its stride until the objective rises: whatever the SNP,
+// it walks one of two fixed sequences of points (towards +inf or -inf), ~20 of the ~27 evaluations of a fit.  At those points everything
+// that does not involve the genotype -- the weights w_i = 1 / ((1 - delta) S_i + delta), sum log D_i, the weighted Grams of [y | W] -- is
+// the same for every SNP of a rho: crm_fit_table_kernel computes it once per rho and point with the arithmetic of FitProblem::eval, and
+// eval_tab() adds the three genotype terms (one multiply and P fused multiply-adds per element instead of a division, a quarter of a log and
+// the full Gram).  Same operations in the same order on the genotype terms, identical values elsewhere: the fits are bit-identical.
+constexpr int FIT_TAB_K = 30;          // points per direction (2e-6 * 2^30 is far beyond where any search stops)
+constexpr int FIT_TAB_HDR = 64;        // doubles of header per record: [x, delta, ld, syy, sXy (C), sXX (C x C)], then w[mp]
+__host__ __device__ inline long long fit_tab_record(int mp) { return (long long)FIT_TAB_HDR + mp; }
+// point k of the sequence in direction dir (0: towards +inf, 1: towards -inf; k = 0, 1 are the two starting points, shared)
+__device__ __forceinline__ double fit_bracket_point(int dir, int k) {
+    const double a0 = -CRM_LOGMAX, b0 = CRM_LOGMAX, rtol = 1e-6, atol = 1e-6, gfactor = 2.0;
+    double x0 = fmin(fmax(0.0, a0), b0);
+    const double step0 = gfactor * (rtol * fabs(x0) + atol);
+    double x1 = (x0 - a0 > b0 - x0) ? fmax(x0 - step0, a0) : fmin(x0 + step0, b0);
+    if (k == 0) return x0;
+    if (k == 1) return x1;
+    if (dir) { const double t = x0; x0 = x1; x1 = t; }
+    for (int t = 2; t <= k; t++) {
+        double x2 = x1 + (x1 - x0) * gfactor;
+        x2 = fmin(fmax(x2, a0), b0);
+        x0 = x1; x1 = x2;
+    }
+    return x1;
+}
+
 template <int P, bool HAS_G>
 struct FitProblem {
+    const double* tab = nullptr;   // records of this rho: [2][tab_k][FIT_TAB_HDR + mp]
+    int tab_k = 0;
     const double *S, *yr, *Wr, *gr;
     int m, mp, lane;
     double n, df;
@@ -111,14 +140,59 @@ struct FitProblem {
                 for (int b = 0; b <= a; b++) sXX[a][b] += wx * xv[b]; }
         }
         ld += log(prod);
-        const double inv_delta = 1.0 / delta;
-        const double yKy = warp_sum(syy) + yy_res * inv_delta;
+        syy = warp_sum(syy);
         ld = warp_sum(ld) + (n - m) * log(delta);
+#pragma unroll
+        for (int a = 0; a < P; a++) { sXy[a] = warp_sum(sXy[a]);
+#pragma unroll
+            for (int c2 = 0; c2 <= a; c2++) sXX[a][c2] = warp_sum(sXX[a][c2]); }
+        return finish(delta, syy, ld, sXy, sXX);
+    }
+
+    // the same evaluation at bracket point (dir, k) of the table: only the genotype terms are summed here
+    __device__ double eval_tab(int dir, int k) {
+        constexpr int C = HAS_G ? P - 1 : P;
+        nfev++;
+        const double* rec = tab + ((long long)dir * tab_k + k) * fit_tab_record(mp);
+        const double* w = rec + FIT_TAB_HDR;
+        double sXy[P], sXX[P][P];
+#pragma unroll
+        for (int a = 0; a < P; a++) { sXy[a] = 0.0;
+#pragma unroll
+            for (int b = 0; b < P; b++) sXX[a][b] = 0.0; }
+        if (HAS_G) {
+            for (int i = lane; i < m; i += 32) {
+                const double wx = w[i] * gr[i];
+                sXy[P - 1] += wx * yr[i];
+#pragma unroll
+                for (int b = 0; b < C; b++) sXX[P - 1][b] += wx * Wr[(long long)b * mp + i];
+                sXX[P - 1][P - 1] += wx * gr[i];
+            }
+            sXy[P - 1] = warp_sum(sXy[P - 1]);
+#pragma unroll
+            for (int b = 0; b < P; b++) sXX[P - 1][b] = warp_sum(sXX[P - 1][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < C; a++) { sXy[a] = rec[4 + a];
+#pragma unroll
+            for (int b = 0; b <= a; b++) sXX[a][b] = rec[4 + C + a * C + b]; }
+        return finish(rec[1], rec[3], rec[2], sXy, sXX);
+    }
+    // bracket point (dir, k) at x: from the table when it holds exactly this point
+    __device__ __forceinline__ double eval_point(double x, int dir, int k) {
+        if (tab && k < tab_k && tab[((long long)dir * tab_k + k) * fit_tab_record(mp)] == x) return eval_tab(dir, k);
+        return eval(x);
+    }
+
+    // objective from the reduced sums (lower triangle of sXX): reduced design, conditional optimum of beta and scale
+    __device__ double finish(double delta, double syy_sum, double ld, const double (&sXy)[P], const double (&sXX)[P][P]) {
+        const double inv_delta = 1.0 / delta;
+        const double yKy = syy_sum + yy_res * inv_delta;
         double A[P][P], b[P];
 #pragma unroll
-        for (int a = 0; a < P; a++) { b[a] = warp_sum(sXy[a]) + Xy_res[a] * inv_delta;
+        for (int a = 0; a < P; a++) { b[a] = sXy[a] + Xy_res[a] * inv_delta;
 #pragma unroll
-            for (int c2 = 0; c2 <= a; c2++) { A[a][c2] = warp_sum(sXX[a][c2]) + XX_res[a][c2] * inv_delta; A[c2][a] = A[a][c2]; } }
+            for (int c2 = 0; c2 <= a; c2++) { A[a][c2] = sXX[a][c2] + XX_res[a][c2] * inv_delta; A[c2][a] = A[a][c2]; } }
         // reparametrise: A' = Vx' A Vx, b' = Vx' b ; dropped directions zeroed
         double T[P][P], Ar[P][P], br[P];
 #pragma unroll
@@ -168,14 +242,15 @@ __device__ double brent_minimize(Prob& pr, double* fbest) {
     double x0 = fmin(fmax(0.0, a0), b0);
     const double step0 = gfactor * (rtol * fabs(x0) + atol);
     double x1 = (x0 - a0 > b0 - x0) ? fmax(x0 - step0, a0) : fmin(x0 + step0, b0);
-    double f0 = pr.eval(x0), f1 = pr.eval(x1);
-    if (f0 < f1) { double tx = x0; x0 = x1; x1 = tx; double tf = f0; f0 = f1; f1 = tf; }
+    double f0 = pr.eval_point(x0, 0, 0), f1 = pr.eval_point(x1, 0, 1);
+    int dir = 0;                         // which of the two fixed point sequences the search walks (fit_bracket_point)
+    if (f0 < f1) { double tx = x0; x0 = x1; x1 = tx; double tf = f0; f0 = f1; f1 = tf; dir = 1; }
     double x2 = x1, f2 = f1;
     for (int it = 0; it < maxiter; it++) {
         x2 = x1 + (x1 - x0) * gfactor;
         x2 = fmin(fmax(x2, a0), b0);
         if (x2 == x1) { f2 = f1; break; }
-        f2 = pr.eval(x2);
+        f2 = pr.eval_point(x2, dir, it + 2);
         if (f2 > f1) break;
         x0 = x1; f0 = f1; x1 = x2; f1 = f2;
     }
@@ -226,10 +301,61 @@ __device__ double brent_minimize(Prob& pr, double* fbest) {
     return xb;
 }
 
+// one warp per (rho, direction, point): the genotype-free part of FitProblem::eval at that point, same arithmetic (see FIT_TAB_* above)
+template <int C>
+__global__ void __launch_bounds__(32) crm_fit_table_kernel(const FitArgs args, double* tab_all) {
+    const int k = blockIdx.x, dir = blockIdx.y, rho = blockIdx.z, lane = threadIdx.x;
+    if (dir == 1 && k < 2) return;                      // the two starting points are shared (stored under direction 0)
+    const int mp = args.mp, m = args.m;
+    const double* S = args.S + (long long)rho * mp;
+    const double* yr = args.yr + (long long)rho * mp;
+    const double* Wr = args.Wr + (long long)rho * C * mp;
+    double* rec = tab_all + (((long long)rho * 2 + dir) * args.tab_k + k) * fit_tab_record(mp);
+    const double x = fit_bracket_point(dir, k);
+    const double delta = logistic_delta(x), omd = 1.0 - delta;
+    double syy = 0.0, ld = 0.0, sXy[C], sXX[C][C];
+#pragma unroll
+    for (int a = 0; a < C; a++) { sXy[a] = 0.0;
+#pragma unroll
+        for (int b = 0; b < C; b++) sXX[a][b] = 0.0; }
+    double prod = 1.0;
+    int cnt = 0;
+    for (int i = lane; i < m; i += 32) {
+        const double D = fma(S[i], omd, delta);
+        const double w = 1.0 / D;
+        prod *= D;
+        if (++cnt == 4) { ld += log(prod); prod = 1.0; cnt = 0; }
+        rec[FIT_TAB_HDR + i] = w;
+        double xv[C];
+#pragma unroll
+        for (int a = 0; a < C; a++) xv[a] = Wr[(long long)a * mp + i];
+        const double yv = yr[i], wy = w * yv;
+        syy += wy * yv;
+#pragma unroll
+        for (int a = 0; a < C; a++) { const double wx = w * xv[a]; sXy[a] += wx * yv;
+#pragma unroll
+            for (int b = 0; b <= a; b++) sXX[a][b] += wx * xv[b]; }
+    }
+    ld += log(prod);
+    syy = warp_sum(syy);
+    ld = warp_sum(ld) + (args.n - m) * log(delta);
+#pragma unroll
+    for (int a = 0; a < C; a++) { sXy[a] = warp_sum(sXy[a]);
+#pragma unroll
+        for (int b = 0; b <= a; b++) sXX[a][b] = warp_sum(sXX[a][b]); }
+    if (lane == 0) {
+        rec[0] = x; rec[1] = delta; rec[2] = ld; rec[3] = syy;
+#pragma unroll
+        for (int a = 0; a < C; a++) { rec[4 + a] = sXy[a];
+#pragma unroll
+            for (int b = 0; b <= a; b++) rec[4 + C + a * C + b] = sXX[a][b]; }
+    }
+}
+
 constexpr int FIT_WARPS = 8;
 
 template <int P, bool HAS_G>
-__global__ void __launch_bounds__(FIT_WARPS * 32) crm_fit_kernel(const FitArgs args, const int use_smem) {
+__global__ void __launch_bounds__(FIT_WARPS * 32, (P <= 3 ? 2 : 1)) crm_fit_kernel(const FitArgs args, const int use_smem) {
     extern __shared__ __align__(16) double fsm[];
     constexpr int C = HAS_G ? P - 1 : P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,6 +384,7 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) crm_fit_kernel(const FitArgs a
     FitProblem<P, HAS_G> pr;
     pr.S = S; pr.yr = yr; pr.Wr = Wr; pr.gr = gr; pr.m = m; pr.mp = mp; pr.lane = lane;
     pr.n = args.n; pr.restricted = args.restricted != 0;
+    if (HAS_G && args.tab) { pr.tab = args.tab + (long long)rho * 2 * args.tab_k * fit_tab_record(mp); pr.tab_k = args.tab_k; }
     double XX[P][P], Xy[P];
 #pragma unroll
     for (int a = 0; a < C; a++) { Xy[a] = args.stats[1 + a];

@@ -18,6 +18,28 @@ int launch_fit_t(const FitArgs& fa, cudaStream_t st) {
 }
 
 #ifndef CRM_FIT_NULL_TU
+template <int C>
+static int launch_fit_table_t(const FitArgs& fa, double* tab, cudaStream_t st) {
+    crm_fit_table_kernel<C><<<dim3((unsigned)fa.tab_k, 2, (unsigned)fa.R), 32, 0, st>>>(fa, tab);
+    CRM_CUDA(cudaGetLastError()); count_launch();
+    return CRM_OK;
+}
+size_t fit_table_bytes(int R, int mp) { return (size_t)R * 2 * FIT_TAB_K * (size_t)fit_tab_record(mp) * sizeof(double); }
+int fit_table_points() { return FIT_TAB_K; }
+// fa.tab_k must be set (fit_table_points()); fills `tab` (fit_table_bytes) for the S / yr / Wr of fa
+int launch_fit_table(const FitArgs& fa, double* tab, cudaStream_t st) {
+    switch (fa.c) {
+        case 1: return launch_fit_table_t<1>(fa, tab, st);
+        case 2: return launch_fit_table_t<2>(fa, tab, st);
+        case 3: return launch_fit_table_t<3>(fa, tab, st);
+        case 4: return launch_fit_table_t<4>(fa, tab, st);
+        case 5: return launch_fit_table_t<5>(fa, tab, st);
+        case 6: return launch_fit_table_t<6>(fa, tab, st);
+        case 7: return launch_fit_table_t<7>(fa, tab, st);
+    }
+    set_error("fit table: %d covariate columns outside the compiled range (1..7)", fa.c);
+    return CRM_ERR_UNSUPPORTED;
+}
 int launch_fit_with_g(const FitArgs& fa, cudaStream_t st) {
     switch (fa.c + 1) {
         case 1: return launch_fit_t<1, true>(fa, st);

@@ -35,6 +35,10 @@ void gemm_set_symmetric(bool on);
 int launch_fit_with_g(const FitArgs& fa, cudaStream_t st);   // design [W g], P = c + 1 in 1..8
 int launch_fit_null(const FitArgs& fa, cudaStream_t st);     // design W,     P = c     in 1..7
 inline int launch_fit(const FitArgs& fa, bool has_g, cudaStream_t st) { return has_g ? launch_fit_with_g(fa, st) : launch_fit_null(fa, st); }
+// table of the bracket points of the search (fit.cuh): bytes, points per direction, builder (fa.tab_k = fit_table_points())
+size_t fit_table_bytes(int R, int mp);
+int fit_table_points();
+int launch_fit_table(const FitArgs& fa, double* tab, cudaStream_t st);
 
 int launch_score(const ScoreArgs& sa, long long count, cudaStream_t st);
 int launch_select(const double* lml, const double* delta, const double* scale, int p, int R, int* rho_idx, double* best_lml,

@@ -359,6 +359,24 @@ def test_structured_background_needs_matching_contexts(cuda_device):
     np.testing.assert_array_equal(pv_a, pv_b)
 
 
+@pytest.mark.parametrize("covariates", [1, 3])
+def test_fit_table_is_bit_identical(cuda_device, monkeypatch, covariates):
+    """The REML fits read the genotype-free part of the objective at the common bracket points from a table built once per batch
+    (fit.cuh: FIT_TAB_*); with or without it every fit takes the same path to the same bits (lml grid, evaluation counts, outputs)."""
+    from cellregmap_b200._cellregmap import _make_interaction_model
+    d = make_data(n=700, donors=50, k=5, p=90, q=6, seed=61, n_covariates=covariates)
+    model = _make_interaction_model(d.y, d.E, d.W, None, None, d.hK)
+    on = model._scan_interaction_device(d.G, diagnostics=True)
+    monkeypatch.setenv("CRM_FIT_TABLE", "0")
+    off = model._scan_interaction_device(d.G, diagnostics=True)
+    for key in ("pv", "rho1", "e2", "g2", "eps2", "lml", "delta", "scale", "nfev"):
+        np.testing.assert_array_equal(on[key].cpu().numpy(), off[key].cpu().numpy(), err_msg=key)
+    pa_off, _ = model.scan_association(d.G)              # ML fits of the association scan take the same table
+    monkeypatch.delenv("CRM_FIT_TABLE")
+    pa_on, _ = model.scan_association(d.G)
+    np.testing.assert_array_equal(pa_on, pa_off)
+
+
 def test_donor_level_genotypes_match_expanded(cuda_device):
     """Extension: donor-level genotypes + donor_index give the results of the expanded call (all scans)."""
     import torch
