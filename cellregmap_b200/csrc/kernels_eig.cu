@@ -88,6 +88,11 @@ int eig_workspace_bytes(int n, int batch, size_t* bytes) {
 // (V[b][t * n_b + i] = component i of vector t) -> slot b of V [batch][nmax][nmax]; quality [batch] (device) =
 // largest residual |T z - lambda z|_inf / |T| over the vectors (NaN/inf when the Cholesky-QR step broke down).
 // ws: eig_workspace_bytes(n, batch) bytes; lib_work: at least lib_lwork doubles (max of potrf / ormtr needs, queried by the caller).
+// side streams of the back-transformation, one set per device (eig_batched runs under the per-device lock of the set-up)
+constexpr int EIG_WAYS = 4;
+struct EigSide { bool ready = false; cudaStream_t stream[EIG_WAYS - 1]; cusolverDnHandle_t solver[EIG_WAYS - 1]; cudaEvent_t done[EIG_WAYS - 1]; cudaEvent_t fork; };
+static EigSide g_eig_side[32];
+
 int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n, int batch, double* W, double* V, double* quality, void* ws, double* lib_work,
                 int lib_lwork, int* info_dev, cudaStream_t st, int group_batch, const int* ids, const std::function<int()>* after_sytrd) {
     cusolverDnHandle_t solver = (cusolverDnHandle_t)solver_v;
@@ -203,13 +208,42 @@ int eig_batched(void* solver_v, void* blas_v, double* A, const int* n_of, int n,
     // residuals of the tridiagonal eigenpairs (before the back-transformation, O(n) per vector)
     eig_residual_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)batch), 128, 0, st>>>(d, e, V, tnorm, sz, rq, (unsigned long long*)quality);
     CRM_CUDA(cudaGetLastError()); count_launch();
-    // 5. back-transformation: eigenvectors of A = Q Z, Q from the reflectors left in A
+    // 5. back-transformation: eigenvectors of A = Q Z, Q from the reflectors left in A.  Dormtr is ~64 small launches per matrix that do
+    // not fill the device: the matrices are dealt over EIG_WAYS streams (one cuSOLVER handle each; workspace = the matrix's own, now free,
+    // inverse-iteration scratch), forked from and joined to `st` with events.
     CRM_SOLVER_(cusolverDnSetStream(solver, st));
-    for (int b = 0; b < batch; b++) {
-        const int nb = sz.n_of[b];
-        SlowSection sec3("eig: one cusolverDnDormtr");
-        CRM_SOLVER_(cusolverDnDormtr(solver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, nb, nb, A + (size_t)b * nn, nb, tau + (size_t)b * n, V + (size_t)b * nn, nb,
-                                     lib_work, lib_lwork, info_dev + batch + b));
+    {
+        static const int ways_env = [] { const char* v = getenv("CRM_EIG_WAYS"); return v ? atoi(v) : EIG_WAYS; }();
+        const int ways = std::max(1, std::min(std::min(ways_env, EIG_WAYS), batch));
+        int dev = 0;
+        CRM_CUDA(cudaGetDevice(&dev));
+        EigSide& side = g_eig_side[dev & 31];
+        const bool own_ws = (size_t)lib_lwork <= 5 * nn;
+        if (ways > 1 && own_ws) {
+            if (!side.ready) {
+                for (int w = 0; w < EIG_WAYS - 1; w++) {
+                    CRM_CUDA(cudaStreamCreateWithFlags(&side.stream[w], cudaStreamNonBlocking));
+                    CRM_SOLVER_(cusolverDnCreate(&side.solver[w]));
+                    CRM_SOLVER_(cusolverDnSetStream(side.solver[w], side.stream[w]));
+                    CRM_CUDA(cudaEventCreateWithFlags(&side.done[w], cudaEventDisableTiming));
+                }
+                CRM_CUDA(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
+                side.ready = true;
+            }
+            CRM_CUDA(cudaEventRecord(side.fork, st));
+            for (int w = 0; w < ways - 1; w++) CRM_CUDA(cudaStreamWaitEvent(side.stream[w], side.fork, 0));
+        }
+        for (int b = 0; b < batch; b++) {
+            const int nb = sz.n_of[b];
+            const int w = (ways > 1 && own_ws) ? b % ways : 0;           // way 0 = the caller's stream and handle
+            cusolverDnHandle_t hs = w == 0 ? solver : side.solver[w - 1];
+            double* ws_b = own_ws ? work + (size_t)b * 5 * nn : lib_work;
+            CRM_SOLVER_(cusolverDnDormtr(hs, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, nb, nb, A + (size_t)b * nn, nb, tau + (size_t)b * n, V + (size_t)b * nn, nb,
+                                         ws_b, own_ws ? (int)std::min<size_t>(5 * nn, 2000000000u) : lib_lwork, info_dev + batch + b));
+        }
+        if (ways > 1 && own_ws) {
+            for (int w = 0; w < ways - 1; w++) { CRM_CUDA(cudaEventRecord(side.done[w], side.stream[w])); CRM_CUDA(cudaStreamWaitEvent(st, side.done[w], 0)); }
+        }
     }
     tr.mark("residuals + back-transformation");
     tr.report("batched eigensolver");
