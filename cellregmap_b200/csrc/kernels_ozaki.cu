@@ -73,8 +73,9 @@ int oz_launch_matrix_planes(const double* X, long long ldx, int cols, long long 
 
 int oz_launch_genotypes(const double* G, long long ldg, long long n, long long B, int8_t* Gt8, int8_t* G2t8, long long Bp, long long Kp, int* flags, cudaStream_t st) {
     CRM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
-    dim3 grid((unsigned)((Kp + OZ_ROWS - 1) / OZ_ROWS), (unsigned)((Bp + OZ_TILE - 1) / OZ_TILE), 1);
-    oz_genotype_kernel<<<grid, 256, 0, st>>>(G, ldg, n, B, Gt8, G2t8, Bp, Kp, flags);
+    const long long blocks = ((Kp + OZ_ROWS - 1) / OZ_ROWS) * ((Bp + OZ_TILE - 1) / OZ_TILE);
+    if (blocks > 2147483647LL) { set_error("genotype block too large for one conversion launch"); return CRM_ERR_UNSUPPORTED; }
+    oz_genotype_kernel<<<(unsigned)blocks, 256, 0, st>>>(G, ldg, n, B, Gt8, G2t8, Bp, Kp, flags);
     CRM_CUDA(cudaGetLastError()); count_launch();
     return CRM_OK;
 }
@@ -115,8 +116,9 @@ int oz_launch_affine_genotypes(const double* G, long long ldg, long long n, long
     oz_colstat_merge_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(partial, chunks, B, aff, lda);
     CRM_CUDA(cudaGetLastError()); count_launch();
     CRM_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
-    dim3 grid((unsigned)((Kp + OZ_ROWS - 1) / OZ_ROWS), (unsigned)((Bp + OZ_TILE - 1) / OZ_TILE), 1);
-    oz_affine_genotype_kernel<<<grid, 256, 0, st>>>(G, ldg, n, B, aff, lda, Gt8, G2t8, Bp, Kp, flags);
+    const long long blocks = ((Kp + OZ_ROWS - 1) / OZ_ROWS) * ((Bp + OZ_TILE - 1) / OZ_TILE);
+    if (blocks > 2147483647LL) { set_error("genotype block too large for one conversion launch"); return CRM_ERR_UNSUPPORTED; }
+    oz_affine_genotype_kernel<<<(unsigned)blocks, 256, 0, st>>>(G, ldg, n, B, aff, lda, Gt8, G2t8, Bp, Kp, flags);
     CRM_CUDA(cudaGetLastError()); count_launch();
     return CRM_OK;
 }

@@ -148,20 +148,26 @@ __global__ void __launch_bounds__(256) oz_genotype_kernel(const double* G, long 
                                                           long long Kp, int* flags) {
     __shared__ double tile[OZ_ROWS][OZ_TILE + 1];
     __shared__ int s_bad, s_max;
-    const long long i0 = (long long)blockIdx.x * OZ_ROWS;
-    const long long s0 = (long long)blockIdx.y * OZ_TILE;
+    // 1-D grid, SNP tiles fastest: blocks in flight together read neighbouring 256-byte pieces of the same genotype rows (DRAM pages)
+    const long long s_tiles = (Bp + OZ_TILE - 1) / OZ_TILE;
+    const long long i0 = ((long long)blockIdx.x / s_tiles) * OZ_ROWS;
+    const long long s0 = ((long long)blockIdx.x % s_tiles) * OZ_TILE;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     if (threadIdx.x == 0) { s_bad = 0; s_max = 0; }
     __syncthreads();
     int bad = 0, gmax = 0;
-    for (int r = ty; r < OZ_ROWS; r += 8) {
-        const long long i = i0 + r, s = s0 + tx;
-        double v = 0.0;
-        if (i < n && s < B) {
-            v = G[i * ldg + s];
-            if (!(v == rint(v)) || fabs(v) > 127.0) { bad = 1; if (!isfinite(v)) bad = 3; } else gmax = max(gmax, (int)fabs(v));
+    {
+        // all 16 loads of the thread are issued before the first value is looked at (the kernel is bound by bytes in flight, not by DRAM)
+        const long long s = s0 + tx;
+        double v[OZ_ROWS / 8];
+#pragma unroll
+        for (int q = 0; q < OZ_ROWS / 8; q++) { const long long i = i0 + ty + 8 * q; v[q] = (i < n && s < B) ? __ldcs(&G[i * ldg + s]) : 0.0; }
+#pragma unroll
+        for (int q = 0; q < OZ_ROWS / 8; q++) {
+            const double x = v[q];
+            if (!(x == rint(x)) || fabs(x) > 127.0) { bad = 1; if (!isfinite(x)) bad = 3; } else gmax = max(gmax, (int)fabs(x));
+            tile[oz_tile_slot(ty + 8 * q)][tx] = x;
         }
-        tile[oz_tile_slot(r)][tx] = v;
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
 #pragma unroll
@@ -300,8 +306,10 @@ __global__ void __launch_bounds__(256) oz_affine_genotype_kernel(const double* G
                                                                  int8_t* G2t8, long long Bp, long long Kp, int* flags) {
     __shared__ double tile[OZ_ROWS][OZ_TILE + 1];
     __shared__ int s_bad, s_max;
-    const long long i0 = (long long)blockIdx.x * OZ_ROWS;
-    const long long s0 = (long long)blockIdx.y * OZ_TILE;
+    // 1-D grid, SNP tiles fastest: blocks in flight together read neighbouring 256-byte pieces of the same genotype rows (DRAM pages)
+    const long long s_tiles = (Bp + OZ_TILE - 1) / OZ_TILE;
+    const long long i0 = ((long long)blockIdx.x / s_tiles) * OZ_ROWS;
+    const long long s0 = ((long long)blockIdx.x % s_tiles) * OZ_TILE;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     if (threadIdx.x == 0) { s_bad = 0; s_max = 0; }
     __syncthreads();
