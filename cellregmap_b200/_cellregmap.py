@@ -208,7 +208,11 @@ class CellRegMap:
             geno = _Genotypes(_prefetch, dev, int(_prefetch.shape[0]))
             if geno.on_host and geno.p > 0:
                 width = int(self._E1.shape[1]) + (0 if Lcat is None else int(Lcat.shape[1])) + 1 + int(self._W.shape[1])
-                basis_cols = (1 + int(self._E0.shape[1])) * (width + (width & 1))
+                k0 = int(self._E0.shape[1])
+                basis_cols = (1 + k0) * (width + (width & 1))
+                if _background_factors is not None:      # compact basis of a structured background (layout in abi.cu: kr_apply)
+                    q = int(_background_factors[0].shape[1])
+                    basis_cols = (width + (width & 1)) + k0 * int(self._E1.shape[1]) + k0 * (1 + int(self._W.shape[1])) + k0 * (k0 + 1) // 2 * q
                 _lib.call("crm_stage_genotypes_typed", self._handle, ctypes.c_void_p(geno.ptr), geno.dtype, geno.ld, geno.rows, geno.p, basis_cols, _stream())
             self._prefetched = (_prefetch, geno)
         self._background_factors = None

@@ -1308,18 +1308,51 @@ static int stage_host_block(Handle* h, const double* G, long long ldg, const dou
     return CRM_OK;
 }
 
-// Column blocks of the feeder: equal blocks of whole 256-SNP tiles of the int8 contraction, at most 3072 columns each (2560 with 16 threads).  Narrow enough
-// that the first block is converted while the set-up runs (25 ms for 100k x 2560 float64 on 16 threads), wide enough that the
+// Width cap of the feeder's column blocks (whole 256-SNP tiles of the int8 contraction, at most 3072 columns; 2816 with 16 threads).  Narrow
+// enough that the first block is converted while the set-up runs (25-30 ms for 100k x 2816 float64 on 16 threads), wide enough that the
 // per-block costs of the scan (launch chain, host synchronisation for the rho groups, the small g^2 contraction) stay a few per cent;
-// measured at bench size: 1792 -> 243 ms, 2560 -> 225 ms, 5120 -> 257 ms per call (profiles/e2e_blocks_ab.py).
-static long long feeder_block_cols(long long p, long long basis_cols) {
-    (void)basis_cols;
-    if (const char* env = getenv("CRM_FEEDER_BLOCK")) { if (atoll(env) > 0) return std::min<long long>(p, atoll(env)); }     // tests: many small blocks
+// measured at bench size with equal blocks: 1792 -> 243 ms, 2560 -> 225 ms, 5120 -> 257 ms per call (profiles/e2e_blocks_ab.py).
+static long long feeder_block_cap() {
     // few host threads (several ranks sharing the cores of a box): narrower blocks, so that a block is converted in ~25 ms whatever the
     // thread count (5 GB/s of float64 per thread) and the scan of block i hides the conversion of block i + 1
-    const long long cap = std::min<long long>(3072, std::max<long long>(512, round_up(160LL * host_threads(), 256)));
+    return std::min<long long>(3072, std::max<long long>(512, round_up(176LL * host_threads(), 256)));
+}
+// Column blocks [starts[b], starts[b + 1]) of the feeder.  Equal blocks under the cap by default.  With the width of the basis operand
+// known (hint of the Python layer) and a wide cap, the widths are chosen in units of the 256-SNP tiles of the int8 contraction so that
+// its persistent grid ends on full waves: a block of t tiles is ceil(m_tiles t / SMs) waves, and four equal blocks of 10 tiles cost 28
+// waves at cfg3 where {11, 11, 11, 7} cost 26 (25.4 of work).  Wider blocks come first: the first one is converted under the set-up.
+static std::vector<long long> feeder_block_starts(long long p, long long basis_cols, int device) {
+    std::vector<long long> starts;
+    if (const char* env = getenv("CRM_FEEDER_BLOCK")) {      // tests: many small blocks
+        if (atoll(env) > 0) { for (long long s0 = 0; s0 < p; s0 += atoll(env)) starts.push_back(s0); starts.push_back(p); return starts; }
+    }
+    const long long cap = feeder_block_cap(), T = (p + 255) / 256, capT = cap / 256;
+    static int sms[32] = {0};
+    if (device >= 0 && device < 32 && !sms[device]) { if (cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); sms[device] = 148; } }
+    const long long nsm = (device >= 0 && device < 32) ? sms[device] : 148;
+    const long long m_tiles = basis_cols > 0 ? (basis_cols + 127) / 128 : 0;
+    if (m_tiles > 0 && capT >= 8 && T > capT && T <= 100000) {
+        // best[t]: least cost (waves + 0.7 per block for its launch chain and host synchronisation) of covering t tiles
+        std::vector<double> best(T + 1, 1e300); std::vector<int> pick(T + 1, 0);
+        best[0] = 0.0;
+        for (long long t = 1; t <= T; t++)
+            for (long long w = 1; w <= std::min(capT, t); w++) {
+                const double c = best[t - w] + (double)((m_tiles * w + nsm - 1) / nsm) + 0.7;
+                if (c < best[t] - 1e-9) { best[t] = c; pick[t] = (int)w; }
+            }
+        std::vector<long long> widths;
+        for (long long t = T; t > 0; t -= pick[t]) widths.push_back(pick[t]);
+        std::sort(widths.begin(), widths.end(), [](long long a, long long b) { return a > b; });
+        long long s0 = 0;
+        for (long long w : widths) { starts.push_back(s0); s0 += w * 256; }
+        starts.push_back(p);
+        return starts;
+    }
     const long long nblocks = (p + cap - 1) / cap;
-    return std::min(p, round_up((p + nblocks - 1) / nblocks, 256));
+    const long long block = std::min(p, round_up((p + nblocks - 1) / nblocks, 256));
+    for (long long s0 = 0; s0 < p; s0 += block) starts.push_back(s0);
+    starts.push_back(p);
+    return starts;
 }
 
 static void drop_feed(Handle* h) {
@@ -1334,10 +1367,10 @@ static int start_feed(Handle* h, const void* G, int dtype, long long ldg, long l
     if (off || host_dtype_size(dtype) == 0) return CRM_OK;
     auto job = std::make_shared<FeedJob>();
     job->src = G; job->dtype = dtype; job->ld = ldg; job->rows = rows; job->p = p;
-    const long long block = feeder_block_cols(p, basis_cols);
-    for (long long s0 = 0; s0 < p; s0 += block) job->starts.push_back(s0);
-    job->starts.push_back(p);
-    job->slot_ld = round_up(std::min(block, p), 16);
+    job->starts = feeder_block_starts(p, basis_cols, h->device);
+    long long block = 0;
+    for (size_t b = 0; b + 1 < job->starts.size(); b++) block = std::max(block, job->starts[b + 1] - job->starts[b]);
+    job->slot_ld = round_up(block, 16);
     job->nslots = (int)std::min<long long>(3, job->nblocks());
     for (int i = 0; i < job->nslots; i++) {
         job->slots[i] = pinned_slot(i, (size_t)rows * job->slot_ld);
@@ -1345,7 +1378,7 @@ static int start_feed(Handle* h, const void* G, int dtype, long long ldg, long l
     }
     feeder_submit(job);
     h->feed = job; h->feed_src = G; h->feed_ld = ldg; h->feed_p = p; h->feed_rows = rows; h->feed_dtype = dtype;
-    if (trace_on()) fprintf(stderr, "[crm trace] host %.1f ms: feeder started, %lld x %lld genotypes (dtype %d) in %lld blocks of %lld columns, %d threads\n", host_ms(), rows, p, dtype,
+    if (trace_on()) fprintf(stderr, "[crm trace] host %.1f ms: feeder started, %lld x %lld genotypes (dtype %d) in %lld blocks of up to %lld columns, %d threads\n", host_ms(), rows, p, dtype,
                             job->nblocks(), block, host_threads());
     return CRM_OK;
 }
@@ -1481,7 +1514,7 @@ static int for_each_block(Handle* h, const GSource& src, const GSource* src2, lo
     long long done = 0;                 // columns handled so far
     if (!src2) {
         if (!(h->feed && h->feed_src == src.ptr && h->feed_ld == src.ld && h->feed_p == p && h->feed_rows == rows && h->feed_dtype == src.dtype))
-            CRM_CHECK(start_feed(h, src.ptr, src.dtype, src.ld, rows, p, h->gs == &h->cells ? (long long)h->kexp * h->ldH : 0));
+            CRM_CHECK(start_feed(h, src.ptr, src.dtype, src.ld, rows, p, h->gs == &h->cells ? plane_rows(h) : 0));
         if (h->feed) {
             std::shared_ptr<FeedJob> job = h->feed;
             const long long nb = job->nblocks();
@@ -1500,14 +1533,15 @@ static int for_each_block(Handle* h, const GSource& src, const GSource* src2, lo
                 const int dslot = (int)(ib & 1);
                 const long long s0 = job->starts[ib], bw = job->starts[ib + 1] - s0;
                 cudaError_t ce = cudaStreamWaitEvent(h->copy_stream, h->ev_done[dslot], 0);          // scan of the block that used this buffer before
-                if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->g8dev[dslot].ptr, job->slots[ib % job->nslots], slot_bytes, cudaMemcpyHostToDevice, h->copy_stream);
+                const long long ld_b = job->block_ld(ib);                           // blocks are packed with their own leading dimension: one contiguous copy
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->g8dev[dslot].ptr, job->slots[ib % job->nslots], (size_t)rows * ld_b, cudaMemcpyHostToDevice, h->copy_stream);
                 if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_copy[dslot], h->copy_stream);
                 if (ce == cudaSuccess) ce = feeder_release_after(job, ib, h->copy_stream);
                 if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, h->ev_copy[dslot], 0);
                 if (ce != cudaSuccess) { set_error("feeder copy failed: %s", cudaGetErrorString(ce)); status = CRM_ERR_CUDA; break; }
                 for (long long c0 = 0; c0 < bw && status == CRM_OK; c0 += B) {       // scan batches inside the block
                     const long long b = std::min(B, bw - c0);
-                    GBlock blk{nullptr, 0, 0, nullptr, 0, b, s0 + c0, h->g8dev[dslot].as<int8_t>() + c0, job->slot_ld, gmax};
+                    GBlock blk{nullptr, 0, 0, nullptr, 0, b, s0 + c0, h->g8dev[dslot].as<int8_t>() + c0, ld_b, gmax};
                     status = fn(blk);
                 }
                 if (status == CRM_OK && cudaEventRecord(h->ev_done[dslot], st) != cudaSuccess) { set_error("cudaEventRecord failed"); status = CRM_ERR_CUDA; }

@@ -224,7 +224,7 @@ struct FeedPoolJob : PoolJob {
         if (!J.cancelled.load()) {
             const long long r0 = rc * J.row_chunk, r1 = std::min(J.rows, r0 + J.row_chunk);
             const long long c0 = J.starts[b], w = J.starts[b + 1] - c0;
-            const NarrowFlags f = narrow_any(J.src, J.dtype, J.ld, r0, r1, c0, w, J.slots[b % J.nslots], J.slot_ld);
+            const NarrowFlags f = narrow_any(J.src, J.dtype, J.ld, r0, r1, c0, w, J.slots[b % J.nslots], J.block_ld(b));
             if (f.bad) J.bad[b].store(1);
             int cur = J.gmax[b].load();
             while (f.gmax > cur && !J.gmax[b].compare_exchange_weak(cur, f.gmax)) {}

@@ -24,8 +24,9 @@ struct FeedJob {
     const void* src = nullptr; int dtype = HD_F64; long long ld = 0, rows = 0, p = 0;
     // column blocks [starts[b], starts[b + 1])
     std::vector<long long> starts;
-    // pinned ring: block b -> slot b % nslots, row-major int8 with leading dimension slot_ld
+    // pinned ring: block b -> slot b % nslots, row-major int8 with leading dimension block_ld(b) (slots are sized for slot_ld, the widest)
     int nslots = 0; int8_t* slots[4] = {nullptr, nullptr, nullptr, nullptr}; long long slot_ld = 0;
+    long long block_ld(long long b) const { const long long w = starts[b + 1] - starts[b]; return (w + 15) / 16 * 16; }
     // work units: (block, row chunk), claimed in order
     long long row_chunk = 0, units_per_block = 0, total_units = 0;
     std::atomic<long long> next_unit{0};

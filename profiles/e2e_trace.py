@@ -15,7 +15,7 @@ a = bench.parse_args()
 gene = bench.make_gene(a)
 Gd = bench.donor_genotypes(a, 0, a.snps)
 G = np.ascontiguousarray(Gd[gene["donor"]])
-for rep in range(3):
+for rep in range(int(os.environ.get("REPS", "3"))):
     torch.cuda.synchronize(); t0 = time.time()
     pv, info = crm.run_interaction(gene["y"], gene["E"], G, W=gene["W"], hK=gene["hK"])
     print(f"[call {rep}] {1e3 * (time.time() - t0):.1f} ms", file=sys.stderr, flush=True)
