@@ -60,6 +60,16 @@ def _scaled_left_vectors(E):
         U, S, _ = torch.linalg.svd(E, full_matrices=False)
         keep = S >= EPS_SMALL
         return U[:, keep] * S[keep], None
+    if os.environ.get("CRM_CONTEXT_SVD") != "qr":
+        # Well-conditioned contexts (the usual case): V from the k x k Gram E'E -- one thin GEMM and a 3 KB read-back instead of the
+        # Householder QR (~160 small launches, 3 ms at n = 100k).  U S = E V only needs V orthogonal, which eigh delivers to rounding
+        # whatever the conditioning; what the Gram cannot do is tell a singular value below sqrt(eps) from zero (the reference's
+        # filter), so anything with sigma_min / sigma_max < 3e-5 takes the QR route below.
+        lam, Vg = np.linalg.eigh((E.T @ E).cpu().numpy())
+        if lam[0] > 1e-9 * lam[-1] and lam[0] > 1e3 * EPS_SMALL ** 2:
+            Vnp = np.empty(Vg.shape, dtype=np.float64, order="C")    # descending singular values, like the SVD (a fresh C-ordered array)
+            Vnp[...] = Vg[:, ::-1]
+            return E @ torch.from_numpy(Vnp).to(E.device), Vnp
     R = torch.linalg.qr(E, mode="r").R
     _, S, Vh = np.linalg.svd(R.cpu().numpy())
     keep = S >= EPS_SMALL
