@@ -27,6 +27,28 @@ def test_scaled_left_vectors_match_numpy_svd(case):
     np.testing.assert_allclose(np.sort(np.linalg.norm(us, axis=0))[::-1], S[keep], rtol=1e-10)
 
 
+@pytest.mark.parametrize("case", ["generic", "cond 1e3", "cond 1e6"])
+def test_context_map_routes_agree(case, monkeypatch):
+    """The context map V with U S = E V comes from the k x k Gram for well-conditioned contexts and from the QR factor otherwise
+    (sigma_min / sigma_max < 3e-5); both give an orthogonal V, U S = E V exactly, and the same E E'."""
+    rng = np.random.default_rng(8)
+    E = rng.standard_normal((600, 6))
+    if case != "generic":
+        E[:, 5] = E[:, 0] + (1e-3 if case == "cond 1e3" else 1e-6) * E[:, 5]
+    Et = torch.from_numpy(E)
+    us_a, V_a = api._scaled_left_vectors(Et)
+    monkeypatch.setenv("CRM_CONTEXT_SVD", "qr")
+    us_b, V_b = api._scaled_left_vectors(Et)
+    for us, V in ((us_a, V_a), (us_b, V_b)):
+        assert V.shape == (6, 6) and V.flags["C_CONTIGUOUS"]
+        np.testing.assert_allclose(V.T @ V, np.eye(6), atol=1e-13)
+        np.testing.assert_allclose(us.numpy(), E @ V, rtol=0, atol=1e-12 * np.abs(E).max())
+    np.testing.assert_allclose((us_a @ us_a.T).numpy(), (us_b @ us_b.T).numpy(), rtol=0, atol=1e-11 * np.abs(E @ E.T).max())
+    # which route ran: the two agree column by column (up to sign) only when both are singular vectors of a well-separated spectrum
+    S = np.linalg.svd(E, compute_uv=False)
+    assert (S[-1] / S[0] < 3e-5) == (case == "cond 1e6")
+
+
 def test_l_concat_equals_the_oracle_blocks():
     """sum_i L_i L_i' from the concatenated blocks equals the oracle's get_L_values (signs of the blocks are free)."""
     rng = np.random.default_rng(4)
