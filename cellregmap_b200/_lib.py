@@ -70,6 +70,7 @@ SIGNATURES = {
     "crm_stage_genotypes_typed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                  ctypes.c_void_p]),
     "crm_host_threads": (ctypes.c_int, []),
+    "crm_feeder_blocks": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "crm_host_narrow": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "crm_fp64_tensor_peak": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]),

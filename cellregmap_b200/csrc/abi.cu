@@ -1313,6 +1313,7 @@ static int stage_host_block(Handle* h, const double* G, long long ldg, const dou
 // per-block costs of the scan (launch chain, host synchronisation for the rho groups, the small g^2 contraction) stay a few per cent;
 // measured at bench size with equal blocks: 1792 -> 243 ms, 2560 -> 225 ms, 5120 -> 257 ms per call (profiles/e2e_blocks_ab.py).
 static long long feeder_block_cap() {
+    if (const char* v = getenv("CRM_FEEDER_CAP")) { if (atoll(v) >= 256) return std::min<long long>(3072, atoll(v) / 256 * 256); }      // tests: cap of another thread count
     // few host threads (several ranks sharing the cores of a box): narrower blocks, so that a block is converted in ~25 ms whatever the
     // thread count (5 GB/s of float64 per thread) and the scan of block i hides the conversion of block i + 1
     return std::min<long long>(3072, std::max<long long>(512, round_up(176LL * host_threads(), 256)));
@@ -2155,6 +2156,16 @@ int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dtype, int
 }
 
 int crm_host_threads(void) { return host_threads(); }
+
+int crm_feeder_blocks(int64_t p, int64_t basis_cols, int64_t* starts, int32_t capacity, int32_t* nblocks) {
+    if (p <= 0 || !nblocks) { set_error("crm_feeder_blocks: bad arguments"); return CRM_ERR_INVALID; }
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }        // no device: the SM count falls back to 148
+    const std::vector<long long> st = feeder_block_starts(p, basis_cols, dev);
+    *nblocks = (int32_t)st.size() - 1;
+    if (starts) for (size_t i = 0; i < st.size() && (int32_t)i < capacity; i++) starts[i] = st[i];
+    return CRM_OK;
+}
 
 int crm_host_narrow(const void* src_host, int dtype, int64_t ld, int64_t rows, int64_t cols, int8_t* dst_host, int64_t ldd, int32_t* bad, int32_t* gmax) {
     if (!src_host || !dst_host || rows < 0 || cols < 0 || ld < cols || ldd < cols || host_dtype_size(dtype) == 0) { set_error("crm_host_narrow: bad arguments"); return CRM_ERR_INVALID; }

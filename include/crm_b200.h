@@ -95,6 +95,10 @@ CRM_API int crm_stage_genotypes_typed(crm_handle_t h, const void* G_host, int dt
 CRM_API int crm_fp64_tensor_peak(double* tflops, void* stream);
 /* Worker threads of the host feeder. */
 CRM_API int crm_host_threads(void);
+/* Column blocks the feeder would cut a host matrix of p SNP columns into when the rotation contracts basis_cols columns (0: unknown):
+ * starts[0..nblocks] (at most `capacity` entries are written; starts may be NULL).  Host-side logic only (tests): widths are whole
+ * 256-SNP tiles chosen so that the persistent grid of the int8 contraction ends on full waves. */
+CRM_API int crm_feeder_blocks(int64_t p, int64_t basis_cols, int64_t* starts, int32_t capacity, int32_t* nblocks);
 /* The feeder's conversion on its own (host memory in, host memory out, no device involved): rows x cols elements of type `dtype`
  * (leading dimension ld) -> int8 (leading dimension ldd bytes); *bad = 1 when some entry is not an integer in [-127, 127] (such
  * entries are written as saturated / arbitrary values), *gmax = largest |entry| among the valid ones. */

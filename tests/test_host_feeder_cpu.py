@@ -64,3 +64,44 @@ def test_narrow_integer_types_out_of_range():
         g[32, 20] = value
         _, bad, _ = _narrow(g)
         assert bad == 1, (dtype, value)
+
+
+def _blocks(p, basis_cols, monkeypatch, cap=2816, env_block=None):
+    monkeypatch.setenv("CRM_FEEDER_CAP", str(cap))           # the cap of a pool of 16 threads, whatever this process has
+    if env_block is not None:
+        monkeypatch.setenv("CRM_FEEDER_BLOCK", str(env_block))
+    starts = (ctypes.c_int64 * 4096)()
+    nb = ctypes.c_int32(0)
+    _lib.call("crm_feeder_blocks", p, basis_cols, starts, 4096, ctypes.byref(nb))
+    return np.array(starts[: nb.value + 1], dtype=np.int64)
+
+
+def _waves(widths, basis_cols, sms=148):
+    m_tiles = -(-basis_cols // 128)
+    return sum(-(-(m_tiles * -(-int(w) // 256)) // sms) for w in widths)
+
+
+def test_feeder_block_schedule(monkeypatch):
+    """Column blocks of the feeder (abi.cu: feeder_block_starts): they tile [0, p) in order, stay under the cap, and -- when the width of
+    the basis operand is known -- are whole 256-SNP tiles whose int8 contractions end on full waves of the persistent grid: never more
+    waves than equal blocks, wider blocks first."""
+    for p, basis, cap in ((10000, 11964, 2816), (10000, 21462, 2816), (2000, 2500, 2816), (777, 11964, 2816), (100000, 11964, 3072), (5000, 0, 2816),
+                          (1250, 11964, 512), (10000, 11964, 1536)):
+        starts = _blocks(p, basis, monkeypatch, cap=cap)
+        widths = np.diff(starts)
+        assert starts[0] == 0 and starts[-1] == p and np.all(widths > 0)
+        assert widths.max() <= cap
+        if basis > 0 and len(widths) > 1:
+            assert np.all(widths[:-1] % 256 == 0)
+            cap = int(widths.max())
+            nb = -(-p // cap)
+            eq = min(p, -(-(-(-p // nb)) // 256) * 256)
+            equal = [min(eq, p - s) for s in range(0, p, eq)]
+            assert _waves(widths, basis) <= _waves(equal, basis)
+            assert np.all(np.diff(widths[:-1]) <= 0)            # wider blocks first (the last one takes the ragged rest)
+    # the bench case with 16 feeder threads: {11, 11, 11, 7} tiles = 26 waves where four blocks of 10 tiles cost 28
+    starts = _blocks(10000, 11964, monkeypatch)
+    assert list(np.diff(starts)) == [2816, 2816, 2816, 1552]
+    # explicit block width (tests of the scan use many small blocks)
+    starts = _blocks(1000, 11964, monkeypatch, env_block=96)
+    assert list(np.diff(starts)) == [96] * 10 + [40]
