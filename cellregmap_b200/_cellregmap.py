@@ -86,14 +86,23 @@ def _L_concat(hK, E, with_map=False):
     return (L, V) if with_map else L
 
 
+class _LValues(list):
+    """The list get_L_values returns, remembering how it was built (hK, E and the map V with U S = E V): a model constructed from it
+    with the same contexts can tell the library about the structure (crm_set_background_factors), which checks it against the blocks."""
+    factors = None
+
+
 def get_L_values(hK, E):
     """List of L_i such that K o EE' = sum_i L_i L_i' (reference :533-545); numpy in, numpy out."""
     E = np.asarray(E, float)
     hK = np.asarray(hK, float)
-    U, S, _ = np.linalg.svd(E, full_matrices=False)
+    U, S, Vt = np.linalg.svd(E, full_matrices=False)
     keep = S >= EPS_SMALL
     us = U[:, keep] * S[keep]
-    return [us[:, i][:, None] * hK for i in range(us.shape[1])]
+    out = _LValues(us[:, i][:, None] * hK for i in range(us.shape[1]))
+    if E.shape[0] >= E.shape[1] and hK.ndim == 2:
+        out.factors = (hK, E, np.ascontiguousarray(Vt[keep, :].T))
+    return out
 
 
 # element types of genotype matrices understood by the C ABI (include/crm_b200.h: CRM_G_*)
@@ -226,6 +235,11 @@ class CellRegMap:
                 _lib.call("crm_stage_genotypes_typed", self._handle, ctypes.c_void_p(geno.ptr), geno.dtype, geno.ld, geno.rows, geno.p, basis_cols, _stream())
             self._prefetched = (_prefetch, geno)
         self._background_factors = None
+        if _background_factors is None and isinstance(Ls, _LValues) and Ls.factors is not None and len(Ls) == Ls.factors[2].shape[1]:
+            # Ls straight from get_L_values(hK, E) with the contexts of this model (the reference's documented way to build a model)
+            hK_l, E_l, V_l = Ls.factors
+            if tuple(E_l.shape) == tuple(self._E0.shape) and bool(torch.equal(_to_dev(E_l, dev), self._E0)):
+                _background_factors = (_to_dev(hK_l, dev, two_d=True), V_l)
         if _background_factors is not None:
             # Ls = get_L_values(hK, E) with U S = E V: declared ahead of the set-up, which verifies it (crm_set_background_factors)
             hKf, V = _background_factors

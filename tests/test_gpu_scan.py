@@ -337,6 +337,32 @@ def test_structured_background_route(cuda_device, monkeypatch, shape):
     np.testing.assert_array_equal(pv_s3, pv_s)
 
 
+def test_structured_background_from_get_L_values(cuda_device, monkeypatch):
+    """CellRegMap(y, E, W, Ls=get_L_values(hK, E)) -- the reference's documented way to build a model -- takes the compact basis too:
+    the list remembers its factors, the library verifies them against the blocks; a list that was edited, or contexts that differ
+    from the ones inside L, fall back to the full basis.  Same scan either way."""
+    from cellregmap_b200 import CellRegMap, get_L_values
+    d = make_data(n=600, donors=40, k=5, p=50, q=4, seed=71)
+    Ls = get_L_values(d.hK, d.E)
+    model = CellRegMap(d.y, d.E, W=d.W, Ls=Ls)
+    assert model._structured_rotation()
+    pv_s, info_s = model.scan_interaction(d.G)
+    monkeypatch.setenv("CRM_KR", "0")
+    pv_f, info_f = model.scan_interaction(d.G)
+    monkeypatch.delenv("CRM_KR")
+    np.testing.assert_array_equal(info_s["rho1"], info_f["rho1"])
+    assert np.max(np.abs(np.log10(pv_s) - np.log10(pv_f))) <= 1e-8
+    # a plain list of the same blocks carries no declaration; an edited block makes the library refuse it; other contexts never declare
+    assert not CellRegMap(d.y, d.E, W=d.W, Ls=list(Ls))._structured_rotation()
+    edited = get_L_values(d.hK, d.E)
+    edited[1] = edited[1] * 1.0001
+    assert not CellRegMap(d.y, d.E, W=d.W, Ls=edited)._structured_rotation()
+    E_other = np.random.default_rng(0).standard_normal(d.E.shape)
+    assert not CellRegMap(d.y, E_other, W=d.W, Ls=get_L_values(d.hK, d.E))._structured_rotation()
+    pv_l, _ = CellRegMap(d.y, d.E, W=d.W, Ls=list(Ls)).scan_interaction(d.G)
+    np.testing.assert_array_equal(pv_l, pv_f)
+
+
 def test_structured_background_needs_matching_contexts(cuda_device):
     """E2 != E (background built from other contexts) or a basis that is not the declared product: the declaration is refused and
     the full basis is used."""
