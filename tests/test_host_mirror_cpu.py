@@ -67,3 +67,22 @@ def test_integer_genotypes_are_recognised_without_a_gpu():
     for dtype, narrow in ((np.int8, True), (np.uint8, True), (np.int16, True), (np.int32, True), (np.int64, False), (np.float32, False), (np.float64, False)):
         arr = np.zeros((3, 2), dtype=dtype)
         assert (arr.dtype.kind in "iub" and arr.dtype.itemsize <= 4) == narrow
+
+
+def test_get_L_values_remembers_its_factors():
+    """get_L_values returns the reference's list of blocks (values as before) and keeps (hK, E, V) with U S = E V beside it, so that a model
+    built from the list can declare the structure of the background; copies and slices are plain lists without it."""
+    rng = np.random.default_rng(12)
+    E = rng.standard_normal((90, 4))
+    hK = rng.standard_normal((90, 3))
+    Ls = api.get_L_values(hK, E)
+    ref = crm_port.get_L_values(hK, E)
+    assert isinstance(Ls, list) and len(Ls) == len(ref) == 4
+    for a, b in zip(Ls, ref):
+        np.testing.assert_allclose(np.abs(a), np.abs(b), rtol=0, atol=1e-13)
+    hK_f, E_f, V = Ls.factors
+    assert hK_f.shape == hK.shape and E_f.shape == E.shape and V.shape == (4, 4)
+    np.testing.assert_allclose(np.concatenate(Ls, 1), ((E @ V)[:, :, None] * hK[:, None, :]).reshape(90, 12), rtol=0, atol=1e-13)
+    assert not hasattr(Ls[:2], "factors") and not hasattr(list(Ls), "factors")
+    # wide context matrices (fewer cells than contexts) have no such map
+    assert api.get_L_values(rng.standard_normal((3, 2)), rng.standard_normal((3, 5))).factors is None
