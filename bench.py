@@ -464,7 +464,7 @@ def run_b200_arm(a):
                         "traffic_unit": "bytes per launch (ncu --set full of this command, profiles/)",
                         "kernel": ("cuBLASLt int8 GEMM + oz_combine_kernel" if os.environ.get("CRM_INT8_GEMM") == "lt" else
                                    "oz_mma_kernel (hand-written tcgen05.mma kind::i8 + TMA, TMEM accumulators, fused fp64 recombination)") +
-                                  ": digit planes of [Hx|Hx.E_j] against int8 dosages, the exact int8 split of the rotation",
+                                  ": digit planes of [Hx|Hx.E_j] (of its distinct columns when the background is structured, see contracted_columns) against int8 dosages, the exact int8 split of the rotation",
                         "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json" if peaks else "2 x 1.59 PFLOP/s fallback of B200_PROFILING.md") +
                                        " (int8 dense = 2 x bf16 dense on B200; both the measured bf16 figure and this kernel are limited by the "
                                        "power cap, so frac can exceed 1: against the nominal 4.5 POP/s the kernel reaches 0.73-0.76)",
